@@ -1,0 +1,80 @@
+// gsr_b200 — extern "C" surface declared in include/gsr_b200.h.
+#include "gsr_common.cuh"
+
+namespace gsr {
+int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,
+                 int32_t* radii, int flags, cudaStream_t st);
+int backward_impl(const gsr_frame* f, const gsr_workspace* ws, const int32_t* radii, const float* out_alpha, const float* dL_dc,
+                  const float* dL_dd, const float* dL_da, const gsr_grads* g, cudaStream_t st);
+int dist2_impl(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t dist2_bytes(int P);
+int profile_begin(int max_frames);
+int profile_end(float* ms, int* frames);
+
+// checkFrustum (rasterizer_impl.cu:54-66): in_frustum() only tests view-space z (auxiliary.h:154)
+__global__ void k_mark_visible(int P, const float* __restrict__ means3D, const float* __restrict__ view, uint8_t* __restrict__ present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float3 p = {means3D[3 * (size_t)idx], means3D[3 * (size_t)idx + 1], means3D[3 * (size_t)idx + 2]};
+    const float3 pv = xform4x3(p, view);
+    present[idx] = !(pv.z <= 0.2f);
+}
+}  // namespace gsr
+
+extern "C" {
+
+int gsr_abi_version(void) { return GSR_ABI_VERSION; }
+const char* gsr_last_error(void) { return gsr::last_error(); }
+
+size_t gsr_geom_bytes(int32_t P) { return gsr::GeomLayout((size_t)(P < 0 ? 0 : P)).total; }
+size_t gsr_binning_bytes(size_t capacity) { return gsr::BinLayout(capacity < 1 ? 1 : capacity).total; }
+size_t gsr_binning_capacity(size_t bytes) { return bytes / 12; }
+size_t gsr_image_bytes(int32_t W, int32_t H) { return gsr::ImageLayout(W < 1 ? 1 : W, H < 1 ? 1 : H).total; }
+
+int gsr_forward(const gsr_frame* frame, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,
+                int32_t* radii, int flags, void* stream) {
+    return gsr::forward_impl(frame, ws, out_color, out_depth, out_alpha, radii, flags, (cudaStream_t)stream);
+}
+
+int gsr_backward(const gsr_frame* frame, const gsr_workspace* ws, const int32_t* radii, const float* out_alpha,
+                 const float* dL_dout_color, const float* dL_dout_depth, const float* dL_dout_alpha, const gsr_grads* grads,
+                 void* stream) {
+    return gsr::backward_impl(frame, ws, radii, out_alpha, dL_dout_color, dL_dout_depth, dL_dout_alpha, grads, (cudaStream_t)stream);
+}
+
+int gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
+                     void* stream) {
+    (void)projmatrix;
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) { gsr::set_error("gsr_mark_visible: bad arguments"); return GSR_ERR_INVALID; }
+    if (P == 0) return GSR_OK;
+    gsr::k_mark_visible<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, means3D, viewmatrix, present);
+    return gsr::check_launch("gsr_mark_visible", false, (cudaStream_t)stream);
+}
+
+size_t gsr_dist2_bytes(int32_t P) { return gsr::dist2_bytes(P); }
+int gsr_dist2(int32_t P, const float* points, float* mean_dists, void* workspace, size_t workspace_bytes, void* stream) {
+    return gsr::dist2_impl(P, points, mean_dists, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gsr_profile_begin(int max_frames) { return gsr::profile_begin(max_frames); }
+int gsr_profile_end(float* ms_per_kernel, int* frames) { return gsr::profile_end(ms_per_kernel, frames); }
+
+int gsr_get_views(const gsr_workspace* ws, int32_t P, int32_t W, int32_t H, gsr_views* out) {
+    if (!ws || !out) { gsr::set_error("gsr_get_views: null argument"); return GSR_ERR_INVALID; }
+    const gsr::GeomLayout gl((size_t)P);
+    const gsr::ImageLayout il(W, H);
+    const gsr::BinLayout bl(ws->binning_bytes / 12);
+    const char* geo = (const char*)ws->geom; const char* img = (const char*)ws->image; const char* bin = (const char*)ws->binning;
+    out->records = (const float*)(geo + gl.records);
+    out->cov3D = (const float*)(geo + gl.cov3D);
+    out->clamped = (const uint8_t*)(geo + gl.clamped);
+    out->point_list = (const uint32_t*)(bin + bl.point_list);
+    out->sorted_keys = (const uint64_t*)(bin + bl.pairs);
+    out->ranges = (const uint32_t*)(img + il.ranges);
+    out->n_contrib = (const uint32_t*)(img + il.n_contrib);
+    out->tile_count = (const uint32_t*)(img + il.tile_count);
+    out->counters = (const gsr_counters*)(img + il.counters);
+    return GSR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+// gsr_b200 — shared device/host helpers.  sm_100a only.
+//
+// Arithmetic note (bit-exact tile/key indexing, SURVEY §7 "hard parts"): every quantity that feeds an
+// integer output of the reference (radii, tile rectangles, depth key bits) is computed with the same
+// fp32 expression TREES as the reference's preprocess (DGR/cuda_rasterizer/forward.cu:74-256 and the
+// GLM 3x3 product it uses, third_party/glm/glm/detail/type_mat3x3.inl:486-519), including the terms
+// that multiply structural zeros, so that nvcc's FMA contraction produces the same roundings.  The
+// memory access pattern, staging and parallel decomposition are ours.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/gsr_b200.h"
+
+#define GSR_TILE 16
+#define GSR_TILE_PIX 256
+#define GSR_FULL 0xffffffffu
+
+namespace gsr {
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- workspace layouts (pure functions of P / capacity / W,H) --------------------------------------
+struct GeomLayout {
+    size_t records, cov3D, clamped, total;
+    __host__ __device__ explicit GeomLayout(size_t P) {
+        size_t o = 0;
+        records = o; o = align_up(o + 48 * P, 256);
+        cov3D = o;   o = align_up(o + 24 * P, 256);
+        clamped = o; o = align_up(o + P, 256);
+        total = o + 256;
+    }
+};
+struct ImageLayout {
+    size_t counters, tile_count, tile_fill, ranges, n_contrib, total;
+    int gx, gy, tiles;
+    __host__ __device__ ImageLayout(int W, int H) {
+        gx = (W + GSR_TILE - 1) / GSR_TILE;
+        gy = (H + GSR_TILE - 1) / GSR_TILE;
+        tiles = gx * gy;
+        size_t o = 0;
+        counters = o;   o = align_up(o + sizeof(gsr_counters), 256);
+        tile_count = o; o = align_up(o + 4 * (size_t)tiles, 256);
+        tile_fill = o;  o = align_up(o + 4 * (size_t)tiles, 256);
+        ranges = o;     o = align_up(o + 8 * (size_t)tiles, 256);
+        n_contrib = o;  o = align_up(o + 4 * (size_t)W * H, 256);
+        total = o + 256;
+    }
+    // bytes [0, zero_bytes) are cleared at the start of every frame (counters + tile_count + tile_fill)
+    __host__ __device__ size_t zero_bytes() const { return ranges; }
+};
+struct BinLayout {
+    size_t pairs, point_list, total, capacity;
+    __host__ __device__ explicit BinLayout(size_t cap) {
+        capacity = cap;
+        pairs = 0;
+        point_list = 8 * cap;
+        total = 12 * cap;
+    }
+};
+
+// ---- camera block staged in shared memory ------------------------------------------------------------
+struct CamConsts {
+    float view[16];
+    float proj[16];
+    float campos[3];
+};
+
+// ---- minimal column-major 3x3 (m[col][row]) with the textbook product order --------------------------
+struct m3 {
+    float m[3][3];
+};
+__device__ __forceinline__ m3 m3_make(float a0, float a1, float a2, float b0, float b1, float b2, float c0, float c1, float c2) {
+    m3 r;
+    r.m[0][0] = a0; r.m[0][1] = a1; r.m[0][2] = a2;
+    r.m[1][0] = b0; r.m[1][1] = b1; r.m[1][2] = b2;
+    r.m[2][0] = c0; r.m[2][1] = c1; r.m[2][2] = c2;
+    return r;
+}
+__device__ __forceinline__ m3 m3_mul(const m3& A, const m3& B) {
+    m3 R;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            R.m[c][r] = A.m[0][r] * B.m[c][0] + A.m[1][r] * B.m[c][1] + A.m[2][r] * B.m[c][2];
+    return R;
+}
+__device__ __forceinline__ m3 m3_t(const m3& A) {
+    m3 R;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) R.m[c][r] = A.m[r][c];
+    return R;
+}
+
+// row-vector * row-major buffer (DGR/cuda_rasterizer/auxiliary.h:58-77)
+__device__ __forceinline__ float3 xform4x3(const float3& p, const float* m) {
+    float3 t = {m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12], m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]};
+    return t;
+}
+__device__ __forceinline__ float4 xform4x4(const float3& p, const float* m) {
+    float4 t = {m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12], m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14], m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15]};
+    return t;
+}
+
+// auxiliary.h:41-44 — double-precision literals make this a double expression
+__device__ __forceinline__ float ndc2pix(float v, int S) { return ((v + 1.0) * S - 1.0) * 0.5; }
+
+// auxiliary.h:46-56
+__device__ __forceinline__ void tile_rect(float px, float py, int r, int gx, int gy, int& x0, int& y0, int& x1, int& y1) {
+    x0 = min(gx, max(0, (int)((px - r) / GSR_TILE)));
+    y0 = min(gy, max(0, (int)((py - r) / GSR_TILE)));
+    x1 = min(gx, max(0, (int)((px + r + GSR_TILE - 1) / GSR_TILE)));
+    y1 = min(gy, max(0, (int)((py + r + GSR_TILE - 1) / GSR_TILE)));
+}
+
+// Run op(tile_index, a, b) once for every tile of this lane's rectangle, (a, b) being the lane's payload.
+// Rectangles of up to SMALL tiles are walked by their own lane; larger ones are walked by the whole warp,
+// 32 tiles at a time (payload broadcast by shuffle), so one huge splat does not serialise a warp.
+// Must be called by all 32 lanes (lanes with nothing to do pass an empty rectangle).
+template <int SMALL, typename Op>
+__device__ __forceinline__ void for_each_tile(int x0, int y0, int x1, int y1, int gx, uint32_t a, uint32_t b, Op op) {
+    const int w = x1 - x0;
+    const int cnt = w * (y1 - y0);
+    const int lane = threadIdx.x & 31;
+    if (cnt > 0 && cnt <= SMALL) {
+        for (int y = y0; y < y1; y++)
+            for (int x = x0; x < x1; x++) op(y * gx + x, a, b);
+    }
+    __syncwarp();
+    unsigned big = __ballot_sync(GSR_FULL, cnt > SMALL);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const int bx0 = __shfl_sync(GSR_FULL, x0, src), by0 = __shfl_sync(GSR_FULL, y0, src);
+        const int bw = __shfl_sync(GSR_FULL, w, src), bn = __shfl_sync(GSR_FULL, cnt, src);
+        const uint32_t ba = __shfl_sync(GSR_FULL, a, src), bb = __shfl_sync(GSR_FULL, b, src);
+        for (int t = lane; t < bn; t += 32) op((by0 + t / bw) * gx + bx0 + t % bw, ba, bb);
+        __syncwarp();
+    }
+}
+
+// SH basis constants (auxiliary.h:22-39)
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+constexpr float SH_C2_0 = 1.0925484305920792f, SH_C2_1 = -1.0925484305920792f, SH_C2_2 = 0.31539156525252005f,
+                           SH_C2_3 = -1.0925484305920792f, SH_C2_4 = 0.5462742152960396f;
+constexpr float SH_C3_0 = -0.5900435899266435f, SH_C3_1 = 2.890611442640554f, SH_C3_2 = -0.4570457994644658f,
+                           SH_C3_3 = 0.3731763325901154f, SH_C3_4 = -0.4570457994644658f, SH_C3_5 = 1.445305721320277f,
+                           SH_C3_6 = -0.5900435899266435f;
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+int check_launch(const char* what, bool debug, cudaStream_t stream);
+
+}  // namespace gsr

@@ -1,0 +1,761 @@
+// gsr_b200 forward pass: preprocess -> tile histogram/scan -> instance emission -> per-tile depth sort -> blend.
+//
+// Replaces CudaRasterizer::Rasterizer::forward (DGR/cuda_rasterizer/rasterizer_impl.cu:197-339) and the
+// kernels it drives (forward.cu:155-256 preprocessCUDA, rasterizer_impl.cu:70-138 duplicateWithKeys /
+// identifyTileRanges, CUB InclusiveSum + DeviceRadixSort, forward.cu:261-378 renderCUDA).
+//
+// Pipeline differences (results are identical):
+//   * one 48-byte record per visible Gaussian {x,y,conic.a,conic.b | conic.c,opacity,depth,tau | r,g,b,-}
+//     replaces the reference's five SoA arrays, so the blend gathers 3 aligned float4 per instance;
+//   * SH coefficients are staged into shared memory with coalesced 16-byte cp.async by each warp, only for
+//     the Gaussians that survived culling, and read back conflict-free (row stride 13 float4);
+//   * binning is a two-level sort: per-tile histogram (atomics, in preprocess) -> exclusive scan over the
+//     tiles (gives the ranges and R on the device, no host round trip) -> scatter of (depth bits, id) pairs
+//     into the tile's bucket -> one CTA per tile sorts its bucket by (depth bits, id) in shared memory.
+//     The resulting order is exactly the reference's stable radix sort of (tile | depth) keys, because the
+//     reference emits every (tile, Gaussian) pair once in ascending Gaussian id (rasterizer_impl.cu:98-108);
+//   * the blend kernel culls splats per 8x4-pixel warp footprint (one splat per lane, ballot) before the
+//     per-pixel evaluation, which itself uses the reference's fp32 expressions.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "gsr_common.cuh"
+
+namespace gsr {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+int check_launch(const char* what, bool debug, cudaStream_t stream) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && debug) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return GSR_ERR_CUDA;
+    }
+    return GSR_OK;
+}
+
+// =====================================================================================================
+// Kernel 1: preprocess
+// =====================================================================================================
+struct PreParams {
+    int P, D, M, W, H, gx, gy;
+    float scale_modifier, tanfovx, tanfovy, focal_x, focal_y;
+    int prefiltered, for_backward, rot_vec;
+    const float *means3D, *shs, *colors_precomp, *opacities, *scales, *rotations, *cov3D_precomp, *view, *proj, *campos;
+    float4* records;
+    float* cov3D;
+    uint8_t* clamped;
+    int* radii;
+    uint32_t* tile_count;
+    gsr_counters* counters;
+};
+
+constexpr int PRE_THREADS = 128;
+
+__host__ __device__ constexpr int sh_nf(int deg) { return 3 * (deg + 1) * (deg + 1); }
+__host__ __device__ constexpr int sh_stride(int deg, bool vec) {
+    // vec: rows of nv float4, padded so that (stride/4) is odd -> conflict-free LDS.128 across 8 lanes
+    // scalar: odd number of words -> conflict-free LDS.32
+    return vec ? (((sh_nf(deg) + 3) / 4) % 2 == 0 ? ((sh_nf(deg) + 3) / 4 + 1) * 4 : ((sh_nf(deg) + 3) / 4) * 4)
+               : (sh_nf(deg) | 1);
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// SH -> RGB for one Gaussian from its staged row (forward.cu:20-71).  Like cov3d_ref_rounding below, the
+// roundings are pinned to the instruction sequence nvcc 12.9 emits for the reference (SASS of oracle/_ref):
+// every coefficient C*poly(dir) is built from separate multiplies (only 3xx-yy, 4zz-xx, 2zz-3xx-3yy, xx-3yy use
+// an FMA), and each term is accumulated with one FMA, in the reference's order.
+template <int DEG>
+__device__ __forceinline__ void sh_eval(const float* sh, float3 pos, const float* campos, float* rgb, unsigned& clamp_bits) {
+    const float dx = __fsub_rn(pos.x, campos[0]), dy = __fsub_rn(pos.y, campos[1]), dz = __fsub_rn(pos.z, campos[2]);
+    const float len = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))));
+    const float x = __fdiv_rn(dx, len), y = __fdiv_rn(dy, len), z = __fdiv_rn(dz, len);
+    float k[16];
+    k[0] = SH_C0;
+    if (DEG > 0) {
+        k[1] = -__fmul_rn(y, SH_C1);
+        k[2] = __fmul_rn(z, SH_C1);
+        k[3] = -__fmul_rn(x, SH_C1);
+    }
+    if (DEG > 1) {
+        const float xy = __fmul_rn(y, x), yz = __fmul_rn(z, y), zz = __fmul_rn(z, z), xx = __fmul_rn(x, x), yy = __fmul_rn(y, y);
+        const float xz = __fmul_rn(z, x), zz2 = __fadd_rn(zz, zz), xmy = __fsub_rn(xx, yy);
+        k[4] = __fmul_rn(xy, SH_C2_0);
+        k[5] = __fmul_rn(yz, SH_C2_1);
+        k[6] = __fmul_rn(__fsub_rn(__fsub_rn(zz2, xx), yy), SH_C2_2);
+        k[7] = __fmul_rn(xz, SH_C2_3);
+        k[8] = __fmul_rn(xmy, SH_C2_4);
+        if (DEG > 2) {
+            const float f = __fsub_rn(__fmaf_rn(zz, 4.0f, -xx), yy);  // 4zz - xx - yy
+            k[9] = __fmul_rn(__fmul_rn(y, SH_C3_0), __fmaf_rn(xx, 3.0f, -yy));
+            k[10] = __fmul_rn(__fmul_rn(xy, SH_C3_1), z);
+            k[11] = __fmul_rn(__fmul_rn(y, SH_C3_2), f);
+            k[12] = __fmul_rn(__fmul_rn(z, SH_C3_3), __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2)));
+            k[13] = __fmul_rn(__fmul_rn(x, SH_C3_4), f);
+            k[14] = __fmul_rn(__fmul_rn(z, SH_C3_5), xmy);
+            k[15] = __fmul_rn(__fmul_rn(x, SH_C3_6), __fmaf_rn(yy, -3.0f, xx));
+        }
+    }
+    constexpr int NC = (DEG + 1) * (DEG + 1);
+    clamp_bits = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float res = __fmul_rn(sh[c], k[0]);
+#pragma unroll
+        for (int i = 1; i < NC; i++) res = __fmaf_rn(k[i], sh[i * 3 + c], res);
+        const float v = __fadd_rn(res, 0.5f);
+        const bool neg = v < 0.f;  // == (res < -0.5f)
+        if (neg) clamp_bits |= 1u << c;
+        rgb[c] = neg ? 0.0f : v;
+    }
+}
+
+// 3D covariance from scale / rotation (forward.cu:118-152: Sigma = (S R)^T (S R), quaternion not normalised).
+// The roundings (which product of each sum is fused into an FMA, which terms multiply the structural zeros of
+// S) are pinned with intrinsics to what nvcc 12.9 emits for the reference's GLM expression on sm_100a
+// (read from the SASS of oracle/_ref), because the compiler's contraction choices depend on common
+// sub-expression sharing and cannot be reproduced by writing "the same" C++ expression in another kernel.
+// A 1-ulp difference here changes conic -> alpha -> the T < 1e-4 termination of a pixel now and then.
+__device__ __forceinline__ void cov3d_ref_rounding(float sx, float sy, float sz, float mod, float4 q, float* c3) {
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    const float xz = __fmul_rn(x, z), rx = __fmul_rn(r, x);
+    const float A02 = __fmaf_rn(r, y, xz), A20 = __fmaf_rn(-r, y, xz);
+    const float rz = __fmul_rn(r, z);
+    const float A12 = __fmaf_rn(y, z, -rx), A21 = __fmaf_rn(y, z, rx);
+    const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+    const float A01 = __fmaf_rn(x, y, -rz), A10 = __fmaf_rn(x, y, rz);
+    const float B22 = __fmaf_rn(x, x, yy), B00 = __fadd_rn(yy, zz), B11 = __fmaf_rn(x, x, zz);
+    const float s0 = __fmul_rn(mod, sx), s1 = __fmul_rn(mod, sy), s2 = __fmul_rn(mod, sz);
+    // rotation matrix, R<c><r> = column c, row r
+    const float R00 = __fsub_rn(1.f, __fadd_rn(B00, B00)), R01 = __fadd_rn(A01, A01), R02 = __fadd_rn(A02, A02);
+    const float R10 = __fadd_rn(A10, A10), R11 = __fsub_rn(1.f, __fadd_rn(B11, B11)), R12 = __fadd_rn(A12, A12);
+    const float R20 = __fadd_rn(A20, A20), R21 = __fadd_rn(A21, A21), R22 = __fsub_rn(1.f, __fadd_rn(B22, B22));
+    // M = S * R with S = diag(s0, s1, s2): M<c><r> = S[0][r] R[c][0] + S[1][r] R[c][1] + S[2][r] R[c][2]
+    const float z0 = __fmul_rn(0.f, R21), z00 = __fmul_rn(0.f, R00), z11 = __fmul_rn(0.f, R11);
+    const float uM22 = __fmaf_rn(0.f, R20, z0), uM20 = __fmaf_rn(s0, R20, z0), uM21 = __fmaf_rn(0.f, R20, __fmul_rn(s1, R21));
+    const float uM01 = __fmaf_rn(s1, R01, z00), uM02 = __fmaf_rn(0.f, R01, z00), uM00 = __fmaf_rn(0.f, R01, __fmul_rn(s0, R00));
+    const float uM10 = __fmaf_rn(s0, R10, z11), uM11 = __fmaf_rn(0.f, R10, __fmul_rn(s1, R11)), uM12 = __fmaf_rn(0.f, R10, z11);
+    const float M20 = __fmaf_rn(0.f, R22, uM20), M21 = __fmaf_rn(0.f, R22, uM21), M22 = __fmaf_rn(s2, R22, uM22);
+    const float M00 = __fmaf_rn(0.f, R02, uM00), M01 = __fmaf_rn(0.f, R02, uM01), M02 = __fmaf_rn(s2, R02, uM02);
+    const float M10 = __fmaf_rn(0.f, R12, uM10), M11 = __fmaf_rn(0.f, R12, uM11), M12 = __fmaf_rn(s2, R12, uM12);
+    // Sigma = M^T M, upper triangle
+    c3[0] = __fmaf_rn(M02, M02, __fmaf_rn(M00, M00, __fmul_rn(M01, M01)));
+    c3[1] = __fmaf_rn(M02, M12, __fmaf_rn(M00, M10, __fmul_rn(M01, M11)));
+    c3[2] = __fmaf_rn(M02, M22, __fmaf_rn(M00, M20, __fmul_rn(M01, M21)));
+    c3[3] = __fmaf_rn(M12, M12, __fmaf_rn(M10, M10, __fmul_rn(M11, M11)));
+    c3[4] = __fmaf_rn(M12, M22, __fmaf_rn(M10, M20, __fmul_rn(M11, M21)));
+    c3[5] = __fmaf_rn(M22, M22, __fmaf_rn(M20, M20, __fmul_rn(M21, M21)));
+}
+
+// DEG = -1: colours are precomputed.  VEC: SH rows are 16-byte aligned (M % 4 == 0) -> cp.async float4 staging.
+template <int DEG, bool VEC>
+__global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
+    constexpr int DG = DEG < 0 ? 0 : DEG;
+    constexpr int NF = sh_nf(DG);
+    constexpr int STRIDE = sh_stride(DG, VEC);
+    __shared__ CamConsts cam;
+    __shared__ __align__(16) float stage[DEG < 0 ? 4 : PRE_THREADS * STRIDE];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 16) cam.view[tid] = p.view[tid];
+    else if (tid < 32) cam.proj[tid - 16] = p.proj[tid - 16];
+    else if (tid < 35) cam.campos[tid - 32] = p.campos[tid - 32];
+    __syncthreads();
+
+    const int idx = blockIdx.x * PRE_THREADS + tid;
+    const bool valid = idx < p.P;
+    bool vis = false;
+    int radius = 0, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    float3 mean = {0, 0, 0};
+    float px = 0, py = 0, depth = 0, con_a = 0, con_b = 0, con_c = 0;
+    float c3[6] = {0, 0, 0, 0, 0, 0};
+
+    if (valid) {
+        mean = make_float3(p.means3D[3 * (size_t)idx], p.means3D[3 * (size_t)idx + 1], p.means3D[3 * (size_t)idx + 2]);
+        // near cull (auxiliary.h:139-164): only view-space z is tested
+        float4 p_hom = xform4x4(mean, cam.proj);
+        float p_w = 1.0f / (p_hom.w + 0.0000001f);
+        float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
+        float3 p_view = xform4x3(mean, cam.view);
+        if (p_view.z <= 0.2f) {
+            if (p.prefiltered) p.counters->trapped = 1;
+        } else {
+            // 3D covariance (forward.cu:118-152)
+            if (p.cov3D_precomp != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) c3[k] = p.cov3D_precomp[6 * (size_t)idx + k];
+            } else {
+                const float sx = p.scales[3 * (size_t)idx], sy = p.scales[3 * (size_t)idx + 1], sz = p.scales[3 * (size_t)idx + 2];
+                float4 q;
+                if (p.rot_vec) q = reinterpret_cast<const float4*>(p.rotations)[idx];
+                else q = make_float4(p.rotations[4 * (size_t)idx], p.rotations[4 * (size_t)idx + 1], p.rotations[4 * (size_t)idx + 2], p.rotations[4 * (size_t)idx + 3]);
+                cov3d_ref_rounding(sx, sy, sz, p.scale_modifier, q, c3);
+            }
+            // EWA 2D covariance (forward.cu:74-113)
+            float3 t = xform4x3(mean, cam.view);
+            const float limx = 1.3f * p.tanfovx, limy = 1.3f * p.tanfovy;
+            const float txtz = t.x / t.z, tytz = t.y / t.z;
+            t.x = min(limx, max(-limx, txtz)) * t.z;
+            t.y = min(limy, max(-limy, tytz)) * t.z;
+            m3 J = m3_make(p.focal_x / t.z, 0.0f, -(p.focal_x * t.x) / (t.z * t.z),
+                           0.0f, p.focal_y / t.z, -(p.focal_y * t.y) / (t.z * t.z),
+                           0, 0, 0);
+            m3 Wm = m3_make(cam.view[0], cam.view[4], cam.view[8], cam.view[1], cam.view[5], cam.view[9],
+                            cam.view[2], cam.view[6], cam.view[10]);
+            m3 T = m3_mul(Wm, J);
+            m3 Vrk = m3_make(c3[0], c3[1], c3[2], c3[1], c3[3], c3[4], c3[2], c3[4], c3[5]);
+            m3 cov = m3_mul(m3_mul(m3_t(T), m3_t(Vrk)), T);
+            cov.m[0][0] += 0.3f;
+            cov.m[1][1] += 0.3f;
+            const float cx = cov.m[0][0], cy = cov.m[0][1], cz = cov.m[1][1];
+            // conic, radius, tile rectangle (forward.cu:217-237)
+            float det = (cx * cz - cy * cy);
+            if (det != 0.0f) {
+                float det_inv = 1.f / det;
+                con_a = cz * det_inv; con_b = -cy * det_inv; con_c = cx * det_inv;
+                float mid = 0.5f * (cx + cz);
+                float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+                float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+                float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+                px = ndc2pix(p_proj.x, p.W);
+                py = ndc2pix(p_proj.y, p.H);
+                tile_rect(px, py, (int)my_radius, p.gx, p.gy, x0, y0, x1, y1);
+                if ((x1 - x0) * (y1 - y0) != 0) {
+                    vis = true;
+                    radius = (int)my_radius;
+                    depth = p_view.z;
+                }
+            }
+        }
+    }
+    if (!vis) { x0 = y0 = x1 = y1 = 0; }
+
+    // per-tile histogram: one RED per (Gaussian, tile) instance
+    {
+        uint32_t* tc = p.tile_count;
+        for_each_tile<8>(x0, y0, x1, y1, p.gx, 0u, 0u, [&](int tile, uint32_t, uint32_t) { atomicAdd(&tc[tile], 1u); });
+    }
+
+    // colour
+    float rgb[3] = {0, 0, 0};
+    unsigned clamp_bits = 0;
+    if constexpr (DEG < 0) {
+        if (vis) {
+            rgb[0] = p.colors_precomp[3 * (size_t)idx];
+            rgb[1] = p.colors_precomp[3 * (size_t)idx + 1];
+            rgb[2] = p.colors_precomp[3 * (size_t)idx + 2];
+        }
+    } else {
+        // Stage the SH rows of this warp's 32 Gaussians: flat work list (Gaussian, part), consecutive lanes
+        // fetch consecutive 16-byte (or 4-byte) parts -> coalesced; rows of culled Gaussians are skipped.
+        const unsigned vismask = __ballot_sync(GSR_FULL, vis);
+        float* wstage = stage + warp * 32 * STRIDE;
+        const size_t gbase = (size_t)(blockIdx.x * PRE_THREADS + warp * 32);
+        const size_t row_floats = (size_t)p.M * 3;
+        if (VEC) {
+            constexpr int NV = (NF + 3) / 4;
+#pragma unroll
+            for (int it = 0; it < NV; it++) {
+                const int item = it * 32 + lane;
+                const int gl = item / NV, part = item - gl * NV;
+                if ((vismask >> gl) & 1u) cp_async16(wstage + gl * STRIDE + part * 4, p.shs + (gbase + gl) * row_floats + part * 4);
+            }
+            cp_async_wait_all();
+        } else {
+#pragma unroll 4
+            for (int it = 0; it < NF; it++) {
+                const int item = it * 32 + lane;
+                const int gl = item / NF, part = item - gl * NF;
+                if ((vismask >> gl) & 1u) wstage[gl * STRIDE + part] = p.shs[(gbase + gl) * row_floats + part];
+            }
+        }
+        __syncwarp();
+        if (vis) sh_eval<DG>(wstage + lane * STRIDE, mean, cam.campos, rgb, clamp_bits);
+    }
+
+    if (valid) {
+        p.radii[idx] = radius;
+        if (vis) {
+            const float opacity = p.opacities[idx];
+            // tau = ln(255 * opacity): a pixel can only be touched where power >= -tau (alpha >= 1/255)
+            const float tau = __logf(255.0f * opacity);
+            float4* rec = p.records + 3 * (size_t)idx;
+            rec[0] = make_float4(px, py, con_a, con_b);
+            rec[1] = make_float4(con_c, opacity, depth, tau);
+            rec[2] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+            if (p.for_backward) {
+                if (p.cov3D_precomp == nullptr) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) p.cov3D[6 * (size_t)idx + k] = c3[k];
+                }
+                p.clamped[idx] = (uint8_t)clamp_bits;
+            }
+        }
+    }
+    const int nvis = __syncthreads_count(vis);
+    if (tid == 0 && nvis) atomicAdd(&p.counters->num_visible, (uint32_t)nvis);
+}
+
+// =====================================================================================================
+// Kernel 2: exclusive scan over the per-tile counts -> ranges, R, overflow flag (single CTA)
+// =====================================================================================================
+__global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
+                                                    gsr_counters* counters, int tiles, uint32_t capacity) {
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t warp_max[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (tiles + 1023) / 1024;
+    const int b = tid * per, e = min(tiles, b + per);
+    uint32_t local = 0, lmax = 0;
+    for (int t = b; t < e; t++) {
+        uint32_t c = tile_count[t];
+        local += c;
+        lmax = max(lmax, c);
+    }
+    uint32_t incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(GSR_FULL, incl, o);
+        if (lane >= o) incl += v;
+        lmax = max(lmax, __shfl_xor_sync(GSR_FULL, lmax, o));
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    if (lane == 0) warp_max[warp] = lmax;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t s = warp_sum[lane], m = warp_max[lane];
+        uint32_t si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(GSR_FULL, si, o);
+            if (lane >= o) si += v;
+            m = max(m, __shfl_xor_sync(GSR_FULL, m, o));
+        }
+        warp_sum[lane] = si - s;  // exclusive
+        if (lane == 31) {
+            counters->num_rendered = si;
+            counters->overflow = si > capacity ? 1u : 0u;
+        }
+        if (lane == 0) counters->max_tile = m;
+    }
+    __syncthreads();
+    uint32_t start = warp_sum[warp] + (incl - local);
+    for (int t = b; t < e; t++) {
+        uint32_t c = tile_count[t];
+        ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
+        start += c;
+    }
+}
+
+
+// =====================================================================================================
+// Kernel 3: scatter one (depth bits, Gaussian id) pair per (Gaussian, tile) instance into the tile's bucket
+// (the work of duplicateWithKeys, rasterizer_impl.cu:70-111; the tile id is implicit in the bucket)
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_emit(int P, int gx, int gy, const int* __restrict__ radii,
+                                              const float4* __restrict__ records, const uint2* __restrict__ ranges,
+                                              uint32_t* __restrict__ tile_fill, uint2* __restrict__ pairs,
+                                              const gsr_counters* __restrict__ counters) {
+    if (counters->overflow) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    uint32_t dbits = 0;
+    if (idx < P) {
+        const int r = radii[idx];
+        if (r > 0) {
+            const float4 r0 = records[3 * (size_t)idx];
+            dbits = __float_as_uint(records[3 * (size_t)idx + 1].z);
+            tile_rect(r0.x, r0.y, r, gx, gy, x0, y0, x1, y1);
+        }
+    }
+    for_each_tile<8>(x0, y0, x1, y1, gx, (uint32_t)idx, dbits, [&](int tile, uint32_t id, uint32_t d) {
+        const uint32_t pos = ranges[tile].x + atomicAdd(&tile_fill[tile], 1u);
+        pairs[pos] = make_uint2(id, d);  // little endian: u64 = (depth bits << 32) | id
+    });
+}
+
+// =====================================================================================================
+// Kernel 4: per-tile sort of the bucket by (depth bits, id) -> point_list
+// Normalised bitonic network (all compare-exchanges ascending), valid for any n by skipping partners >= n.
+// =====================================================================================================
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_CAP = 4096;  // u64 entries in shared memory (32 KB)
+
+template <typename T>
+__device__ __forceinline__ void cmpx(T* a, uint32_t i, uint32_t l) {
+    const unsigned long long x = a[i], y = a[l];
+    if (x > y) { a[i] = y; a[l] = x; }
+}
+// one "flip" step of block size k over the first N slots (N power of two), entries >= n are virtual +inf
+__device__ __forceinline__ void step_flip(unsigned long long* a, uint32_t n, uint32_t N, uint32_t k) {
+    const uint32_t half = k >> 1;
+    for (uint32_t t = threadIdx.x; t < (N >> 1); t += SORT_THREADS) {
+        const uint32_t i = ((t & ~(half - 1)) << 1) | (t & (half - 1));
+        const uint32_t l = i ^ (k - 1);
+        if (l < n) cmpx(a, i, l);
+    }
+}
+__device__ __forceinline__ void step_j(unsigned long long* a, uint32_t n, uint32_t N, uint32_t j) {
+    for (uint32_t t = threadIdx.x; t < (N >> 1); t += SORT_THREADS) {
+        const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const uint32_t l = i + j;
+        if (l < n) cmpx(a, i, l);
+    }
+}
+__device__ __forceinline__ uint32_t next_pow2(uint32_t n) { return n <= 1 ? 1u : 1u << (32 - __clz(n - 1)); }
+
+// full sort of a[0..n) (n <= SORT_CAP) in shared memory
+__device__ void sort_smem(unsigned long long* s, uint32_t n) {
+    const uint32_t N = next_pow2(n);
+    for (uint32_t k = 2; k <= N; k <<= 1) {
+        step_flip(s, n, N, k);
+        __syncthreads();
+        for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+            step_j(s, n, N, j);
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __restrict__ ranges, unsigned long long* __restrict__ pairs,
+                                                             uint32_t* __restrict__ point_list,
+                                                             const gsr_counters* __restrict__ counters, int keep_pairs) {
+    if (counters->overflow) return;
+    __shared__ unsigned long long s[SORT_CAP];
+    const uint2 rg = ranges[blockIdx.x];
+    const uint32_t n = rg.y - rg.x;
+    if (n == 0) return;
+    unsigned long long* g = pairs + rg.x;
+    uint32_t* out = point_list + rg.x;
+    const uint32_t tid = threadIdx.x;
+    if (n <= SORT_CAP) {
+        for (uint32_t i = tid; i < n; i += SORT_THREADS) s[i] = g[i];
+        __syncthreads();
+        sort_smem(s, n);
+        for (uint32_t i = tid; i < n; i += SORT_THREADS) {
+            out[i] = (uint32_t)s[i];
+            if (keep_pairs) g[i] = s[i];
+        }
+        return;
+    }
+    // ---- large tile: chunks sorted in shared memory, cross-chunk steps in global (L2) memory ----
+    const uint32_t N = next_pow2(n);
+    for (uint32_t c0 = 0; c0 < n; c0 += SORT_CAP) {
+        const uint32_t m = min((uint32_t)SORT_CAP, n - c0);
+        for (uint32_t i = tid; i < m; i += SORT_THREADS) s[i] = g[c0 + i];
+        __syncthreads();
+        sort_smem(s, m);
+        for (uint32_t i = tid; i < m; i += SORT_THREADS) g[c0 + i] = s[i];
+        __syncthreads();
+    }
+    for (uint32_t k = 2 * SORT_CAP; k <= N; k <<= 1) {
+        step_flip(g, n, N, k);
+        __syncthreads();
+        uint32_t j = k >> 2;
+        for (; j >= SORT_CAP; j >>= 1) {
+            step_j(g, n, N, j);
+            __syncthreads();
+        }
+        for (uint32_t c0 = 0; c0 < n; c0 += SORT_CAP) {
+            const uint32_t m = min((uint32_t)SORT_CAP, n - c0);
+            for (uint32_t i = tid; i < m; i += SORT_THREADS) s[i] = g[c0 + i];
+            __syncthreads();
+            for (uint32_t jj = SORT_CAP >> 1; jj > 0; jj >>= 1) {
+                step_j(s, m, SORT_CAP, jj);
+                __syncthreads();
+            }
+            for (uint32_t i = tid; i < m; i += SORT_THREADS) g[c0 + i] = s[i];
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = tid; i < n; i += SORT_THREADS) out[i] = (uint32_t)g[i];
+}
+
+// =====================================================================================================
+// Kernel 5: per-tile front-to-back alpha blend (forward.cu:261-378)
+// One CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel footprint.
+// =====================================================================================================
+constexpr int BLEND_THREADS = 256;
+
+// Conservative test: can the splat reach alpha >= 1/255 at any pixel centre of [X0,X1]x[Y0,Y1]?
+// The minimum of q(u,v) = a u^2 + 2 b u v + c v^2 over the box is on a face between the box and the
+// splat centre; power = -q/2 must be >= -tau.  The margin covers the rounding of both this bound and
+// the reference's own evaluation of `power` (a few ulp of the largest term), so a "false" is always a
+// pixel the reference skips too; a "true" only costs the exact per-pixel test.
+__device__ __forceinline__ bool splat_may_touch(const float4 r0, const float4 r1, float X0, float Y0, float X1, float Y1) {
+    const float a = r0.z, b = r0.w, c = r1.x, tau = r1.w;
+    const float u0 = r0.x - X1, u1 = r0.x - X0, v0 = r0.y - Y1, v1 = r0.y - Y0;
+    const float uc = fminf(fmaxf(0.f, u0), u1), vc = fminf(fmaxf(0.f, v0), v1);
+    if (!(a > 0.f && c > 0.f)) return true;  // degenerate conic: no culling
+    float qmin = 0.f;
+    if (uc != 0.f || vc != 0.f) {
+        qmin = 3.0e38f;
+        if (uc != 0.f) {
+            const float vs = fminf(fmaxf(-b * uc / c, v0), v1);
+            qmin = fminf(qmin, a * uc * uc + 2.f * b * uc * vs + c * vs * vs);
+        }
+        if (vc != 0.f) {
+            const float us = fminf(fmaxf(-b * vc / a, u0), u1);
+            qmin = fminf(qmin, a * us * us + 2.f * b * us * vc + c * vc * vc);
+        }
+    }
+    const float um = fmaxf(fabsf(u0), fabsf(u1)), vm = fmaxf(fabsf(v0), fabsf(v1));
+    const float mag = a * um * um + c * vm * vm + 2.f * fabsf(b) * um * vm;
+    return !(0.5f * qmin > tau + 1.0e-3f + 4.0e-6f * mag);
+}
+
+__global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                                                         const float4* __restrict__ records, int W, int H, int gx,
+                                                         const float* __restrict__ bg, float* __restrict__ out_color,
+                                                         float* __restrict__ out_depth, float* __restrict__ out_alpha,
+                                                         uint32_t* __restrict__ n_contrib,
+                                                         const gsr_counters* __restrict__ counters) {
+    __shared__ float4 sA[BLEND_THREADS], sB[BLEND_THREADS], sC[BLEND_THREADS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.y * gx + blockIdx.x;
+    const int X0 = blockIdx.x * GSR_TILE + (warp & 1) * 8, Y0 = blockIdx.y * GSR_TILE + (warp >> 1) * 4;
+    const int pxi = X0 + (lane & 7), pyi = Y0 + (lane >> 3);
+    const bool inside = pxi < W && pyi < H;
+    const float pixx = (float)pxi, pixy = (float)pyi;
+    const float fX0 = (float)X0, fY0 = (float)Y0, fX1 = (float)(X0 + 7), fY1 = (float)(Y0 + 3);
+
+    uint2 range = ranges[tile];
+    if (counters->overflow) range = make_uint2(0u, 0u);
+    const int n = (int)(range.y - range.x);
+    const int nb = (n + BLEND_THREADS - 1) / BLEND_THREADS;
+
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
+    uint32_t last = 0;
+    bool done = !inside;
+
+    // software pipeline: records of batch b and the list entry of batch b+1 are in registers
+    float4 ra = make_float4(0, 0, 0, 0), rb = ra, rc = ra;
+    uint32_t id_next = 0;
+    if (tid < n) {
+        const uint32_t id = point_list[range.x + tid];
+        const float4* r = records + 3 * (size_t)id;
+        ra = r[0]; rb = r[1]; rc = r[2];
+    }
+    if (BLEND_THREADS + tid < n) id_next = point_list[range.x + BLEND_THREADS + tid];
+
+    for (int b = 0; b < nb; b++) {
+        // whole tile finished? (also the barrier that frees the staging buffers)
+        if (__syncthreads_count(done) == BLEND_THREADS) break;
+        const int cnt = min(BLEND_THREADS, n - b * BLEND_THREADS);
+        if (tid < cnt) { sA[tid] = ra; sB[tid] = rb; sC[tid] = rc; }
+        __syncthreads();
+        {
+            const int nxt = (b + 1) * BLEND_THREADS + tid;
+            if (nxt < n) {
+                const float4* r = records + 3 * (size_t)id_next;
+                ra = r[0]; rb = r[1]; rc = r[2];
+            }
+            if (nxt + BLEND_THREADS < n) id_next = point_list[range.x + nxt + BLEND_THREADS];
+        }
+        if (__all_sync(GSR_FULL, done)) continue;
+        for (int base = 0; base < cnt; base += 32) {
+            const int s = base + lane;
+            const bool keep = s < cnt && splat_may_touch(sA[s], sB[s], fX0, fY0, fX1, fY1);
+            unsigned mask = __ballot_sync(GSR_FULL, keep);
+            while (mask) {
+                const int j = base + __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (!done) {
+                    const float4 A = sA[j], B = sB[j];
+                    const float2 d = {A.x - pixx, A.y - pixy};
+                    const float power = -0.5f * (A.z * d.x * d.x + B.x * d.y * d.y) - A.w * d.x * d.y;
+                    if (power > 0.0f) continue;
+                    const float alpha = min(0.99f, B.y * exp(power));
+                    if (alpha < 1.0f / 255.0f) continue;
+                    const float test_T = T * (1 - alpha);
+                    if (test_T < 0.0001f) {
+                        done = true;
+                        continue;
+                    }
+                    const float4 Cc = sC[j];
+                    C0 += Cc.x * alpha * T;
+                    C1 += Cc.y * alpha * T;
+                    C2 += Cc.z * alpha * T;
+                    Dp += B.z * alpha * T;
+                    T = test_T;
+                    last = (uint32_t)(b * BLEND_THREADS + j + 1);
+                }
+            }
+            if (__all_sync(GSR_FULL, done)) break;
+        }
+    }
+    if (inside) {
+        const size_t pid = (size_t)W * pyi + pxi;
+        const size_t HW = (size_t)H * W;
+        out_alpha[pid] = 1 - T;
+        if (n_contrib) n_contrib[pid] = last;
+        out_color[pid] = C0 + T * bg[0];
+        out_color[HW + pid] = C1 + T * bg[1];
+        out_color[2 * HW + pid] = C2 + T * bg[2];
+        out_depth[pid] = Dp;
+    }
+}
+
+// =====================================================================================================
+// optional per-kernel timing (bench.py roofline): CUDA events recorded around each forward kernel on the
+// launching stream; no effect unless gsr_profile_begin() was called.  Not thread safe (one profiled stream).
+// =====================================================================================================
+struct ProfileState {
+    bool on = false;
+    int max_frames = 0, frames = 0;
+    cudaEvent_t* ev = nullptr;  // 6 per frame
+    int allocated = 0;
+};
+static ProfileState g_prof;
+static inline void prof_mark(int k, cudaStream_t st) {
+    if (g_prof.on && g_prof.frames < g_prof.max_frames) cudaEventRecord(g_prof.ev[g_prof.frames * 6 + k], st);
+}
+int profile_begin(int max_frames) {
+    if (max_frames <= 0) { set_error("gsr_profile_begin: max_frames must be > 0"); return GSR_ERR_INVALID; }
+    if (g_prof.allocated < max_frames * 6) {
+        cudaEvent_t* ne = new cudaEvent_t[max_frames * 6];
+        for (int i = 0; i < max_frames * 6; i++) {
+            if (i < g_prof.allocated) ne[i] = g_prof.ev[i];
+            else if (cudaEventCreate(&ne[i]) != cudaSuccess) { set_error("gsr_profile_begin: cudaEventCreate failed"); return GSR_ERR_CUDA; }
+        }
+        delete[] g_prof.ev;
+        g_prof.ev = ne;
+        g_prof.allocated = max_frames * 6;
+    }
+    g_prof.max_frames = max_frames;
+    g_prof.frames = 0;
+    g_prof.on = true;
+    return GSR_OK;
+}
+int profile_end(float* ms, int* frames) {
+    g_prof.on = false;
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (int f = 0; f < g_prof.frames; f++) {
+        if (cudaEventSynchronize(g_prof.ev[f * 6 + 5]) != cudaSuccess) { set_error("gsr_profile_end: event sync failed"); return GSR_ERR_CUDA; }
+        for (int k = 0; k < 5; k++) {
+            float t = 0;
+            cudaEventElapsedTime(&t, g_prof.ev[f * 6 + k], g_prof.ev[f * 6 + k + 1]);
+            acc[k] += t;
+        }
+    }
+    for (int k = 0; k < 5; k++) ms[k] = g_prof.frames ? (float)(acc[k] / g_prof.frames) : 0.f;
+    if (frames) *frames = g_prof.frames;
+    return GSR_OK;
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+template <int DEG>
+static void launch_pre(bool vec, const PreParams& pp, cudaStream_t st) {
+    const int grid = (pp.P + PRE_THREADS - 1) / PRE_THREADS;
+    if (vec) k_preprocess<DEG, true><<<grid, PRE_THREADS, 0, st>>>(pp);
+    else k_preprocess<DEG, false><<<grid, PRE_THREADS, 0, st>>>(pp);
+}
+
+int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,
+                 int32_t* radii, int flags, cudaStream_t st) {
+    if (!f || !ws) { set_error("gsr_forward: null frame/workspace"); return GSR_ERR_INVALID; }
+    if (f->P < 0 || f->W <= 0 || f->H <= 0) { set_error("gsr_forward: bad sizes P=%d W=%d H=%d", f->P, f->W, f->H); return GSR_ERR_INVALID; }
+    if (!out_color || !out_depth || !out_alpha) { set_error("gsr_forward: null output image"); return GSR_ERR_INVALID; }
+    const size_t HW = (size_t)f->W * f->H;
+    const ImageLayout il(f->W, f->H);
+    if (!ws->image || ws->image_bytes < il.total) { set_error("gsr_forward: image workspace too small (%zu < %zu)", ws->image_bytes, il.total); return GSR_ERR_WORKSPACE; }
+    char* img = (char*)ws->image;
+    gsr_counters* counters = (gsr_counters*)(img + il.counters);
+    const bool debug = f->debug != 0;
+    if (f->P == 0) {  // rasterize_points.cu:68-71,82: zero images, nothing else runs
+        cudaMemsetAsync(out_color, 0, 12 * HW, st);
+        cudaMemsetAsync(out_depth, 0, 4 * HW, st);
+        cudaMemsetAsync(out_alpha, 0, 4 * HW, st);
+        cudaMemsetAsync(img, 0, il.zero_bytes(), st);
+        cudaMemsetAsync(img + il.ranges, 0, 8 * (size_t)il.tiles, st);
+        return check_launch("gsr_forward(P=0)", debug, st);
+    }
+    if (!radii || !f->means3D || !f->opacities || !f->viewmatrix || !f->projmatrix || !f->campos || !f->bg) {
+        set_error("gsr_forward: null required input");
+        return GSR_ERR_INVALID;
+    }
+    if ((f->shs == nullptr) == (f->colors_precomp == nullptr)) { set_error("gsr_forward: provide exactly one of shs / colors_precomp"); return GSR_ERR_INVALID; }
+    const bool has_sr = f->scales != nullptr && f->rotations != nullptr;
+    if (has_sr == (f->cov3D_precomp != nullptr) || ((f->scales != nullptr) != (f->rotations != nullptr))) {
+        set_error("gsr_forward: provide exactly one of scales+rotations / cov3D_precomp");
+        return GSR_ERR_INVALID;
+    }
+    const int D = f->D < 0 ? 0 : (f->D > 3 ? 3 : f->D);
+    if (f->shs && (D + 1) * (D + 1) > f->M) { set_error("gsr_forward: sh degree %d needs %d coefficients, shs has M=%d", D, (D + 1) * (D + 1), f->M); return GSR_ERR_INVALID; }
+    const GeomLayout gl((size_t)f->P);
+    if (!ws->geom || ws->geom_bytes < gl.total) { set_error("gsr_forward: geometry workspace too small (%zu < %zu)", ws->geom_bytes, gl.total); return GSR_ERR_WORKSPACE; }
+    const size_t cap = ws->binning ? ws->binning_bytes / 12 : 0;
+    if (cap < 1) { set_error("gsr_forward: binning workspace too small"); return GSR_ERR_WORKSPACE; }
+    const BinLayout bl(cap);
+    char* geo = (char*)ws->geom;
+    char* bin = (char*)ws->binning;
+
+    cudaMemsetAsync(img, 0, il.zero_bytes(), st);
+    prof_mark(0, st);
+
+    PreParams pp;
+    pp.P = f->P; pp.D = D; pp.M = f->M; pp.W = f->W; pp.H = f->H; pp.gx = il.gx; pp.gy = il.gy;
+    pp.scale_modifier = f->scale_modifier; pp.tanfovx = f->tanfovx; pp.tanfovy = f->tanfovy;
+    pp.focal_y = f->H / (2.0f * f->tanfovy);  // rasterizer_impl.cu:223-224
+    pp.focal_x = f->W / (2.0f * f->tanfovx);
+    pp.rot_vec = (((uintptr_t)f->rotations & 15) == 0) ? 1 : 0;
+    pp.prefiltered = f->prefiltered; pp.for_backward = (flags & GSR_FLAG_FOR_BACKWARD) ? 1 : 0;
+    pp.means3D = f->means3D; pp.shs = f->shs; pp.colors_precomp = f->colors_precomp; pp.opacities = f->opacities;
+    pp.scales = f->scales; pp.rotations = f->rotations; pp.cov3D_precomp = f->cov3D_precomp;
+    pp.view = f->viewmatrix; pp.proj = f->projmatrix; pp.campos = f->campos;
+    pp.records = (float4*)(geo + gl.records); pp.cov3D = (float*)(geo + gl.cov3D); pp.clamped = (uint8_t*)(geo + gl.clamped);
+    pp.radii = radii; pp.tile_count = (uint32_t*)(img + il.tile_count); pp.counters = counters;
+
+    if (f->colors_precomp) launch_pre<-1>(false, pp, st);
+    else {
+        const bool vec = (f->M % 4 == 0) && (((uintptr_t)f->shs & 15) == 0);
+        switch (D) {
+            case 0: launch_pre<0>(vec, pp, st); break;
+            case 1: launch_pre<1>(vec, pp, st); break;
+            case 2: launch_pre<2>(vec, pp, st); break;
+            default: launch_pre<3>(vec, pp, st); break;
+        }
+    }
+    prof_mark(1, st);
+    int rc = check_launch("gsr_forward/preprocess", debug, st);
+    if (rc) return rc;
+
+    uint2* ranges = (uint2*)(img + il.ranges);
+    k_tile_scan<<<1, 1024, 0, st>>>(pp.tile_count, ranges, counters, il.tiles, (uint32_t)(cap > 0xffffffffull ? 0xffffffffull : cap));
+    prof_mark(2, st);
+    if ((rc = check_launch("gsr_forward/tile_scan", debug, st))) return rc;
+
+    k_emit<<<(f->P + 255) / 256, 256, 0, st>>>(f->P, il.gx, il.gy, radii, pp.records, ranges, (uint32_t*)(img + il.tile_fill),
+                                               (uint2*)(bin + bl.pairs), counters);
+    prof_mark(3, st);
+    if ((rc = check_launch("gsr_forward/emit", debug, st))) return rc;
+
+    k_sort_tiles<<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list),
+                                                   counters, (flags & GSR_FLAG_SORTED_KEYS) ? 1 : 0);
+    prof_mark(4, st);
+    if ((rc = check_launch("gsr_forward/sort", debug, st))) return rc;
+
+    k_blend<<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>(ranges, (const uint32_t*)(bin + bl.point_list), pp.records, f->W, f->H, il.gx,
+                                                          f->bg, out_color, out_depth, out_alpha,
+                                                          (flags & GSR_FLAG_FOR_BACKWARD) ? (uint32_t*)(img + il.n_contrib) : nullptr,
+                                                          counters);
+    prof_mark(5, st);
+    if (g_prof.on && g_prof.frames < g_prof.max_frames) g_prof.frames++;
+    return check_launch("gsr_forward/blend", debug, st);
+}
+
+}  // namespace gsr

@@ -1,0 +1,396 @@
+"""Drop-in replacement for the reference package ``diff_gaussian_rasterization``.
+
+Same public surface as ``sugar/gaussian_splatting/submodules/diff-gaussian-rasterization/
+diff_gaussian_rasterization/__init__.py`` (reference lines in brackets):
+
+* ``GaussianRasterizationSettings``  NamedTuple, 12 fields                        [:160-172]
+* ``GaussianRasterizer(nn.Module)``  ``.forward(...)`` -> (color, depth, alpha, radii), ``.markVisible``  [:174-223]
+* ``rasterize_gaussians(...)`` and ``_RasterizeGaussians`` (autograd.Function)     [:21-158]
+
+Host code stays Python/PyTorch; all device work happens in the hand-written sm_100a library behind the C ABI
+of ``include/gsr_b200.h`` (loaded through ctypes by ``_lib``).  PyTorch only provides memory (the caching
+allocator), the current stream and autograd plumbing.  There is no CPU path.
+
+Differences a caller can observe:
+* kernels run on PyTorch's *current* stream and on ``means3D``'s device (the reference uses the legacy default
+  stream and the current device, rasterize_points.cu:73);
+* the three opaque buffers saved for backward have a different (smaller) layout;
+* by default one event synchronisation per forward remains (the reference blocks on a cudaMemcpy,
+  rasterizer_impl.cu:281-282); ``set_sync_mode("async")`` removes it (see ``FrameTicket``).
+"""
+from __future__ import annotations
+
+import collections
+import ctypes as C
+from typing import Dict, NamedTuple, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import lib as _L
+
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "set_sync_mode", "get_sync_mode",
+           "last_frame_stats", "FrameTicket", "forward_raw", "debug_views"]
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+# ----------------------------------------------------------------------------------------------- engine state
+_SYNC_MODE = "safe"
+
+
+def set_sync_mode(mode: str) -> None:
+    """"safe": every forward validates the binning capacity before returning (one event sync, automatic
+    re-run on overflow).  "async": no host synchronisation at all; each forward returns immediately and its
+    ``FrameTicket`` (``last_ticket()``) must be validated by the caller before the images are trusted."""
+    global _SYNC_MODE
+    if mode not in ("safe", "async"):
+        raise ValueError("sync mode must be 'safe' or 'async'")
+    _SYNC_MODE = mode
+
+
+def get_sync_mode() -> str:
+    return _SYNC_MODE
+
+
+class FrameTicket:
+    """Handle on the device-side counters of one forward call (gsr_counters, include/gsr_b200.h)."""
+
+    __slots__ = ("event", "slot", "capacity", "_state")
+
+    def __init__(self, event, slot, capacity, state):
+        self.event, self.slot, self.capacity, self._state = event, slot, capacity, state
+
+    def ready(self) -> bool:
+        return self.event.query()
+
+    def stats(self) -> Dict[str, int]:
+        """Blocks until the frame's counters have reached the host."""
+        self.event.synchronize()
+        c = self.slot
+        return {"num_rendered": int(c[0]), "overflow": int(c[1]), "max_tile": int(c[2]), "trapped": int(c[3]),
+                "num_visible": int(c[4]), "capacity": int(self.capacity)}
+
+    def ok(self) -> bool:
+        s = self.stats()
+        if s["overflow"]:
+            self._state.grow(int(s["num_rendered"]))
+        return not s["overflow"]
+
+
+class _DeviceState:
+    RING = 64
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.capacity = 1 << 20
+        self.pinned = torch.zeros((self.RING, 8), dtype=torch.int32).pin_memory()
+        self.events = [None] * self.RING
+        self.cursor = 0
+        self.cache: Dict[Tuple, torch.Tensor] = {}
+        self.last_ticket: Optional[FrameTicket] = None
+
+    def grow(self, needed: int) -> None:
+        self.capacity = max(self.capacity, int(needed * 1.25) + 4096)
+
+    def ensure_capacity(self, P: int) -> None:
+        # first guess: a few instances per Gaussian; corrected from the counters of real frames
+        if self.capacity < 4 * P:
+            self.capacity = 4 * P
+
+    def next_slot(self):
+        i = self.cursor
+        self.cursor = (i + 1) % self.RING
+        ev = self.events[i]
+        if ev is not None:
+            ev.synchronize()  # the slot is only reused once its previous copy has landed
+        ev = torch.cuda.Event()
+        self.events[i] = ev
+        return self.pinned[i], ev
+
+    def workspace(self, kind: str, nbytes: int, fresh: bool) -> torch.Tensor:
+        if fresh:
+            return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        key = (kind, torch.cuda.current_stream(self.device).cuda_stream)
+        t = self.cache.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(int(nbytes * 1.1) + 256, dtype=torch.uint8, device=self.device)
+            self.cache[key] = t
+        return t
+
+
+_STATES: Dict[int, _DeviceState] = {}
+
+
+def _state(device: torch.device) -> _DeviceState:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _STATES.get(idx)
+    if st is None:
+        st = _DeviceState(torch.device("cuda", idx))
+        _STATES[idx] = st
+    return st
+
+
+def last_ticket(device=None) -> Optional[FrameTicket]:
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    return _state(dev).last_ticket
+
+
+def last_frame_stats(device=None) -> Dict[str, int]:
+    """num_rendered (R), num_visible (P_vis), max_tile ... of the most recent forward on ``device``."""
+    t = last_ticket(device)
+    if t is None:
+        raise RuntimeError("no frame has been rasterized on this device yet")
+    return t.stats()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _dev_f32(t: torch.Tensor, device: torch.device) -> torch.Tensor:
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _opt(t: Optional[torch.Tensor], device: torch.device) -> Optional[torch.Tensor]:
+    if t is None or t.numel() == 0:
+        return None
+    return _dev_f32(t, device)
+
+
+def _fill_frame(fr: _lib.gsr_frame, P, D, M, W, H, settings, bg, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D,
+                view, proj, campos):
+    fr.P, fr.D, fr.M, fr.W, fr.H = P, D, M, W, H
+    fr.scale_modifier = settings.scale_modifier
+    fr.tanfovx, fr.tanfovy = settings.tanfovx, settings.tanfovy
+    fr.prefiltered, fr.debug = int(bool(settings.prefiltered)), int(bool(settings.debug))
+    fr.bg, fr.means3D, fr.shs, fr.colors_precomp = _ptr(bg), _ptr(means3D), _ptr(shs), _ptr(colors_precomp)
+    fr.opacities, fr.scales, fr.rotations, fr.cov3D_precomp = _ptr(opacities), _ptr(scales), _ptr(rotations), _ptr(cov3D)
+    fr.viewmatrix, fr.projmatrix, fr.campos = _ptr(view), _ptr(proj), _ptr(campos)
+
+
+def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, settings: GaussianRasterizationSettings,
+                for_backward: bool = False, sorted_keys: bool = False, sync: Optional[bool] = None, out=None):
+    """One rasterizer forward through the C ABI.  Returns (color, depth, alpha, radii, workspaces, ticket, keepalive).
+    ``workspaces`` = (geom, binning, image) byte tensors; fresh allocations when ``for_backward`` (they must outlive
+    the call), otherwise per-(device, stream) cached buffers.  ``out`` optionally supplies preallocated
+    (color, depth, alpha, radii) tensors (used by the frame loop to render straight into its ring)."""
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:57-59
+    if not means3D.is_cuda:
+        raise RuntimeError("autovfx_b200 rasterizer: means3D must be a CUDA tensor (there is no CPU path)")
+    device = means3D.device
+    st = _state(device)
+    P = means3D.size(0)
+    H, W = int(settings.image_height), int(settings.image_width)
+    with torch.cuda.device(device):
+        means3D = _dev_f32(means3D, device)
+        shs, colors_precomp = _opt(shs, device), _opt(colors_precomp, device)
+        scales, rotations, cov3D_precomp = _opt(scales, device), _opt(rotations, device), _opt(cov3D_precomp, device)
+        opacities = _dev_f32(opacities, device)
+        bg = _dev_f32(settings.bg, device)
+        view = _dev_f32(settings.viewmatrix, device)
+        proj = _dev_f32(settings.projmatrix, device)
+        campos = _dev_f32(settings.campos, device)
+        M = shs.size(1) if shs is not None else 0
+        if out is None:
+            color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+            depth = torch.empty((1, H, W), dtype=torch.float32, device=device)
+            alpha = torch.empty((1, H, W), dtype=torch.float32, device=device)
+            radii = torch.empty((P,), dtype=torch.int32, device=device)
+        else:
+            color, depth, alpha, radii = out
+        flags = (_lib.GSR_FLAG_FOR_BACKWARD if for_backward else 0) | (_lib.GSR_FLAG_SORTED_KEYS if sorted_keys else 0)
+        fr = _lib.gsr_frame()
+        _fill_frame(fr, P, int(settings.sh_degree), M, W, H, settings, bg, means3D, shs, colors_precomp, opacities, scales, rotations,
+                    cov3D_precomp, view, proj, campos)
+        geom_b, img_b = _L.gsr_geom_bytes(P), _L.gsr_image_bytes(W, H)
+        geom = st.workspace("geom", geom_b, for_backward)
+        image = st.workspace("image", img_b, for_backward)
+        st.ensure_capacity(P)
+        do_sync = (_SYNC_MODE == "safe") if sync is None else sync
+        stream = torch.cuda.current_stream(device)
+        while True:
+            cap = st.capacity
+            binning = st.workspace("binning", _L.gsr_binning_bytes(cap), for_backward)
+            ws = _lib.gsr_workspace(geom.data_ptr(), geom.numel(), binning.data_ptr(), binning.numel(), image.data_ptr(), image.numel())
+            rc = _L.gsr_forward(C.byref(fr), C.byref(ws), color.data_ptr(), depth.data_ptr(), alpha.data_ptr(),
+                                radii.data_ptr() if P > 0 else None, flags, C.c_void_p(stream.cuda_stream))
+            _lib.check(rc, "gsr_forward")
+            slot, ev = st.next_slot()
+            slot.copy_(image[:32].view(torch.int32), non_blocking=True)
+            ev.record(stream)
+            ticket = FrameTicket(ev, slot, _L.gsr_binning_capacity(binning.numel()), st)
+            st.last_ticket = ticket
+            if not do_sync:
+                break
+            s = ticket.stats()
+            if s["trapped"]:
+                raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")  # auxiliary.h:158
+            if not s["overflow"]:
+                break
+            st.grow(s["num_rendered"])  # rare: first frames of a new scene; re-run with a larger binning buffer
+    keep = (means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, view, proj, campos)
+    return color, depth, alpha, radii, (geom, binning, image), ticket, keep
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+        need_bw = any(isinstance(t, torch.Tensor) and t.requires_grad for t in
+                      (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
+        color, depth, alpha, radii, (geom, binning, image), ticket, keep = forward_raw(
+            means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings, for_backward=need_bw)
+        ctx.raster_settings = raster_settings
+        ctx.ticket = ticket
+        ctx.has = (sh.numel() != 0, colors_precomp.numel() != 0, scales.numel() != 0, cov3Ds_precomp.numel() != 0)
+        ctx.needs = need_bw
+        k_means3D, k_shs, k_colors, _k_op, k_scales, k_rot, k_cov, k_bg, k_view, k_proj, k_campos = keep
+        e = torch.empty(0, device=means3D.device)
+        ctx.save_for_backward(k_colors if k_colors is not None else e, k_means3D, k_scales if k_scales is not None else e,
+                              k_rot if k_rot is not None else e, k_cov if k_cov is not None else e, radii,
+                              k_shs if k_shs is not None else e, geom, binning, image, alpha, k_bg, k_view, k_proj, k_campos)
+        ctx.mark_non_differentiable(radii)
+        return color, depth, alpha, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_out_depth, grad_out_alpha, _):
+        if not ctx.needs:
+            return (None,) * 9
+        s = ctx.raster_settings
+        (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, image, alpha, bg, view, proj,
+         campos) = ctx.saved_tensors
+        if _SYNC_MODE != "safe" and not ctx.ticket.ok():
+            raise RuntimeError("autovfx_b200: the forward of this graph overflowed its binning buffer (async mode); re-run it")
+        device = means3D.device
+        P = means3D.size(0)
+        H, W = int(s.image_height), int(s.image_width)
+        M = sh.size(1) if sh.numel() else 0
+        with torch.cuda.device(device):
+            def img_grad(g, c):
+                if g is None:
+                    return torch.zeros((c, H, W), dtype=torch.float32, device=device)
+                return _dev_f32(g, device)
+            g_color, g_depth, g_alpha = img_grad(grad_out_color, 3), img_grad(grad_out_depth, 1), img_grad(grad_out_alpha, 1)
+            f32 = dict(dtype=torch.float32, device=device)
+            dL_dmeans3D = torch.empty((P, 3), **f32)
+            dL_dmeans2D = torch.empty((P, 3), **f32)
+            dL_dcolors = torch.empty((P, 3), **f32)
+            dL_ddepths = torch.empty((P, 1), **f32)
+            dL_dconic = torch.empty((P, 2, 2), **f32)
+            dL_dopacity = torch.empty((P, 1), **f32)
+            dL_dcov3D = torch.empty((P, 6), **f32)
+            dL_dsh = torch.empty((P, M, 3), **f32)
+            dL_dscales = torch.empty((P, 3), **f32)
+            dL_drotations = torch.empty((P, 4), **f32)
+            fr = _lib.gsr_frame()
+            _fill_frame(fr, P, int(s.sh_degree), M, W, H, s, bg, means3D, sh, colors_precomp, None, scales, rotations, cov3Ds_precomp,
+                        view, proj, campos)
+            ws = _lib.gsr_workspace(geom.data_ptr(), geom.numel(), binning.data_ptr(), binning.numel(), image.data_ptr(), image.numel())
+            gr = _lib.gsr_grads(_ptr(dL_dmeans2D), _ptr(dL_dconic), _ptr(dL_dopacity), _ptr(dL_dcolors), _ptr(dL_ddepths),
+                                _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations))
+            rc = _L.gsr_backward(C.byref(fr), C.byref(ws), _ptr(radii), _ptr(alpha), _ptr(g_color), _ptr(g_depth), _ptr(g_alpha),
+                                 C.byref(gr), C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+            _lib.check(rc, "gsr_backward")
+        has_sh, has_col, has_scale, has_cov = ctx.has
+        # reference order (__init__.py:146-156): means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, settings
+        return (dL_dmeans3D, dL_dmeans2D, dL_dsh if has_sh else None, dL_dcolors if has_col else None, dL_dopacity,
+                dL_dscales if has_scale else None, dL_drotations if has_scale else None, dL_dcov3D if has_cov else None, None)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        """Boolean mask of the points in front of the near plane (__init__.py:179-188, rasterizer_impl.cu:54-66)."""
+        with torch.no_grad():
+            s = self.raster_settings
+            if not positions.is_cuda:
+                raise RuntimeError("autovfx_b200 rasterizer: positions must be a CUDA tensor")
+            device = positions.device
+            with torch.cuda.device(device):
+                pos = _dev_f32(positions, device)
+                view, proj = _dev_f32(s.viewmatrix, device), _dev_f32(s.projmatrix, device)
+                P = pos.size(0)
+                present = torch.zeros((P,), dtype=torch.bool, device=device)
+                rc = _L.gsr_mark_visible(P, _ptr(pos), _ptr(view), _ptr(proj), _ptr(present),
+                                         C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+                _lib.check(rc, "gsr_mark_visible")
+        return present
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None):
+        raster_settings = self.raster_settings
+
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+
+        # absent inputs travel as empty tensors (their null data_ptr is the C side's "None", __init__.py:200-210)
+        if shs is None:
+            shs = torch.Tensor([])
+        if colors_precomp is None:
+            colors_precomp = torch.Tensor([])
+        if scales is None:
+            scales = torch.Tensor([])
+        if rotations is None:
+            rotations = torch.Tensor([])
+        if cov3D_precomp is None:
+            cov3D_precomp = torch.Tensor([])
+
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, raster_settings)
+
+
+def debug_views(workspaces, P: int, W: int, H: int) -> Dict[str, torch.Tensor]:
+    """Typed tensor views into the opaque workspaces of a forward (parity tests: per-stage buffers)."""
+    geom, binning, image = workspaces
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    tiles = gx * gy
+    ws = _lib.gsr_workspace(geom.data_ptr(), geom.numel(), binning.data_ptr(), binning.numel(), image.data_ptr(), image.numel())
+    v = _lib.gsr_views()
+    _lib.check(_L.gsr_get_views(C.byref(ws), P, W, H, C.byref(v)), "gsr_get_views")
+    cap = _L.gsr_binning_capacity(binning.numel())
+
+    def view(base_t, ptr, nbytes, dtype, shape):
+        off = ptr - base_t.data_ptr()
+        return base_t[off:off + nbytes].view(dtype).view(*shape)
+
+    return {
+        "records": view(geom, v.records, 48 * P, torch.float32, (P, 12)),
+        "cov3D": view(geom, v.cov3D, 24 * P, torch.float32, (P, 6)),
+        "clamped": view(geom, v.clamped, P, torch.uint8, (P,)),
+        "point_list": view(binning, v.point_list, 4 * cap, torch.int32, (cap,)),
+        "sorted_keys": view(binning, v.sorted_keys, 8 * cap, torch.int64, (cap,)),
+        "ranges": view(image, v.ranges, 8 * tiles, torch.int32, (tiles, 2)),
+        "n_contrib": view(image, v.n_contrib, 4 * W * H, torch.int32, (H, W)),
+        "tile_count": view(image, v.tile_count, 4 * tiles, torch.int32, (tiles,)),
+        "counters": view(image, v.counters, 32, torch.int32, (8,)),
+    }

@@ -1,0 +1,179 @@
+"""Per-frame render loop and its multi-GPU sharding.
+
+Replaces the reference's frame loops (``scene_representation.py:355-438`` render_from_3DGS, ``sugar/gaussian_splatting/
+render.py:53-64`` render_set, ``sugar/render.py:109-139``): those call the rasterizer once per camera from Python, block on
+a device->host copy inside every forward (rasterizer_impl.cu:281-282) and then copy / encode four images per frame
+synchronously.  ``FrameLoop`` keeps the Gaussian parameters resident, issues every frame without a host synchronisation
+(``forward_raw(sync=False)``), renders straight into a ring of ``[5,H,W]`` device frames (rgb | depth | alpha), streams
+finished frames to pinned host memory on a copy stream that overlaps the next frame's kernels, and validates each
+frame's device-side counters before handing it to the consumer (a frame whose binning buffer overflowed is re-rendered).
+
+Multi-GPU: frames are independent given the parameters, so ranks shard the camera list; the only
+collectives are the one-time parameter broadcast, the camera scatter and the gather of per-frame statistics.  The
+rendered frames stay on the rank that produced them (the reference writes them to disk per frame anyway).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+
+from .scene import Camera
+
+CAM_FLOATS = 37  # view(16) | proj(16) | campos(3) | tanfovx | tanfovy
+
+
+# ----------------------------------------------------------------------------- sharding (pure host logic)
+def shard_indices(n_frames: int, rank: int, world: int, mode: str = "roundrobin") -> List[int]:
+    """Frames owned by ``rank``.  Round-robin balances the slowly varying per-frame cost (R changes smoothly along a
+    trajectory); "block" keeps contiguous runs."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    if mode == "roundrobin":
+        return list(range(rank, n_frames, world))
+    if mode == "block":
+        per = (n_frames + world - 1) // world
+        return list(range(rank * per, min(n_frames, (rank + 1) * per)))
+    raise ValueError("mode must be 'roundrobin' or 'block'")
+
+
+def pack_cameras(cams: Sequence[Camera]) -> torch.Tensor:
+    """[N,37] fp32 host tensor, the per-camera payload of the scatter."""
+    if len(cams) == 0:
+        return torch.zeros((0, CAM_FLOATS), dtype=torch.float32)
+    return torch.stack([c.packed() for c in cams]).contiguous()
+
+
+def scatter_cameras(packed: Optional[torch.Tensor], n_frames: int, device, mode: str = "roundrobin", group=None) -> torch.Tensor:
+    """Rank 0 holds ``packed`` [N,37]; every rank receives the rows of its own frames via one ``dist.scatter`` (padded to
+    equal length; NCCL on GPUs, gloo in the CPU tests).  Single-process: just moves the tensor."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return packed.to(device)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    per = (n_frames + world - 1) // world
+    recv = torch.zeros((per, CAM_FLOATS), dtype=torch.float32, device=device)
+    chunks = None
+    if rank == 0:
+        chunks = []
+        for r in range(world):
+            idx = shard_indices(n_frames, r, world, mode)
+            c = torch.zeros((per, CAM_FLOATS), dtype=torch.float32)
+            if idx:
+                c[:len(idx)] = packed[idx]
+            chunks.append(c.to(device))
+    dist.scatter(recv, chunks, src=0, group=group)
+    return recv[:len(shard_indices(n_frames, rank, world, mode))]
+
+
+def broadcast_gaussians(g: Optional[Dict[str, torch.Tensor]], device, group=None) -> Dict[str, torch.Tensor]:
+    """One-time replication of the parameters from rank 0 (708 MB at 3M Gaussians / M=16)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return {k: v.to(device) for k, v in g.items()}
+    rank = dist.get_rank(group)
+    keys = ["means3D", "scales", "rotations", "opacities", "shs"]
+    meta = [None]
+    if rank == 0:
+        meta = [{k: tuple(g[k].shape) for k in keys}]
+    dist.broadcast_object_list(meta, src=0, group=group)
+    out = {}
+    for k in keys:
+        t = g[k].to(device).float().contiguous() if rank == 0 else torch.empty(meta[0][k], dtype=torch.float32, device=device)
+        dist.broadcast(t, src=0, group=group)
+        out[k] = t
+    return out
+
+
+def gather_stats(local: torch.Tensor, group=None) -> Optional[List[torch.Tensor]]:
+    """Gather a small per-rank statistics tensor on rank 0."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return [local]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    bufs = [torch.zeros_like(local) for _ in range(world)] if rank == 0 else None
+    dist.gather(local, bufs, dst=0, group=group)
+    return bufs
+
+
+# ----------------------------------------------------------------------------- the loop
+class FrameLoop:
+    """Renders a list of cameras for one resident set of Gaussians on one GPU."""
+
+    def __init__(self, gaussians: Dict[str, torch.Tensor], sh_degree: int, width: int, height: int, bg=(0.0, 0.0, 0.0),
+                 scale_modifier: float = 1.0, device=None, ring: int = 3, to_host: bool = True):
+        from . import rasterizer as R  # requires the CUDA library
+        self._R = R
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.g = {k: v.to(self.device).float().contiguous() for k, v in gaussians.items()}
+        self.sh_degree, self.W, self.H, self.scale_modifier = sh_degree, width, height, scale_modifier
+        self.bg = torch.tensor(bg, dtype=torch.float32, device=self.device)
+        self.ring = ring
+        self.to_host = to_host
+        P = self.g["means3D"].shape[0]
+        self.frames = [torch.empty((5, height, width), dtype=torch.float32, device=self.device) for _ in range(ring)]
+        self.radii = [torch.empty((P,), dtype=torch.int32, device=self.device) for _ in range(ring)]
+        self.host = [torch.empty((5, height, width), dtype=torch.float32).pin_memory() for _ in range(ring)] if to_host else None
+        self.copy_stream = torch.cuda.Stream(self.device) if to_host else None
+        self.cam_pinned = torch.empty((ring, CAM_FLOATS), dtype=torch.float32).pin_memory()
+        self.cam_dev = torch.empty((ring, CAM_FLOATS), dtype=torch.float32, device=self.device)
+        self.h2d_bytes_per_frame = CAM_FLOATS * 4
+        self.d2h_bytes_per_frame = 5 * height * width * 4 if to_host else 0
+        self.rerendered = 0
+
+    def _settings(self, slot: int, tanfovx: float, tanfovy: float):
+        c = self.cam_dev[slot]
+        return self._R.GaussianRasterizationSettings(
+            image_height=self.H, image_width=self.W, tanfovx=tanfovx, tanfovy=tanfovy, bg=self.bg, scale_modifier=self.scale_modifier,
+            viewmatrix=c[0:16], projmatrix=c[16:32], sh_degree=self.sh_degree, campos=c[32:35], prefiltered=False, debug=False)
+
+    def _issue(self, slot: int, cam_row: torch.Tensor, sync: bool):
+        """host camera row -> pinned -> device (H2D inside the frame), then the forward into ring slot ``slot``."""
+        self.cam_pinned[slot].copy_(cam_row)
+        self.cam_dev[slot].copy_(self.cam_pinned[slot], non_blocking=True)
+        f = self.frames[slot]
+        g = self.g
+        out = (f[0:3], f[3:4], f[4:5], self.radii[slot])
+        res = self._R.forward_raw(g["means3D"], g["shs"], None, g["opacities"], g["scales"], g["rotations"], None,
+                                  self._settings(slot, float(cam_row[35]), float(cam_row[36])), sync=sync, out=out)
+        return res[5]  # ticket
+
+    def render(self, packed_cams: torch.Tensor, consume: Optional[Callable[[int, torch.Tensor, Dict[str, int]], None]] = None) -> List[Dict[str, int]]:
+        """Render every row of ``packed_cams`` ([N,37] host tensor).  ``consume(i, frame, stats)`` receives the finished
+        frame ``[5,H,W]`` (pinned host tensor if ``to_host`` else the device ring slot) — valid until ``ring-1`` further
+        frames have been issued.  Returns the per-frame statistics."""
+        n = packed_cams.shape[0]
+        stats: List[Optional[Dict[str, int]]] = [None] * n
+        inflight = []  # (frame index, slot, ticket, copy_done_event)
+        cur = torch.cuda.current_stream(self.device)
+
+        def retire(entry):
+            i, slot, ticket, ev = entry
+            if not ticket.ok():  # binning overflow: re-render this frame synchronously with the grown capacity
+                self.rerendered += 1
+                ticket = self._issue(slot, packed_cams[i], sync=True)
+                if self.to_host:
+                    self.host[slot].copy_(self.frames[slot], non_blocking=True)
+                    cur.synchronize()
+            elif ev is not None:
+                ev.synchronize()
+            stats[i] = ticket.stats()
+            if consume is not None:
+                consume(i, self.host[slot] if self.to_host else self.frames[slot], stats[i])
+
+        for i in range(n):
+            slot = i % self.ring
+            if len(inflight) == self.ring:
+                retire(inflight.pop(0))  # frees this slot (device frame + pinned frame)
+            ticket = self._issue(slot, packed_cams[i], sync=False)
+            ev = None
+            if self.to_host:
+                self.copy_stream.wait_event(ticket.event)
+                with torch.cuda.stream(self.copy_stream):
+                    self.host[slot].copy_(self.frames[slot], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self.copy_stream)
+            inflight.append((i, slot, ticket, ev))
+        while inflight:
+            retire(inflight.pop(0))
+        return stats  # type: ignore[return-value]

@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — rendered frames/s at 1920x1080 with 3M Gaussians (BASELINE.json metric), plus HBM roofline.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A *step* is one pass of the rasterizer hot path (one ``GaussianRasterizer`` forward in SH mode: preprocess ->
+binning -> blend) over one camera of the synthetic 300-frame trajectory, per rank.  With N
+ranks every rank renders its own round-robin shard of the trajectory (no data-path collective; weak scaling), so the
+job renders N*K frames in the timed region and ``value`` = N*K / max-over-ranks time.
+
+* ``value``     frames/s with the Gaussians and cameras resident in HBM (async issue, no host sync, no D2H).
+* ``e2e``       frames/s through the public frame loop (``autovfx_b200.render_loop.FrameLoop``) with HOST buffers:
+                every step copies its camera payload pinned-host -> device and the finished [5,H,W] frame
+                device -> pinned-host inside the timed region.
+* ``roofline``  dominant kernel: algorithmic bytes per launch / its CUDA-event duration, vs the measured
+                HBM peak of MEASURED_PEAKS.json; ``frame_*`` keys give the same for the whole frame (B_fwd of SURVEY §8d).
+* ``cpu_baseline``  the CPU oracle (oracle/gsr_oracle.c, OpenMP) on one frame of the same workload (rank 0, N=1).
+* ``--impl reference``  the UNMODIFIED reference CUDA rasterizer (oracle/_ref, compiled from /root/reference) on the same
+                GPU and workload.  The reference's implementation of this path *is* CUDA (there is no CPU implementation
+                in the reference), so the reference arm runs on the device; BASELINE.md names it as the >=10x target.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from autovfx_b200 import scene  # noqa: E402
+
+W_IMG, H_IMG = 1920, 1080
+N_TRAJ = 300
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_setup():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def algorithmic_bytes(P, P_vis, R, M_used=16):
+    """SURVEY §8d / DESIGN.md: bytes that must move once per forward frame, split per stage."""
+    pre = P * (44 + 12 * M_used) + P * 4 + P_vis * 40
+    binning = R * 24
+    blend = R * 40 + W_IMG * H_IMG * 20
+    return {"preprocess": pre, "binning": binning, "blend": blend, "frame": pre + binning + blend}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gaussians", type=int, default=3_000_000, help="override only for debugging; the metric is quoted at 3M")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    K, Wm = args.steps, max(args.warmup, 3)
+    rank, world, local = dist_setup()
+
+    if args.impl == "reference" and rank != 0:
+        return 0  # only rank 0 runs the reference arm
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    use_dist = world > 1 and args.impl == "ours"
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- workload: synthetic 3M-Gaussian scene + 300-camera trajectory (generated on rank 0, broadcast over NCCL) ----
+    t0 = time.time()
+    traj = scene.trajectory_dict(radius=4.0, num_views=N_TRAJ, theta=30.0, w=W_IMG, h=H_IMG, fov_x_deg=60.0)
+    cams = scene.cameras_from_trajectory(traj)
+    g_cpu = scene.config3_scene(P=args.gaussians) if rank == 0 else None
+    from autovfx_b200 import render_loop as RL
+    g = RL.broadcast_gaussians(g_cpu, dev) if use_dist else {k: v.to(dev) for k, v in g_cpu.items()}
+    packed_all = RL.pack_cameras(cams) if rank == 0 else None
+    n_local = len(RL.shard_indices(N_TRAJ, rank, world))
+    my_cams = RL.scatter_cameras(packed_all, N_TRAJ, dev) if use_dist else packed_all.to(dev)
+    my_cams_host = my_cams.cpu()
+    P = g["means3D"].shape[0]
+    log("[bench] rank %d: scene P=%d, %d local cameras, setup %.1fs" % (rank, P, my_cams.shape[0], time.time() - t0))
+    workload = "synthetic %.1fM Gaussians SH-deg 3 (M=16), %dx%d, 300-frame half-sphere trajectory, forward" % (P / 1e6, W_IMG, H_IMG)
+    peak, peak_src = measured_hbm_peak()
+
+    def barrier():
+        if use_dist:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if not use_dist:
+            return x
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if not use_dist:
+            return x
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    cam_of_step = lambda s: s % my_cams.shape[0]  # noqa: E731
+
+    # =================================================================================== reference arm
+    if args.impl == "reference":
+        from oracle import ref_cuda
+        if not ref_cuda.available():
+            # no compiled reference on this box: fall back to the CPU oracle port on a bounded sample
+            from tests import helpers as Hh
+            case = dict(g={k: v.cpu() for k, v in g.items()}, cam=cams[0], sh_degree=3, bg=(0.0, 0.0, 0.0), scale_modifier=1.0)
+            a = Hh.resolve(case)
+            t = time.time()
+            Hh.run_oracle(a)
+            dt = time.time() - t
+            fps = 1.0 / dt
+            line = {"impl": "reference", "metric": "rendered frames/sec at 1920x1080, 3M Gaussians", "value": fps, "unit": "frames/s",
+                    "n_gpus": 0, "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload},
+                    "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": "1 frame (camera 0), CPU oracle"},
+                    "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            print(json.dumps(line))
+            return 0
+
+        def ref_frame(s):
+            c = my_cams[cam_of_step(s)]
+            return ref_cuda.forward(g["means3D"], g["opacities"], c[0:16], c[16:32], c[32:35], W_IMG, H_IMG, float(my_cams_host[cam_of_step(s), 35]),
+                                    float(my_cams_host[cam_of_step(s), 36]), shs=g["shs"], scales=g["scales"], rotations=g["rotations"], sh_degree=3)
+        for s in range(Wm):
+            ref_frame(s)
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        Rs = []
+        for s in range(K):
+            Rs.append(ref_frame(Wm + s)["num_rendered"])
+        e1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        ms = e0.elapsed_time(e1)
+        fps = K / (ms * 1e-3)
+        line = {"impl": "reference", "metric": "rendered frames/sec at 1920x1080, 3M Gaussians", "value": fps, "unit": "frames/s", "n_gpus": 1,
+                "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "reference": "unmodified diff-gaussian-rasterization CUDA (oracle/_ref) on the same B200",
+                           "avg_num_rendered": sum(Rs) / len(Rs), "l2": "inputs larger than L2 (708 MB of SH per frame)"},
+                "clocks": clocks,
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference",
+                                 "sample": "%d frames; the reference path is CUDA, driven by 1 host thread incl. its per-frame blocking D2H" % K},
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # =================================================================================== our arm
+    from autovfx_b200 import rasterizer as R
+    from autovfx_b200 import _lib
+    import ctypes as C
+    bg = torch.zeros(3, device=dev)
+
+    def settings_for(s):
+        ci = cam_of_step(s)
+        c = my_cams[ci]
+        return R.GaussianRasterizationSettings(image_height=H_IMG, image_width=W_IMG, tanfovx=float(my_cams_host[ci, 35]), tanfovy=float(my_cams_host[ci, 36]),
+                                               bg=bg, scale_modifier=1.0, viewmatrix=c[0:16], projmatrix=c[16:32], sh_degree=3, campos=c[32:35],
+                                               prefiltered=False, debug=False)
+
+    all_settings = [settings_for(s) for s in range(Wm + K)]
+    out_ring = [(torch.empty((3, H_IMG, W_IMG), device=dev), torch.empty((1, H_IMG, W_IMG), device=dev), torch.empty((1, H_IMG, W_IMG), device=dev),
+                 torch.empty((P,), dtype=torch.int32, device=dev)) for _ in range(2)]
+
+    def frame(s, sync):
+        return R.forward_raw(g["means3D"], g["shs"], None, g["opacities"], g["scales"], g["rotations"], None, all_settings[s], sync=sync, out=out_ring[s % 2])
+
+    # pre-pass (untimed, synchronous): sizes the binning capacity for every camera of the run and warms everything up
+    for s in range(Wm + K):
+        frame(s, True)
+    attempts = 0
+    while True:
+        attempts += 1
+        for s in range(Wm):
+            frame(s, False)
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        _lib.check(_lib.lib.gsr_profile_begin(K), "gsr_profile_begin")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tickets = []
+        e0.record()
+        for s in range(K):
+            tickets.append(frame(Wm + s, False)[5])
+        e1.record()
+        barrier()
+        ms_k = (C.c_float * 5)()
+        nfr = C.c_int(0)
+        _lib.check(_lib.lib.gsr_profile_end(ms_k, C.byref(nfr)), "gsr_profile_end")
+        clocks = sampler.stop()
+        ms_local = e0.elapsed_time(e1)
+        st = [t.stats() for t in tickets]
+        bad = [x for x in st if x["overflow"]]
+        throttled = any(r in clocks["reasons"] for r in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"))
+        if (not bad and not throttled) or attempts >= 2:
+            break
+        log("[bench] re-measuring (overflow=%d throttled=%s)" % (len(bad), throttled))
+    ms = max_over_ranks(ms_local)
+    frames_total = K * world
+    value = frames_total / (ms * 1e-3)
+    avg_R = sum(x["num_rendered"] for x in st) / len(st)
+    avg_vis = sum(x["num_visible"] for x in st) / len(st)
+    kernels = ["preprocess", "tile_scan", "emit", "sort_tiles", "blend"]
+    kms = {k: float(ms_k[i]) for i, k in enumerate(kernels)}
+    ab = algorithmic_bytes(P, avg_vis, avg_R)
+    stage_bytes = {"preprocess": ab["preprocess"], "tile_scan": 0, "emit": ab["binning"] / 2, "sort_tiles": ab["binning"] / 2, "blend": ab["blend"]}
+    dom = max(kms, key=kms.get)
+    dom_bytes = stage_bytes[dom]
+    dom_gbs = dom_bytes / (kms[dom] * 1e-3) / 1e9 if kms[dom] > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get(dom)
+        except Exception:  # noqa: BLE001
+            traffic = None
+    frame_gbs = ab["frame"] / (ms_local / K * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": kms,
+                "kernel_share": {k: (v / sum(kms.values()) if sum(kms.values()) else 0) for k, v in kms.items()},
+                "per_kernel_gbs": {k: (stage_bytes[k] / (v * 1e-3) / 1e9 if v > 0 else 0) for k, v in kms.items()},
+                "frame_algorithmic_bytes": ab["frame"], "frame_achieved": frame_gbs, "frame_frac": frame_gbs / peak,
+                "note": "blend is FP32/MUFU-bound, not HBM-bound (SURVEY §7); its HBM fraction is reported because the metric names the HBM roofline"}
+
+    # ---- e2e: public frame loop, host camera payload in, finished frame out to pinned host memory, every step ----
+    loop = RL.FrameLoop(g, 3, W_IMG, H_IMG, device=dev, ring=3, to_host=True)
+    e2e_cams = torch.stack([my_cams_host[cam_of_step(Wm + s)] for s in range(K)])
+    loop.render(e2e_cams[:min(K, 6)])  # warm-up (pinned buffers, copy stream)
+    barrier()
+    t_start = time.perf_counter()
+    checksum = [0.0]
+
+    def consume(i, host_frame, stats):
+        checksum[0] += float(host_frame[4, H_IMG // 2, W_IMG // 2])  # touch the host copy of the result
+
+    loop.render(e2e_cams, consume)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t_start
+    e2e_s = max_over_ranks(e2e_s)
+    e2e = {"value": frames_total / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": loop.h2d_bytes_per_frame, "d2h_bytes_per_step": loop.d2h_bytes_per_frame,
+           "api": "autovfx_b200.render_loop.FrameLoop.render (GaussianRasterizer forward per frame, async D2H ring)", "rerendered": loop.rerendered}
+
+    # ---- CPU baseline: the oracle port on one frame of the same workload (rank 0, N=1 only) ----
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from tests import helpers as Hh
+            case = dict(g=g_cpu, cam=cams[0], sh_degree=3, bg=(0.0, 0.0, 0.0), scale_modifier=1.0)
+            a = Hh.resolve(case)
+            t = time.time()
+            Hh.run_oracle(a)
+            dt = time.time() - t
+            cpu_baseline = {"value": 1.0 / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                            "sample": "1 full frame (trajectory camera 0) of the same 3M/1080p workload, oracle/gsr_oracle.c with OpenMP, %.1f s" % dt}
+        except Exception as ex:  # noqa: BLE001
+            cpu_baseline = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %s" % ex}
+
+    if rank == 0:
+        line = {"metric": "rendered frames/sec at 1920x1080, 3M Gaussians", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "gaussians": P, "avg_visible": avg_vis, "avg_num_rendered": avg_R, "frames_per_rank": K,
+                           "parallelism": "frame-sharded x%d (round-robin cameras, NCCL only for parameter broadcast + camera scatter)" % world,
+                           "l2": "inputs larger than L2 (708 MB of SH read per frame; 126 MB L2)", "sync": "async issue, counters validated after the timed region"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * K * world, "roofline": roofline}
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    if use_dist:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,165 @@
+/* gsr_b200 — C ABI of the B200-native 3D-Gaussian-splatting rasterizer hot path.
+ *
+ * This is the drop-in boundary for the reference's native entry points ("DGR/" =
+ * sugar/gaussian_splatting/submodules/diff-gaussian-rasterization, "KNN/" = .../simple-knn of
+ * haoyuhsu/autovfx):
+ *
+ *   gsr_forward       replaces  _C.rasterize_gaussians           DGR/rasterize_points.cu:35-119
+ *                               (CudaRasterizer::Rasterizer::forward, DGR/cuda_rasterizer/rasterizer_impl.cu:197-339)
+ *   gsr_backward      replaces  _C.rasterize_gaussians_backward  DGR/rasterize_points.cu:121-209
+ *                               (Rasterizer::backward, rasterizer_impl.cu:343-446)
+ *   gsr_mark_visible  replaces  _C.mark_visible                  DGR/rasterize_points.cu:211-230
+ *   gsr_dist2         replaces  simple_knn._C.distCUDA2          KNN/spatial.cu:15-26 (SimpleKNN::knn, KNN/simple_knn.cu:185-220)
+ *
+ * Conventions (same as the reference's C++ layer):
+ *   - every pointer is a DEVICE pointer to contiguous fp32 / int32 data unless it says "host";
+ *   - a NULL pointer means "input absent" (the reference encodes None as an empty tensor whose
+ *     data_ptr is null, DGR/diff_gaussian_rasterization/__init__.py:200-210);
+ *   - no torch types; the caller owns every buffer, the library never allocates device memory;
+ *   - `stream` is a cudaStream_t (the reference uses the legacy default stream; pass 0 for that);
+ *   - functions return GSR_OK or a negative error code, gsr_last_error() gives the message;
+ *     CUDA errors are only checked synchronously when frame->debug != 0 (reference: CHECK_CUDA,
+ *     DGR/cuda_rasterizer/auxiliary.h:166-173).
+ */
+#ifndef GSR_B200_H_INCLUDED
+#define GSR_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_ABI_VERSION 1
+
+enum {
+    GSR_OK = 0,
+    GSR_ERR_INVALID = -1,   /* bad argument combination / sizes                                   */
+    GSR_ERR_WORKSPACE = -2, /* a workspace is smaller than the gsr_*_bytes() query                 */
+    GSR_ERR_CUDA = -3,      /* CUDA runtime error (launch failure, or any error when debug is set) */
+};
+
+/* gsr_forward flags */
+enum {
+    GSR_FLAG_FOR_BACKWARD = 1, /* also keep cov3D, SH clamp flags and n_contrib for gsr_backward   */
+    GSR_FLAG_SORTED_KEYS = 2,  /* also write the sorted 64-bit (tile<<32 | depth bits) keys (parity/debug) */
+};
+
+/* One rasterizer invocation = the argument list of Rasterizer::forward (DGR/cuda_rasterizer/rasterizer.h:33-58). */
+typedef struct gsr_frame {
+    int32_t P;              /* number of Gaussians                                                 */
+    int32_t D;              /* active SH degree (0..3; larger values are treated as 3, forward.cu:29-59) */
+    int32_t M;              /* SH coefficients per channel in `shs` (stride), 0 if shs == NULL      */
+    int32_t W, H;           /* image width / height                                               */
+    float scale_modifier;
+    float tanfovx, tanfovy;
+    int32_t prefiltered;    /* !=0: a near-culled point is an error (reference __trap()s, auxiliary.h:156-160) */
+    int32_t debug;          /* !=0: synchronise and check for CUDA errors after the call          */
+    const float* bg;            /* [3]                                                            */
+    const float* means3D;       /* [P,3]                                                          */
+    const float* shs;           /* [P,M,3] coefficient-major, or NULL                             */
+    const float* colors_precomp;/* [P,3] or NULL  (exactly one of shs / colors_precomp)            */
+    const float* opacities;     /* [P]                                                            */
+    const float* scales;        /* [P,3] or NULL                                                  */
+    const float* rotations;     /* [P,4] (r,x,y,z), NOT normalised here, or NULL                  */
+    const float* cov3D_precomp; /* [P,6] or NULL  (exactly one of scales+rotations / cov3D_precomp) */
+    const float* viewmatrix;    /* [16] row-major torch buffer of the transposed W2C              */
+    const float* projmatrix;    /* [16] view @ proj                                               */
+    const float* campos;        /* [3]                                                            */
+} gsr_frame;
+
+/* Opaque workspaces, the analogue of the reference's geomBuffer / binningBuffer / imgBuffer
+ * (rasterizer_impl.h:30-63).  They must stay untouched between gsr_forward and the matching
+ * gsr_backward.  `binning` is sized by a CAPACITY in splat instances, not by the exact count: the
+ * pipeline never reads the instance count back to the host (the reference's blocking cudaMemcpy,
+ * rasterizer_impl.cu:281-282).  If the frame produces more instances than the capacity the frame is
+ * incomplete, gsr_counters.overflow is set, and the caller re-runs with a larger binning workspace. */
+typedef struct gsr_workspace {
+    void* geom;    size_t geom_bytes;    /* >= gsr_geom_bytes(P)                                   */
+    void* binning; size_t binning_bytes; /* >= gsr_binning_bytes(capacity), capacity >= 1          */
+    void* image;   size_t image_bytes;   /* >= gsr_image_bytes(W, H)                               */
+} gsr_workspace;
+
+/* First bytes of the image workspace; copy them to the host (async) to learn the frame's statistics. */
+typedef struct gsr_counters {
+    uint32_t num_rendered; /* R = sum over Gaussians of tiles touched (what the reference returns)  */
+    uint32_t overflow;     /* 1 if R > binning capacity: outputs are incomplete                    */
+    uint32_t max_tile;     /* longest per-tile list                                               */
+    uint32_t trapped;      /* 1 if prefiltered was set and a point was near-culled                 */
+    uint32_t num_visible;  /* Gaussians with radii > 0                                             */
+    uint32_t reserved[3];
+} gsr_counters;
+
+size_t gsr_geom_bytes(int32_t P);
+size_t gsr_binning_bytes(size_t capacity_instances);
+size_t gsr_image_bytes(int32_t W, int32_t H);
+/* Largest capacity (in instances) a binning workspace of `bytes` bytes provides. */
+size_t gsr_binning_capacity(size_t bytes);
+
+/* Forward: preprocess -> per-tile histogram/scan -> key emission -> per-tile depth sort -> blend.
+ * Outputs: out_color [3,H,W], out_depth [1,H,W], out_alpha [1,H,W], radii [P] (int32).
+ * All four are fully written (no pre-zeroing needed).  With P == 0 the images are zero-filled
+ * (reference: rasterize_points.cu:68-71,82).  Asynchronous on `stream`. */
+int gsr_forward(const gsr_frame* frame, const gsr_workspace* ws, float* out_color, float* out_depth,
+                float* out_alpha, int32_t* radii, int flags, void* stream);
+
+/* Gradient buffers, all caller-allocated; the library zero-fills what it accumulates into (the
+ * reference's torch::zeros, rasterize_points.cu:158-168).  dL_dsh may be NULL when shs is NULL,
+ * dL_dscales / dL_drotations may be NULL when scales is NULL. */
+typedef struct gsr_grads {
+    float* dL_dmeans2D;   /* [P,3]  (x,y in NDC-scaled units, z = 0), returned to Python            */
+    float* dL_dconic;     /* [P,4]  scratch (slots 0,1,3)                                          */
+    float* dL_dopacity;   /* [P]                                                                   */
+    float* dL_dcolors;    /* [P,3]  = grad of colors_precomp, or scratch for the SH backward        */
+    float* dL_ddepths;    /* [P]    scratch                                                        */
+    float* dL_dmeans3D;   /* [P,3]                                                                 */
+    float* dL_dcov3D;     /* [P,6]                                                                 */
+    float* dL_dsh;        /* [P,M,3] or NULL                                                       */
+    float* dL_dscales;    /* [P,3] or NULL                                                         */
+    float* dL_drotations; /* [P,4] or NULL                                                         */
+} gsr_grads;
+
+/* Backward of the frame last run through gsr_forward(..., GSR_FLAG_FOR_BACKWARD) on `ws`.
+ * out_alpha is the forward's alpha image; dL_dout_* are the three image gradients
+ * ([3,H,W], [1,H,W], [1,H,W]); radii is the forward's radii output. */
+int gsr_backward(const gsr_frame* frame, const gsr_workspace* ws, const int32_t* radii, const float* out_alpha,
+                 const float* dL_dout_color, const float* dL_dout_depth, const float* dL_dout_alpha,
+                 const gsr_grads* grads, void* stream);
+
+/* present[i] = (view-space z of means3D[i] > 0.2)  — checkFrustum, rasterizer_impl.cu:54-66. */
+int gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream);
+
+/* Mean squared distance to the 3 nearest neighbours.  `workspace` needs gsr_dist2_bytes(P) bytes. */
+size_t gsr_dist2_bytes(int32_t P);
+int gsr_dist2(int32_t P, const float* points, float* mean_dists, void* workspace, size_t workspace_bytes,
+              void* stream);
+
+/* Device pointers into the workspaces of the last layout (P, capacity, W, H) — for parity tests that
+ * compare per-stage buffers with the reference.  Pure pointer arithmetic, no CUDA calls. */
+typedef struct gsr_views {
+    const float* records;        /* [P,12]: x, y, conic_a, conic_b | conic_c, opacity, depth, tau | r, g, b, - */
+    const float* cov3D;          /* [P,6]  (GSR_FLAG_FOR_BACKWARD only)                             */
+    const uint8_t* clamped;      /* [P]    bit c set = channel c clamped (GSR_FLAG_FOR_BACKWARD only) */
+    const uint32_t* point_list;  /* [capacity] Gaussian ids, per tile front-to-back                 */
+    const uint64_t* sorted_keys; /* [capacity] (GSR_FLAG_SORTED_KEYS only)                          */
+    const uint32_t* ranges;      /* [tiles,2]                                                       */
+    const uint32_t* n_contrib;   /* [H,W]  (GSR_FLAG_FOR_BACKWARD only)                             */
+    const uint32_t* tile_count;  /* [tiles]                                                         */
+    const gsr_counters* counters;
+} gsr_views;
+int gsr_get_views(const gsr_workspace* ws, int32_t P, int32_t W, int32_t H, gsr_views* out);
+
+/* Per-kernel device timing of gsr_forward (CUDA events on the launching stream), for roofline reports.
+ * ms_per_kernel[5] = average ms of {preprocess, tile_scan, emit, sort_tiles, blend} over the profiled frames. */
+int gsr_profile_begin(int max_frames);
+int gsr_profile_end(float* ms_per_kernel, int* frames);
+
+const char* gsr_last_error(void);
+int gsr_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSR_B200_H_INCLUDED */

@@ -157,6 +157,11 @@ int ref_get_state(RefState* s) {
     return 0;
 }
 
+// Device-to-device copy helper so Python can snapshot the buffers ref_get_state points at.
+int ref_copy(void* dst, const void* src, size_t bytes) {
+    return (int)cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice);
+}
+
 // Mirrors markVisible (DGR/rasterize_points.cu:211-230).
 int ref_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      unsigned char* present) {
