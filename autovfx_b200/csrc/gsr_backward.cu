@@ -22,29 +22,6 @@ namespace gsr {
 
 constexpr int BWD_THREADS = 256;
 
-__device__ __forceinline__ bool may_touch(const float4 r0, const float4 r1, float X0, float Y0, float X1, float Y1) {
-    // same conservative footprint test as the forward blend (gsr_forward.cu: splat_may_touch)
-    const float a = r0.z, b = r0.w, c = r1.x, tau = r1.w;
-    const float u0 = r0.x - X1, u1 = r0.x - X0, v0 = r0.y - Y1, v1 = r0.y - Y0;
-    const float uc = fminf(fmaxf(0.f, u0), u1), vc = fminf(fmaxf(0.f, v0), v1);
-    if (!(a > 0.f && c > 0.f)) return true;
-    float qmin = 0.f;
-    if (uc != 0.f || vc != 0.f) {
-        qmin = 3.0e38f;
-        if (uc != 0.f) {
-            const float vs = fminf(fmaxf(-b * uc / c, v0), v1);
-            qmin = fminf(qmin, a * uc * uc + 2.f * b * uc * vs + c * vs * vs);
-        }
-        if (vc != 0.f) {
-            const float us = fminf(fmaxf(-b * vc / a, u0), u1);
-            qmin = fminf(qmin, a * us * us + 2.f * b * us * vc + c * vc * vc);
-        }
-    }
-    const float um = fmaxf(fabsf(u0), fabsf(u1)), vm = fmaxf(fabsf(v0), fabsf(v1));
-    const float mag = a * um * um + c * vm * vm + 2.f * fabsf(b) * um * vm;
-    return !(0.5f * qmin > tau + 1.0e-3f + 4.0e-6f * mag);
-}
-
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(GSR_FULL, v, o);
@@ -68,7 +45,7 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
     const int pxi = X0 + (lane & 7), pyi = Y0 + (lane >> 3);
     const bool inside = pxi < W && pyi < H;
     const float pixx = (float)pxi, pixy = (float)pyi;
-    const float fX0 = (float)X0, fY0 = (float)Y0, fX1 = (float)(X0 + 7), fY1 = (float)(Y0 + 3);
+    const float fcx = (float)X0 + FOOT_HX, fcy = (float)Y0 + FOOT_HY;
     const size_t pid = (size_t)W * pyi + pxi, HW = (size_t)H * W;
 
     const uint2 range = ranges[tile];
@@ -118,7 +95,7 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
             for (int base = ((cnt - 1) / 32) * 32; base >= 0; base -= 32) {
                 const int s = base + lane;
                 const bool keep = s < cnt && (uint32_t)(b * BWD_THREADS + s + 1) <= warp_last &&
-                                  may_touch(sA[s], sB[s], fX0, fY0, fX1, fY1);
+                                  footprint_may_touch(sA[s].x - fcx, sA[s].y - fcy, sA[s].z, sA[s].w, sB[s].x, sB[s].w);
                 unsigned mask = __ballot_sync(GSR_FULL, keep);
                 while (mask) {
                     const int hi = 31 - __clz(mask);

@@ -143,6 +143,34 @@ __device__ __forceinline__ void for_each_tile(int x0, int y0, int x1, int y1, in
     }
 }
 
+// ---- warp-footprint culling shared by the forward and backward blend kernels ------------------------------
+// A warp owns an 8x4 pixel footprint (half extents FOOT_HX x FOOT_HY around its centre).  A splat can reach
+// alpha >= 1/255 at a pixel p only if q(p) = (p-mu)^T A (p-mu) <= 2*tau with tau = ln(255*opacity) (A = conic).
+// sqrt(q) is a norm, so q(p) >= (sqrt(q(c)) - rho)^2 for every pixel of the footprint, where c is the
+// footprint centre and rho^2 = a hx^2 + 2|b| hx hy + c hy^2 bounds sqrt(q) of any centre-to-pixel offset.
+// The splat is therefore irrelevant for the whole footprint unless q(c) <= (sqrt(2 tau) + rho)^2 =: thr.
+// thr depends only on the splat, so preprocess stores it in the record and the test in the blend loop is one
+// quadratic form and one compare.  Margins: tau is inflated by 1e-3, thr by 1e-4 relative, and the
+// comparison discounts 4e-6 of the magnitude of the terms (float rounding here and in the reference's own
+// evaluation of `power`), so a rejected (footprint, splat) pair is one the reference skips at every pixel.
+constexpr float FOOT_HX = 3.5f, FOOT_HY = 1.5f;
+__device__ __forceinline__ float footprint_threshold(float a, float b, float c, float opacity) {
+    if (!(a > 0.f && c > 0.f && a * c - b * b > 0.f)) return 3.0e38f;  // not positive definite: never cull
+    const float tau = __logf(255.0f * opacity) + 1.0e-3f;
+    if (tau != tau) return 3.0e38f;  // NaN opacity: never cull
+    if (tau < 0.f) return -1.0f;     // opacity < 1/255: alpha < 1/255 everywhere
+    const float rho = sqrtf(a * FOOT_HX * FOOT_HX + 2.f * fabsf(b) * FOOT_HX * FOOT_HY + c * FOOT_HY * FOOT_HY);
+    const float s = sqrtf(2.f * tau) + rho;
+    return s * s * 1.0001f + 1.0e-4f;
+}
+// dx, dy: splat centre minus footprint centre
+__device__ __forceinline__ bool footprint_may_touch(float dx, float dy, float a, float b, float c, float thr) {
+    const float ax = a * dx * dx, cy = c * dy * dy, bxy = b * dx * dy;
+    const float q = ax + cy + 2.f * bxy;
+    const float mag = ax + cy + 2.f * fabsf(bxy);
+    return !(q - 4.0e-6f * mag > thr);
+}
+
 // SH basis constants (auxiliary.h:22-39)
 constexpr float SH_C0 = 0.28209479177387814f;
 constexpr float SH_C1 = 0.4886025119029199f;

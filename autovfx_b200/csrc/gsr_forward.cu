@@ -5,7 +5,7 @@
 // identifyTileRanges, CUB InclusiveSum + DeviceRadixSort, forward.cu:261-378 renderCUDA).
 //
 // Pipeline differences (results are identical):
-//   * one 48-byte record per visible Gaussian {x,y,conic.a,conic.b | conic.c,opacity,depth,tau | r,g,b,-}
+//   * one 48-byte record per visible Gaussian {x,y,conic.a,conic.b | conic.c,opacity,depth,thr | r,g,b,-}
 //     replaces the reference's five SoA arrays, so the blend gathers 3 aligned float4 per instance;
 //   * SH coefficients are staged into shared memory with coalesced 16-byte cp.async by each warp, only for
 //     the Gaussians that survived culling, and read back conflict-free (row stride 13 float4);
@@ -182,8 +182,21 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
     float px = 0, py = 0, depth = 0, con_a = 0, con_b = 0, con_c = 0;
     float c3[6] = {0, 0, 0, 0, 0, 0};
 
+    // all per-Gaussian inputs are requested up front (one memory round trip instead of three dependent ones);
+    // the few near-culled Gaussians pay for 32 unused bytes
+    float opacity = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+    float4 q = make_float4(0, 0, 0, 0);
     if (valid) {
         mean = make_float3(p.means3D[3 * (size_t)idx], p.means3D[3 * (size_t)idx + 1], p.means3D[3 * (size_t)idx + 2]);
+        opacity = p.opacities[idx];
+        if (p.cov3D_precomp != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) c3[k] = p.cov3D_precomp[6 * (size_t)idx + k];
+        } else {
+            sx = p.scales[3 * (size_t)idx]; sy = p.scales[3 * (size_t)idx + 1]; sz = p.scales[3 * (size_t)idx + 2];
+            if (p.rot_vec) q = reinterpret_cast<const float4*>(p.rotations)[idx];
+            else q = make_float4(p.rotations[4 * (size_t)idx], p.rotations[4 * (size_t)idx + 1], p.rotations[4 * (size_t)idx + 2], p.rotations[4 * (size_t)idx + 3]);
+        }
         // near cull (auxiliary.h:139-164): only view-space z is tested
         float4 p_hom = xform4x4(mean, cam.proj);
         float p_w = 1.0f / (p_hom.w + 0.0000001f);
@@ -193,16 +206,7 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
             if (p.prefiltered) p.counters->trapped = 1;
         } else {
             // 3D covariance (forward.cu:118-152)
-            if (p.cov3D_precomp != nullptr) {
-#pragma unroll
-                for (int k = 0; k < 6; k++) c3[k] = p.cov3D_precomp[6 * (size_t)idx + k];
-            } else {
-                const float sx = p.scales[3 * (size_t)idx], sy = p.scales[3 * (size_t)idx + 1], sz = p.scales[3 * (size_t)idx + 2];
-                float4 q;
-                if (p.rot_vec) q = reinterpret_cast<const float4*>(p.rotations)[idx];
-                else q = make_float4(p.rotations[4 * (size_t)idx], p.rotations[4 * (size_t)idx + 1], p.rotations[4 * (size_t)idx + 2], p.rotations[4 * (size_t)idx + 3]);
-                cov3d_ref_rounding(sx, sy, sz, p.scale_modifier, q, c3);
-            }
+            if (p.cov3D_precomp == nullptr) cov3d_ref_rounding(sx, sy, sz, p.scale_modifier, q, c3);
             // EWA 2D covariance (forward.cu:74-113)
             float3 t = xform4x3(mean, cam.view);
             const float limx = 1.3f * p.tanfovx, limy = 1.3f * p.tanfovy;
@@ -288,12 +292,9 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
     if (valid) {
         p.radii[idx] = radius;
         if (vis) {
-            const float opacity = p.opacities[idx];
-            // tau = ln(255 * opacity): a pixel can only be touched where power >= -tau (alpha >= 1/255)
-            const float tau = __logf(255.0f * opacity);
             float4* rec = p.records + 3 * (size_t)idx;
             rec[0] = make_float4(px, py, con_a, con_b);
-            rec[1] = make_float4(con_c, opacity, depth, tau);
+            rec[1] = make_float4(con_c, opacity, depth, footprint_threshold(con_a, con_b, con_c, opacity));
             rec[2] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
             if (p.for_backward) {
                 if (p.cov3D_precomp == nullptr) {
@@ -380,9 +381,29 @@ __global__ void __launch_bounds__(256) k_emit(int P, int gx, int gy, const int* 
             tile_rect(r0.x, r0.y, r, gx, gy, x0, y0, x1, y1);
         }
     }
-    for_each_tile<8>(x0, y0, x1, y1, gx, (uint32_t)idx, dbits, [&](int tile, uint32_t id, uint32_t d) {
-        const uint32_t pos = ranges[tile].x + atomicAdd(&tile_fill[tile], 1u);
-        pairs[pos] = make_uint2(id, d);  // little endian: u64 = (depth bits << 32) | id
+    // Small rectangles (<= 8 tiles): issue all position atomics first, then the dependent stores, so the
+    // atomic round trips overlap.  Large rectangles are walked by the whole warp (for_each_tile's big path).
+    const int w = x1 - x0, cnt = w * (y1 - y0);
+    if (cnt > 0 && cnt <= 8) {
+        uint32_t pos[8];
+        int tx = x0, ty = y0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (k < cnt) {
+                const int tile = ty * gx + tx;
+                pos[k] = ranges[tile].x + atomicAdd(&tile_fill[tile], 1u);
+                if (++tx == x1) { tx = x0; ty++; }
+            }
+        }
+        const uint2 pr = make_uint2((uint32_t)idx, dbits);  // little endian: u64 = (depth bits << 32) | id
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (k < cnt) pairs[pos[k]] = pr;
+    }
+    const bool big = cnt > 8;
+    for_each_tile<0>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, (uint32_t)idx, dbits, [&](int tile, uint32_t id, uint32_t d) {
+        const uint32_t p2 = ranges[tile].x + atomicAdd(&tile_fill[tile], 1u);
+        pairs[p2] = make_uint2(id, d);
     });
 }
 
@@ -429,6 +450,92 @@ __device__ void sort_smem(unsigned long long* s, uint32_t n) {
     }
 }
 
+// ---- register-blocked variant for n <= SORT_CAP ------------------------------------------------------------
+// Thread t holds the E consecutive keys [tE, tE+E) in registers (N = 256*E >= n, missing keys are +inf).
+// Compare-exchange partners at element distance < E are in the same thread, at thread distance < 32 in the
+// same warp (shuffles); only the remaining steps go through shared memory.  Same normalised network as above.
+__device__ __forceinline__ void cx(unsigned long long& lo, unsigned long long& hi) {
+    const unsigned long long a = lo, b = hi;
+    lo = a < b ? a : b;
+    hi = a < b ? b : a;
+}
+template <int E>
+__device__ __forceinline__ void regs_in_thread_steps(unsigned long long (&v)[E], int from_j) {
+#pragma unroll
+    for (int j = E / 2; j > 0; j >>= 1) {
+        if (j > from_j) continue;
+#pragma unroll
+        for (int e = 0; e < E; e++)
+            if ((e & j) == 0) cx(v[e], v[e + j]);
+    }
+}
+template <int E>
+__device__ void sort_regs(const unsigned long long* __restrict__ g, uint32_t n, uint32_t* __restrict__ out,
+                          unsigned long long* __restrict__ gkeep, unsigned long long* s) {
+    const uint32_t t = threadIdx.x;
+    const uint32_t N = SORT_THREADS * E;
+    unsigned long long v[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) v[e] = (t * E + e < n) ? g[t * E + e] : ~0ull;
+    // phase 1: sort the E keys of each thread
+#pragma unroll
+    for (int k = 2; k <= E; k <<= 1) {
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const int l = e ^ (k - 1);
+            if (l > e) cx(v[e], v[l]);
+        }
+        regs_in_thread_steps<E>(v, k >> 2);
+    }
+    // phase 2: merges across threads
+    for (uint32_t m = 2; m * E <= N; m <<= 1) {  // merge block of m threads (k = m*E keys)
+        unsigned long long pv[E];
+        {   // flip: partner thread t ^ (m-1), partner key E-1-e
+            const bool lower = (t & (m >> 1)) == 0;
+            if (m <= 32) {
+#pragma unroll
+                for (int e = 0; e < E; e++) pv[e] = __shfl_xor_sync(GSR_FULL, v[E - 1 - e], m - 1);
+            } else {
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < E; e++) s[e * SORT_THREADS + t] = v[e];
+                __syncthreads();
+                const uint32_t pt = t ^ (m - 1);
+#pragma unroll
+                for (int e = 0; e < E; e++) pv[e] = s[(E - 1 - e) * SORT_THREADS + pt];
+            }
+#pragma unroll
+            for (int e = 0; e < E; e++) v[e] = lower ? (v[e] < pv[e] ? v[e] : pv[e]) : (v[e] < pv[e] ? pv[e] : v[e]);
+        }
+        for (uint32_t jj = m >> 2; jj >= 1; jj >>= 1) {  // half-cleaners at thread distance jj
+            const bool lower = (t & jj) == 0;
+            if (jj < 32) {
+#pragma unroll
+                for (int e = 0; e < E; e++) pv[e] = __shfl_xor_sync(GSR_FULL, v[e], jj);
+            } else {
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < E; e++) s[e * SORT_THREADS + t] = v[e];
+                __syncthreads();
+                const uint32_t pt = t ^ jj;
+#pragma unroll
+                for (int e = 0; e < E; e++) pv[e] = s[e * SORT_THREADS + pt];
+            }
+#pragma unroll
+            for (int e = 0; e < E; e++) v[e] = lower ? (v[e] < pv[e] ? v[e] : pv[e]) : (v[e] < pv[e] ? pv[e] : v[e]);
+        }
+        regs_in_thread_steps<E>(v, E / 2);
+    }
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const uint32_t i = t * E + e;
+        if (i < n) {
+            out[i] = (uint32_t)v[e];
+            if (gkeep) gkeep[i] = v[e];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __restrict__ ranges, unsigned long long* __restrict__ pairs,
                                                              uint32_t* __restrict__ point_list,
                                                              const gsr_counters* __restrict__ counters, int keep_pairs) {
@@ -441,13 +548,12 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __rest
     uint32_t* out = point_list + rg.x;
     const uint32_t tid = threadIdx.x;
     if (n <= SORT_CAP) {
-        for (uint32_t i = tid; i < n; i += SORT_THREADS) s[i] = g[i];
-        __syncthreads();
-        sort_smem(s, n);
-        for (uint32_t i = tid; i < n; i += SORT_THREADS) {
-            out[i] = (uint32_t)s[i];
-            if (keep_pairs) g[i] = s[i];
-        }
+        unsigned long long* gk = keep_pairs ? g : nullptr;
+        if (n <= SORT_THREADS) sort_regs<1>(g, n, out, gk, s);
+        else if (n <= SORT_THREADS * 2) sort_regs<2>(g, n, out, gk, s);
+        else if (n <= SORT_THREADS * 4) sort_regs<4>(g, n, out, gk, s);
+        else if (n <= SORT_THREADS * 8) sort_regs<8>(g, n, out, gk, s);
+        else sort_regs<16>(g, n, out, gk, s);
         return;
     }
     // ---- large tile: chunks sorted in shared memory, cross-chunk steps in global (L2) memory ----
@@ -486,34 +592,21 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __rest
 // =====================================================================================================
 // Kernel 5: per-tile front-to-back alpha blend (forward.cu:261-378)
 // One CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel footprint.
+//   stage   : 256 list entries per batch -> 48-byte records in shared memory (registers prefetch the next batch)
+//   cull    : one splat per lane against the warp's footprint (footprint_may_touch, ~12 instructions), ballot
+//   compact : surviving records are copied, in order, into the warp's private queue (warp prefix via popc)
+//   blend   : the queue is walked by all 32 lanes with the reference's per-pixel arithmetic
 // =====================================================================================================
 constexpr int BLEND_THREADS = 256;
+constexpr int BLEND_QCAP = 96;  // queue entries per warp (flushed when fewer than 32 slots remain)
 
-// Conservative test: can the splat reach alpha >= 1/255 at any pixel centre of [X0,X1]x[Y0,Y1]?
-// The minimum of q(u,v) = a u^2 + 2 b u v + c v^2 over the box is on a face between the box and the
-// splat centre; power = -q/2 must be >= -tau.  The margin covers the rounding of both this bound and
-// the reference's own evaluation of `power` (a few ulp of the largest term), so a "false" is always a
-// pixel the reference skips too; a "true" only costs the exact per-pixel test.
-__device__ __forceinline__ bool splat_may_touch(const float4 r0, const float4 r1, float X0, float Y0, float X1, float Y1) {
-    const float a = r0.z, b = r0.w, c = r1.x, tau = r1.w;
-    const float u0 = r0.x - X1, u1 = r0.x - X0, v0 = r0.y - Y1, v1 = r0.y - Y0;
-    const float uc = fminf(fmaxf(0.f, u0), u1), vc = fminf(fmaxf(0.f, v0), v1);
-    if (!(a > 0.f && c > 0.f)) return true;  // degenerate conic: no culling
-    float qmin = 0.f;
-    if (uc != 0.f || vc != 0.f) {
-        qmin = 3.0e38f;
-        if (uc != 0.f) {
-            const float vs = fminf(fmaxf(-b * uc / c, v0), v1);
-            qmin = fminf(qmin, a * uc * uc + 2.f * b * uc * vs + c * vs * vs);
-        }
-        if (vc != 0.f) {
-            const float us = fminf(fmaxf(-b * vc / a, u0), u1);
-            qmin = fminf(qmin, a * us * us + 2.f * b * us * vc + c * vc * vc);
-        }
-    }
-    const float um = fmaxf(fabsf(u0), fabsf(u1)), vm = fmaxf(fabsf(v0), fabsf(v1));
-    const float mag = a * um * um + c * vm * vm + 2.f * fabsf(b) * um * vm;
-    return !(0.5f * qmin > tau + 1.0e-3f + 4.0e-6f * mag);
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
@@ -522,14 +615,18 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
                                                          float* __restrict__ out_depth, float* __restrict__ out_alpha,
                                                          uint32_t* __restrict__ n_contrib,
                                                          const gsr_counters* __restrict__ counters) {
-    __shared__ float4 sA[BLEND_THREADS], sB[BLEND_THREADS], sC[BLEND_THREADS];
+    __shared__ __align__(16) float4 sRec[BLEND_THREADS * 3];                       // staged batch, 48 B per splat
+    __shared__ __align__(16) float4 sQ[(BLEND_THREADS / 32) * BLEND_QCAP * 3];     // per-warp survivor queues
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.y * gx + blockIdx.x;
     const int X0 = blockIdx.x * GSR_TILE + (warp & 1) * 8, Y0 = blockIdx.y * GSR_TILE + (warp >> 1) * 4;
     const int pxi = X0 + (lane & 7), pyi = Y0 + (lane >> 3);
     const bool inside = pxi < W && pyi < H;
     const float pixx = (float)pxi, pixy = (float)pyi;
-    const float fX0 = (float)X0, fY0 = (float)Y0, fX1 = (float)(X0 + 7), fY1 = (float)(Y0 + 3);
+    const float cx = (float)X0 + FOOT_HX, cy = (float)Y0 + FOOT_HY;  // footprint centre
+    const uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(sRec);
+    const uint32_t q_base = (uint32_t)__cvta_generic_to_shared(sQ) + (uint32_t)warp * (BLEND_QCAP * 48);
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     uint2 range = ranges[tile];
     if (counters->overflow) range = make_uint2(0u, 0u);
@@ -539,6 +636,37 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
     uint32_t last = 0;
     bool done = !inside;
+    int qn = 0;  // entries in this warp's queue (warp-uniform)
+
+    // blend every queued splat into this lane's pixel (reference arithmetic, forward.cu:330-366)
+    auto drain = [&]() {
+        __syncwarp();
+        uint32_t qa = q_base;
+        for (int k = 0; k < qn; k++, qa += 48) {
+            if (!done) {
+                const float4 A = lds128(qa), B = lds128(qa + 16);
+                const float2 d = {A.x - pixx, A.y - pixy};
+                const float power = -0.5f * (A.z * d.x * d.x + B.x * d.y * d.y) - A.w * d.x * d.y;
+                if (power > 0.0f) continue;
+                const float alpha = min(0.99f, B.y * exp(power));
+                if (alpha < 1.0f / 255.0f) continue;
+                const float test_T = T * (1 - alpha);
+                if (test_T < 0.0001f) {
+                    done = true;
+                    continue;
+                }
+                const float4 Cc = lds128(qa + 32);
+                C0 += Cc.x * alpha * T;
+                C1 += Cc.y * alpha * T;
+                C2 += Cc.z * alpha * T;
+                Dp += B.z * alpha * T;
+                T = test_T;
+                last = __float_as_uint(Cc.w);
+            }
+        }
+        qn = 0;
+        __syncwarp();
+    };
 
     // software pipeline: records of batch b and the list entry of batch b+1 are in registers
     float4 ra = make_float4(0, 0, 0, 0), rb = ra, rc = ra;
@@ -549,12 +677,17 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
         ra = r[0]; rb = r[1]; rc = r[2];
     }
     if (BLEND_THREADS + tid < n) id_next = point_list[range.x + BLEND_THREADS + tid];
+    bool warp_done = false;
 
     for (int b = 0; b < nb; b++) {
-        // whole tile finished? (also the barrier that frees the staging buffers)
+        // whole tile finished? (also the barrier that frees the staging buffer)
         if (__syncthreads_count(done) == BLEND_THREADS) break;
         const int cnt = min(BLEND_THREADS, n - b * BLEND_THREADS);
-        if (tid < cnt) { sA[tid] = ra; sB[tid] = rb; sC[tid] = rc; }
+        if (tid < cnt) {
+            rc.w = __uint_as_float((uint32_t)(b * BLEND_THREADS + tid + 1));  // 1-based position in the tile list
+            const uint32_t sa = rec_base + (uint32_t)tid * 48;
+            sts128(sa, ra); sts128(sa + 16, rb); sts128(sa + 32, rc);
+        }
         __syncthreads();
         {
             const int nxt = (b + 1) * BLEND_THREADS + tid;
@@ -564,38 +697,31 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
             }
             if (nxt + BLEND_THREADS < n) id_next = point_list[range.x + nxt + BLEND_THREADS];
         }
-        if (__all_sync(GSR_FULL, done)) continue;
+        if (warp_done) continue;
         for (int base = 0; base < cnt; base += 32) {
             const int s = base + lane;
-            const bool keep = s < cnt && splat_may_touch(sA[s], sB[s], fX0, fY0, fX1, fY1);
-            unsigned mask = __ballot_sync(GSR_FULL, keep);
-            while (mask) {
-                const int j = base + __ffs(mask) - 1;
-                mask &= mask - 1;
-                if (!done) {
-                    const float4 A = sA[j], B = sB[j];
-                    const float2 d = {A.x - pixx, A.y - pixy};
-                    const float power = -0.5f * (A.z * d.x * d.x + B.x * d.y * d.y) - A.w * d.x * d.y;
-                    if (power > 0.0f) continue;
-                    const float alpha = min(0.99f, B.y * exp(power));
-                    if (alpha < 1.0f / 255.0f) continue;
-                    const float test_T = T * (1 - alpha);
-                    if (test_T < 0.0001f) {
-                        done = true;
-                        continue;
-                    }
-                    const float4 Cc = sC[j];
-                    C0 += Cc.x * alpha * T;
-                    C1 += Cc.y * alpha * T;
-                    C2 += Cc.z * alpha * T;
-                    Dp += B.z * alpha * T;
-                    T = test_T;
-                    last = (uint32_t)(b * BLEND_THREADS + j + 1);
+            const uint32_t sa = rec_base + (uint32_t)s * 48;
+            bool keep = false;
+            float4 A, B;
+            if (s < cnt) {
+                A = lds128(sa); B = lds128(sa + 16);
+                keep = footprint_may_touch(A.x - cx, A.y - cy, A.z, A.w, B.x, B.w);
+            }
+            const unsigned mask = __ballot_sync(GSR_FULL, keep);
+            if (mask) {
+                if (keep) {
+                    const uint32_t qa = q_base + (uint32_t)(qn + __popc(mask & lt_mask)) * 48;
+                    sts128(qa, A); sts128(qa + 16, B); sts128(qa + 32, lds128(sa + 32));
+                }
+                qn += __popc(mask);
+                if (qn > BLEND_QCAP - 32) {
+                    drain();
+                    if (__all_sync(GSR_FULL, done)) { warp_done = true; break; }
                 }
             }
-            if (__all_sync(GSR_FULL, done)) break;
         }
     }
+    if (qn) drain();
     if (inside) {
         const size_t pid = (size_t)W * pyi + pxi;
         const size_t HW = (size_t)H * W;

@@ -65,7 +65,7 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -121,7 +121,7 @@ def algorithmic_bytes(P, P_vis, R, M_used=16):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gaussians", type=int, default=3_000_000, help="override only for debugging; the metric is quoted at 3M")
@@ -204,11 +204,11 @@ def main():
             c = my_cams[cam_of_step(s)]
             return ref_cuda.forward(g["means3D"], g["opacities"], c[0:16], c[16:32], c[32:35], W_IMG, H_IMG, float(my_cams_host[cam_of_step(s), 35]),
                                     float(my_cams_host[cam_of_step(s), 36]), shs=g["shs"], scales=g["scales"], rotations=g["rotations"], sh_degree=3)
+        sampler = ClockSampler(local)
+        sampler.start()
         for s in range(Wm):
             ref_frame(s)
         torch.cuda.synchronize()
-        sampler = ClockSampler(local)
-        sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         Rs = []
@@ -257,11 +257,11 @@ def main():
     attempts = 0
     while True:
         attempts += 1
+        sampler = ClockSampler(local)
+        sampler.start()
         for s in range(Wm):
             frame(s, False)
         barrier()
-        sampler = ClockSampler(local)
-        sampler.start()
         _lib.check(_lib.lib.gsr_profile_begin(K), "gsr_profile_begin")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tickets = []
