@@ -41,7 +41,7 @@ class gsr_grads(C.Structure):
 
 class gsr_views(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("records", "cov3D", "clamped", "point_list", "sorted_keys", "ranges", "n_contrib",
-                                          "tile_count", "counters")]
+                                          "tile_count", "tile_big", "counters")]
 
 
 GSR_FLAG_FOR_BACKWARD = 1

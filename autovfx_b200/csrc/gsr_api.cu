@@ -73,6 +73,7 @@ int gsr_get_views(const gsr_workspace* ws, int32_t P, int32_t W, int32_t H, gsr_
     out->ranges = (const uint32_t*)(img + il.ranges);
     out->n_contrib = (const uint32_t*)(img + il.n_contrib);
     out->tile_count = (const uint32_t*)(img + il.tile_count);
+    out->tile_big = (const uint32_t*)(img + il.tile_big);
     out->counters = (const gsr_counters*)(img + il.counters);
     return GSR_OK;
 }

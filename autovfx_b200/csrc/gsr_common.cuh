@@ -21,17 +21,18 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 
 // ---- workspace layouts (pure functions of P / capacity / W,H) --------------------------------------
 struct GeomLayout {
-    size_t records, cov3D, clamped, total;
+    size_t records, ranks, cov3D, clamped, total;
     __host__ __device__ explicit GeomLayout(size_t P) {
         size_t o = 0;
         records = o; o = align_up(o + 48 * P, 256);
+        ranks = o;   o = align_up(o + 32 * P, 256);  // 8 x u32 in-tile ranks for Gaussians touching <= 8 tiles
         cov3D = o;   o = align_up(o + 24 * P, 256);
         clamped = o; o = align_up(o + P, 256);
         total = o + 256;
     }
 };
 struct ImageLayout {
-    size_t counters, tile_count, tile_fill, ranges, n_contrib, total;
+    size_t counters, tile_count, tile_big, tile_fill, ranges, n_contrib, total;
     int gx, gy, tiles;
     __host__ __device__ ImageLayout(int W, int H) {
         gx = (W + GSR_TILE - 1) / GSR_TILE;
@@ -39,14 +40,15 @@ struct ImageLayout {
         tiles = gx * gy;
         size_t o = 0;
         counters = o;   o = align_up(o + sizeof(gsr_counters), 256);
-        tile_count = o; o = align_up(o + 4 * (size_t)tiles, 256);
-        tile_fill = o;  o = align_up(o + 4 * (size_t)tiles, 256);
+        tile_count = o; o = align_up(o + 4 * (size_t)tiles, 256);  // instances of Gaussians touching <= 8 tiles (ranked)
+        tile_big = o;   o = align_up(o + 4 * (size_t)tiles, 256);  // instances of Gaussians touching > 8 tiles
+        tile_fill = o;  o = align_up(o + 4 * (size_t)tiles, 256);  // cursor for the latter, written by the scan
         ranges = o;     o = align_up(o + 8 * (size_t)tiles, 256);
         n_contrib = o;  o = align_up(o + 4 * (size_t)W * H, 256);
         total = o + 256;
     }
-    // bytes [0, zero_bytes) are cleared at the start of every frame (counters + tile_count + tile_fill)
-    __host__ __device__ size_t zero_bytes() const { return ranges; }
+    // bytes [0, zero_bytes) are cleared at the start of every frame (counters + tile_count + tile_big)
+    __host__ __device__ size_t zero_bytes() const { return tile_fill; }
 };
 struct BinLayout {
     size_t pairs, point_list, total, capacity;
@@ -145,30 +147,34 @@ __device__ __forceinline__ void for_each_tile(int x0, int y0, int x1, int y1, in
 
 // ---- warp-footprint culling shared by the forward and backward blend kernels ------------------------------
 // A warp owns an 8x4 pixel footprint (half extents FOOT_HX x FOOT_HY around its centre).  A splat can reach
-// alpha >= 1/255 at a pixel p only if q(p) = (p-mu)^T A (p-mu) <= 2*tau with tau = ln(255*opacity) (A = conic).
-// sqrt(q) is a norm, so q(p) >= (sqrt(q(c)) - rho)^2 for every pixel of the footprint, where c is the
-// footprint centre and rho^2 = a hx^2 + 2|b| hx hy + c hy^2 bounds sqrt(q) of any centre-to-pixel offset.
-// The splat is therefore irrelevant for the whole footprint unless q(c) <= (sqrt(2 tau) + rho)^2 =: thr.
-// thr depends only on the splat, so preprocess stores it in the record and the test in the blend loop is one
-// quadratic form and one compare.  Margins: tau is inflated by 1e-3, thr by 1e-4 relative, and the
-// comparison discounts 4e-6 of the magnitude of the terms (float rounding here and in the reference's own
-// evaluation of `power`), so a rejected (footprint, splat) pair is one the reference skips at every pixel.
+// alpha >= 1/255 at a pixel p only where power(p) = -q(p)/2 >= -tau, q(p) = (mu-p)^T A (mu-p) (A = conic),
+// tau = ln(255*opacity).  The test computes the exact minimum of the convex form q over the footprint: it lies
+// on one of the two box faces that face the splat centre, where q restricted to the face is a parabola.  Both
+// face minima are evaluated branch-free (a face that does not separate the box from the centre yields a value
+// >= the true minimum, so taking the smaller of the two is always right).  The reciprocals are approximate
+// (MUFU.RCP): an imprecise minimiser only raises the evaluated q by a second-order amount.  Margins: 1e-3 on
+// tau and 4e-6 of the magnitude of the terms (float rounding here and in the reference's own evaluation of
+// `power`), so a rejected (footprint, splat) pair is one the reference skips at every pixel of the footprint.
+// Non positive-definite conics and NaNs are never culled.
 constexpr float FOOT_HX = 3.5f, FOOT_HY = 1.5f;
-__device__ __forceinline__ float footprint_threshold(float a, float b, float c, float opacity) {
-    if (!(a > 0.f && c > 0.f && a * c - b * b > 0.f)) return 3.0e38f;  // not positive definite: never cull
-    const float tau = __logf(255.0f * opacity) + 1.0e-3f;
-    if (tau != tau) return 3.0e38f;  // NaN opacity: never cull
-    if (tau < 0.f) return -1.0f;     // opacity < 1/255: alpha < 1/255 everywhere
-    const float rho = sqrtf(a * FOOT_HX * FOOT_HX + 2.f * fabsf(b) * FOOT_HX * FOOT_HY + c * FOOT_HY * FOOT_HY);
-    const float s = sqrtf(2.f * tau) + rho;
-    return s * s * 1.0001f + 1.0e-4f;
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
+__device__ __forceinline__ float footprint_tau(float opacity) { return __logf(255.0f * opacity); }
 // dx, dy: splat centre minus footprint centre
-__device__ __forceinline__ bool footprint_may_touch(float dx, float dy, float a, float b, float c, float thr) {
-    const float ax = a * dx * dx, cy = c * dy * dy, bxy = b * dx * dy;
-    const float q = ax + cy + 2.f * bxy;
-    const float mag = ax + cy + 2.f * fabsf(bxy);
-    return !(q - 4.0e-6f * mag > thr);
+__device__ __forceinline__ bool footprint_may_touch(float dx, float dy, float a, float b, float c, float tau) {
+    const float uc = dx - fminf(fmaxf(dx, -FOOT_HX), FOOT_HX);  // signed distance of the box from the centre, 0 if it straddles
+    const float vc = dy - fminf(fmaxf(dy, -FOOT_HY), FOOT_HY);
+    const float vs = fminf(fmaxf(-b * uc * rcp_approx(c), dy - FOOT_HY), dy + FOOT_HY);  // minimiser on the face u = uc
+    const float us = fminf(fmaxf(-b * vc * rcp_approx(a), dx - FOOT_HX), dx + FOOT_HX);  // minimiser on the face v = vc
+    const float q1 = a * uc * uc + 2.f * b * uc * vs + c * vs * vs;
+    const float q2 = a * us * us + 2.f * b * us * vc + c * vc * vc;
+    const float um = fabsf(dx) + FOOT_HX, vm = fabsf(dy) + FOOT_HY;
+    const float mag = a * um * um + c * vm * vm + 2.f * fabsf(b) * um * vm;
+    const bool pd = a > 0.f && c > 0.f;
+    return !(pd && 0.5f * fminf(q1, q2) > tau + 1.0e-3f + 4.0e-6f * mag);
 }
 
 // SH basis constants (auxiliary.h:22-39)

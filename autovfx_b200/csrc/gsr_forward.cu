@@ -5,7 +5,7 @@
 // identifyTileRanges, CUB InclusiveSum + DeviceRadixSort, forward.cu:261-378 renderCUDA).
 //
 // Pipeline differences (results are identical):
-//   * one 48-byte record per visible Gaussian {x,y,conic.a,conic.b | conic.c,opacity,depth,thr | r,g,b,-}
+//   * one 48-byte record per visible Gaussian {x,y,conic.a,conic.b | conic.c,opacity,depth,tau | r,g,b,-}
 //     replaces the reference's five SoA arrays, so the blend gathers 3 aligned float4 per instance;
 //   * SH coefficients are staged into shared memory with coalesced 16-byte cp.async by each warp, only for
 //     the Gaussians that survived culling, and read back conflict-free (row stride 13 float4);
@@ -54,6 +54,8 @@ struct PreParams {
     uint8_t* clamped;
     int* radii;
     uint32_t* tile_count;
+    uint32_t* tile_big;
+    uint32_t* ranks;
     gsr_counters* counters;
 };
 
@@ -246,10 +248,26 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
     }
     if (!vis) { x0 = y0 = x1 = y1 = 0; }
 
-    // per-tile histogram: one RED per (Gaussian, tile) instance
+    // Per-tile histogram.  Gaussians touching <= 8 tiles take a ranked ticket per tile (atomic with return; the
+    // results are only needed at the end of the kernel, so the round trips overlap the SH work) and store the
+    // ranks for k_emit, which then needs no atomics.  Larger rectangles are counted separately, warp-cooperatively.
+    uint32_t rk[8];
+    const int rect_w = x1 - x0, rect_n = rect_w * (y1 - y0);
+    if (rect_n > 0 && rect_n <= 8) {
+        int tx = x0, ty = y0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (k < rect_n) {
+                rk[k] = atomicAdd(&p.tile_count[ty * p.gx + tx], 1u);
+                if (++tx == x1) { tx = x0; ty++; }
+            }
+        }
+    }
     {
-        uint32_t* tc = p.tile_count;
-        for_each_tile<8>(x0, y0, x1, y1, p.gx, 0u, 0u, [&](int tile, uint32_t, uint32_t) { atomicAdd(&tc[tile], 1u); });
+        const bool big = rect_n > 8;
+        uint32_t* tb = p.tile_big;
+        for_each_tile<0>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, p.gx, 0u, 0u,
+                         [&](int tile, uint32_t, uint32_t) { atomicAdd(&tb[tile], 1u); });
     }
 
     // colour
@@ -294,8 +312,13 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
         if (vis) {
             float4* rec = p.records + 3 * (size_t)idx;
             rec[0] = make_float4(px, py, con_a, con_b);
-            rec[1] = make_float4(con_c, opacity, depth, footprint_threshold(con_a, con_b, con_c, opacity));
+            rec[1] = make_float4(con_c, opacity, depth, footprint_tau(opacity));
             rec[2] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+            if (rect_n <= 8) {
+                uint4* rr = reinterpret_cast<uint4*>(p.ranks + 8 * (size_t)idx);
+                rr[0] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
+                if (rect_n > 4) rr[1] = make_uint4(rk[4], rk[5], rk[6], rk[7]);
+            }
             if (p.for_backward) {
                 if (p.cov3D_precomp == nullptr) {
 #pragma unroll
@@ -312,7 +335,8 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
 // =====================================================================================================
 // Kernel 2: exclusive scan over the per-tile counts -> ranges, R, overflow flag (single CTA)
 // =====================================================================================================
-__global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
+__global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_big,
+                                                    uint32_t* __restrict__ tile_fill, uint2* __restrict__ ranges,
                                                     gsr_counters* counters, int tiles, uint32_t capacity) {
     __shared__ uint32_t warp_sum[32];
     __shared__ uint32_t warp_max[32];
@@ -321,7 +345,7 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
     const int b = tid * per, e = min(tiles, b + per);
     uint32_t local = 0, lmax = 0;
     for (int t = b; t < e; t++) {
-        uint32_t c = tile_count[t];
+        uint32_t c = tile_count[t] + tile_big[t];
         local += c;
         lmax = max(lmax, c);
     }
@@ -354,21 +378,21 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
     __syncthreads();
     uint32_t start = warp_sum[warp] + (incl - local);
     for (int t = b; t < e; t++) {
-        uint32_t c = tile_count[t];
+        const uint32_t cs = tile_count[t], c = cs + tile_big[t];
         ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
+        tile_fill[t] = start + cs;  // absolute cursor of the tile's un-ranked (large-rectangle) instances
         start += c;
     }
 }
-
 
 // =====================================================================================================
 // Kernel 3: scatter one (depth bits, Gaussian id) pair per (Gaussian, tile) instance into the tile's bucket
 // (the work of duplicateWithKeys, rasterizer_impl.cu:70-111; the tile id is implicit in the bucket)
 // =====================================================================================================
 __global__ void __launch_bounds__(256) k_emit(int P, int gx, int gy, const int* __restrict__ radii,
-                                              const float4* __restrict__ records, const uint2* __restrict__ ranges,
-                                              uint32_t* __restrict__ tile_fill, uint2* __restrict__ pairs,
-                                              const gsr_counters* __restrict__ counters) {
+                                              const float4* __restrict__ records, const uint32_t* __restrict__ ranks,
+                                              const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_fill,
+                                              uint2* __restrict__ pairs, const gsr_counters* __restrict__ counters) {
     if (counters->overflow) return;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
@@ -381,29 +405,28 @@ __global__ void __launch_bounds__(256) k_emit(int P, int gx, int gy, const int* 
             tile_rect(r0.x, r0.y, r, gx, gy, x0, y0, x1, y1);
         }
     }
-    // Small rectangles (<= 8 tiles): issue all position atomics first, then the dependent stores, so the
-    // atomic round trips overlap.  Large rectangles are walked by the whole warp (for_each_tile's big path).
+    // <= 8 tiles: the in-tile rank of every instance was drawn by k_preprocess -> plain scatter, no atomics
     const int w = x1 - x0, cnt = w * (y1 - y0);
     if (cnt > 0 && cnt <= 8) {
-        uint32_t pos[8];
+        const uint4* rr = reinterpret_cast<const uint4*>(ranks + 8 * (size_t)idx);
+        const uint4 ra = rr[0];
+        uint4 rb = make_uint4(0, 0, 0, 0);
+        if (cnt > 4) rb = rr[1];
+        const uint32_t rk[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+        const uint2 pr = make_uint2((uint32_t)idx, dbits);  // little endian: u64 = (depth bits << 32) | id
         int tx = x0, ty = y0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             if (k < cnt) {
-                const int tile = ty * gx + tx;
-                pos[k] = ranges[tile].x + atomicAdd(&tile_fill[tile], 1u);
+                pairs[ranges[ty * gx + tx].x + rk[k]] = pr;
                 if (++tx == x1) { tx = x0; ty++; }
             }
         }
-        const uint2 pr = make_uint2((uint32_t)idx, dbits);  // little endian: u64 = (depth bits << 32) | id
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (k < cnt) pairs[pos[k]] = pr;
     }
+    // > 8 tiles: walked by the whole warp, positions from the per-tile cursor initialised by k_tile_scan
     const bool big = cnt > 8;
     for_each_tile<0>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, (uint32_t)idx, dbits, [&](int tile, uint32_t id, uint32_t d) {
-        const uint32_t p2 = ranges[tile].x + atomicAdd(&tile_fill[tile], 1u);
-        pairs[p2] = make_uint2(id, d);
+        pairs[atomicAdd(&tile_fill[tile], 1u)] = make_uint2(id, d);
     });
 }
 
@@ -593,7 +616,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __rest
 // Kernel 5: per-tile front-to-back alpha blend (forward.cu:261-378)
 // One CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel footprint.
 //   stage   : 256 list entries per batch -> 48-byte records in shared memory (registers prefetch the next batch)
-//   cull    : one splat per lane against the warp's footprint (footprint_may_touch, ~12 instructions), ballot
+//   cull    : one splat per lane against the warp's footprint (footprint_may_touch: exact box minimum of the quadratic form), ballot
 //   compact : surviving records are copied, in order, into the warp's private queue (warp prefix via popc)
 //   blend   : the queue is walked by all 32 lanes with the reference's per-pixel arithmetic
 // =====================================================================================================
@@ -844,7 +867,8 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     pp.scales = f->scales; pp.rotations = f->rotations; pp.cov3D_precomp = f->cov3D_precomp;
     pp.view = f->viewmatrix; pp.proj = f->projmatrix; pp.campos = f->campos;
     pp.records = (float4*)(geo + gl.records); pp.cov3D = (float*)(geo + gl.cov3D); pp.clamped = (uint8_t*)(geo + gl.clamped);
-    pp.radii = radii; pp.tile_count = (uint32_t*)(img + il.tile_count); pp.counters = counters;
+    pp.radii = radii; pp.tile_count = (uint32_t*)(img + il.tile_count); pp.tile_big = (uint32_t*)(img + il.tile_big);
+    pp.ranks = (uint32_t*)(geo + gl.ranks); pp.counters = counters;
 
     if (f->colors_precomp) launch_pre<-1>(false, pp, st);
     else {
@@ -861,11 +885,11 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     if (rc) return rc;
 
     uint2* ranges = (uint2*)(img + il.ranges);
-    k_tile_scan<<<1, 1024, 0, st>>>(pp.tile_count, ranges, counters, il.tiles, (uint32_t)(cap > 0xffffffffull ? 0xffffffffull : cap));
+    k_tile_scan<<<1, 1024, 0, st>>>(pp.tile_count, pp.tile_big, (uint32_t*)(img + il.tile_fill), ranges, counters, il.tiles, (uint32_t)(cap > 0xffffffffull ? 0xffffffffull : cap));
     prof_mark(2, st);
     if ((rc = check_launch("gsr_forward/tile_scan", debug, st))) return rc;
 
-    k_emit<<<(f->P + 255) / 256, 256, 0, st>>>(f->P, il.gx, il.gy, radii, pp.records, ranges, (uint32_t*)(img + il.tile_fill),
+    k_emit<<<(f->P + 255) / 256, 256, 0, st>>>(f->P, il.gx, il.gy, radii, pp.records, pp.ranks, ranges, (uint32_t*)(img + il.tile_fill),
                                                (uint2*)(bin + bl.pairs), counters);
     prof_mark(3, st);
     if ((rc = check_launch("gsr_forward/emit", debug, st))) return rc;

@@ -391,6 +391,6 @@ def debug_views(workspaces, P: int, W: int, H: int) -> Dict[str, torch.Tensor]:
         "sorted_keys": view(binning, v.sorted_keys, 8 * cap, torch.int64, (cap,)),
         "ranges": view(image, v.ranges, 8 * tiles, torch.int32, (tiles, 2)),
         "n_contrib": view(image, v.n_contrib, 4 * W * H, torch.int32, (H, W)),
-        "tile_count": view(image, v.tile_count, 4 * tiles, torch.int32, (tiles,)),
+        "tile_count": view(image, v.tile_count, 4 * tiles, torch.int32, (tiles,)) + view(image, v.tile_big, 4 * tiles, torch.int32, (tiles,)),
         "counters": view(image, v.counters, 32, torch.int32, (8,)),
     }

@@ -146,7 +146,8 @@ typedef struct gsr_views {
     const uint64_t* sorted_keys; /* [capacity] (GSR_FLAG_SORTED_KEYS only)                          */
     const uint32_t* ranges;      /* [tiles,2]                                                       */
     const uint32_t* n_contrib;   /* [H,W]  (GSR_FLAG_FOR_BACKWARD only)                             */
-    const uint32_t* tile_count;  /* [tiles]                                                         */
+    const uint32_t* tile_count;  /* [tiles] instances of Gaussians touching <= 8 tiles                   */
+    const uint32_t* tile_big;    /* [tiles] instances of Gaussians touching > 8 tiles                    */
     const gsr_counters* counters;
 } gsr_views;
 int gsr_get_views(const gsr_workspace* ws, int32_t P, int32_t W, int32_t H, gsr_views* out);

@@ -124,6 +124,23 @@ def time_both(a, iters=20):
         torch.cuda.synchronize()
         print("  timing %-5s %.3f ms/frame" % (nm, e0.elapsed_time(e1) / iters))
     print("  ours stats:", R.last_frame_stats())
+    # forward + backward (BASELINE config 3): public autograd API vs the reference's forward+backward
+    dc, dd, da = Hh.image_grads(a, device=a["means3D"].device)
+    def ours_fb():
+        Hh.ours_backward(a, dc, dd, da)
+    def ref_fb():
+        ref_cuda.backward(Hh.run_ref(a), dc, dd, da)
+    for nm, fn in (("ours fwd+bwd", ours_fb), ("ref  fwd+bwd", ref_fb)):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        print("  timing %-13s %.3f ms/iter" % (nm, e0.elapsed_time(e1) / 5))
 
 
 def main():
