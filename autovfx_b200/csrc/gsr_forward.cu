@@ -473,89 +473,104 @@ __device__ void sort_smem(unsigned long long* s, uint32_t n) {
     }
 }
 
-// ---- register-blocked variant for n <= SORT_CAP ------------------------------------------------------------
-// Thread t holds the E consecutive keys [tE, tE+E) in registers (N = 256*E >= n, missing keys are +inf).
-// Compare-exchange partners at element distance < E are in the same thread, at thread distance < 32 in the
-// same warp (shuffles); only the remaining steps go through shared memory.  Same normalised network as above.
-__device__ __forceinline__ void cx(unsigned long long& lo, unsigned long long& hi) {
-    const unsigned long long a = lo, b = hi;
-    lo = a < b ? a : b;
-    hi = a < b ? b : a;
-}
-template <int E>
-__device__ __forceinline__ void regs_in_thread_steps(unsigned long long (&v)[E], int from_j) {
-#pragma unroll
-    for (int j = E / 2; j > 0; j >>= 1) {
-        if (j > from_j) continue;
-#pragma unroll
-        for (int e = 0; e < E; e++)
-            if ((e & j) == 0) cx(v[e], v[e + j]);
+// ---- bucket sort for n <= SORT_CAP (the common case) -----------------------------------------------------
+// The keys of one tile are (depth bits << 32 | id) with depths spread over [zmin, zmax] of the tile.  A monotone
+// linear quantisation of the depth into B >= n/2 buckets (float subtract, multiply by a positive constant and
+// truncation are all monotone) puts ~1 key in each bucket, so the sort is: histogram (shared atomics, the
+// returned value is the key's slot in its bucket) -> exclusive scan -> scatter -> per-bucket insertion sort on
+// the full 64-bit key, O(n) work instead of the O(n log^2 n) network.  The result is the unique ascending
+// order, whatever order the atomics happened in.  Buckets holding more than SORT_BUCKET_MAX keys (all depths
+// equal, or extreme clustering) trigger the generic network on the same shared array instead.
+constexpr int SORT_BUCKETS = 2048;
+constexpr int SORT_BUCKET_MAX = 24;
+
+__device__ void sort_bucket(const unsigned long long* __restrict__ g, uint32_t n, uint32_t* __restrict__ out,
+                            unsigned long long* __restrict__ gkeep, unsigned long long* s, uint32_t* hist /*[SORT_BUCKETS+1]*/) {
+    __shared__ uint32_t red_min[SORT_THREADS / 32], red_max[SORT_THREADS / 32], wsum[SORT_THREADS / 32];
+    __shared__ int fallback;
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t B = min((uint32_t)SORT_BUCKETS, max(32u, next_pow2(n)));
+    // the keys are read three times from global memory (L2 hits after the first pass) instead of being held in
+    // up to 32 registers per thread: min/max, bucket + ticket, scatter
+    uint32_t dmin = 0xffffffffu, dmax = 0u;
+    for (uint32_t i = t; i < n; i += SORT_THREADS) {
+        const uint32_t d = (uint32_t)(g[i] >> 32);
+        dmin = min(dmin, d);
+        dmax = max(dmax, d);
     }
-}
-template <int E>
-__device__ void sort_regs(const unsigned long long* __restrict__ g, uint32_t n, uint32_t* __restrict__ out,
-                          unsigned long long* __restrict__ gkeep, unsigned long long* s) {
-    const uint32_t t = threadIdx.x;
-    const uint32_t N = SORT_THREADS * E;
-    unsigned long long v[E];
 #pragma unroll
-    for (int e = 0; e < E; e++) v[e] = (t * E + e < n) ? g[t * E + e] : ~0ull;
-    // phase 1: sort the E keys of each thread
+    for (int o = 16; o > 0; o >>= 1) {
+        dmin = min(dmin, __shfl_xor_sync(GSR_FULL, dmin, o));
+        dmax = max(dmax, __shfl_xor_sync(GSR_FULL, dmax, o));
+    }
+    if (lane == 0) { red_min[warp] = dmin; red_max[warp] = dmax; }
+    if (t == 0) fallback = 0;
+    for (uint32_t b = t; b <= B; b += SORT_THREADS) hist[b] = 0;
+    __syncthreads();
 #pragma unroll
-    for (int k = 2; k <= E; k <<= 1) {
+    for (int w = 0; w < SORT_THREADS / 32; w++) { dmin = min(dmin, red_min[w]); dmax = max(dmax, red_max[w]); }
+    const float zmin = __uint_as_float(dmin), zmax = __uint_as_float(dmax);  // positive floats: bit order == value order
+    const float scale = zmax > zmin ? (float)(B - 1) / (zmax - zmin) : 0.f;
+    // ticket = (bucket << 16) | slot-in-bucket, parked in the output array until the scatter (a bucket with
+    // >= 65536 keys cannot occur: n <= SORT_CAP)
+    for (uint32_t i = t; i < n; i += SORT_THREADS) {
+        const float d = __uint_as_float((uint32_t)(g[i] >> 32));
+        const uint32_t b = min(B - 1, (uint32_t)((d - zmin) * scale));
+        out[i] = (b << 16) | atomicAdd(&hist[b], 1u);
+    }
+    __syncthreads();
+    {   // exclusive scan of hist[0..B) in place, hist[B] = n
+        const uint32_t per = B / SORT_THREADS > 0 ? B / SORT_THREADS : 1;  // B is a power of two >= 32
+        const uint32_t b0 = t * per;
+        uint32_t loc[SORT_BUCKETS / SORT_THREADS];
+        uint32_t sum = 0;
 #pragma unroll
-        for (int e = 0; e < E; e++) {
-            const int l = e ^ (k - 1);
-            if (l > e) cx(v[e], v[l]);
+        for (uint32_t k = 0; k < SORT_BUCKETS / SORT_THREADS; k++) {
+            loc[k] = 0;
+            if (k < per && b0 + k < B) { loc[k] = hist[b0 + k]; }
+            sum += loc[k];
         }
-        regs_in_thread_steps<E>(v, k >> 2);
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(GSR_FULL, incl, o);
+            if (lane >= o) incl += x;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        uint32_t base = incl - sum;
+#pragma unroll
+        for (int w = 0; w < SORT_THREADS / 32; w++) base += (w < (int)warp) ? wsum[w] : 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < SORT_BUCKETS / SORT_THREADS; k++) {
+            if (k < per && b0 + k < B) { hist[b0 + k] = base; base += loc[k]; }
+        }
+        if (t == 0) hist[B] = n;
     }
-    // phase 2: merges across threads
-    for (uint32_t m = 2; m * E <= N; m <<= 1) {  // merge block of m threads (k = m*E keys)
-        unsigned long long pv[E];
-        {   // flip: partner thread t ^ (m-1), partner key E-1-e
-            const bool lower = (t & (m >> 1)) == 0;
-            if (m <= 32) {
-#pragma unroll
-                for (int e = 0; e < E; e++) pv[e] = __shfl_xor_sync(GSR_FULL, v[E - 1 - e], m - 1);
-            } else {
-                __syncthreads();
-#pragma unroll
-                for (int e = 0; e < E; e++) s[e * SORT_THREADS + t] = v[e];
-                __syncthreads();
-                const uint32_t pt = t ^ (m - 1);
-#pragma unroll
-                for (int e = 0; e < E; e++) pv[e] = s[(E - 1 - e) * SORT_THREADS + pt];
+    __syncthreads();
+    for (uint32_t i = t; i < n; i += SORT_THREADS) {
+        const uint32_t tk = out[i];
+        s[hist[tk >> 16] + (tk & 0xffffu)] = g[i];
+    }
+    __syncthreads();
+    for (uint32_t b = t; b < B; b += SORT_THREADS) {  // order the few keys that share a bucket
+        const uint32_t lo = hist[b], c = hist[b + 1] - lo;
+        if (c > (uint32_t)SORT_BUCKET_MAX) fallback = 1;
+        else if (c > 1) {
+            for (uint32_t i = 1; i < c; i++) {
+                const unsigned long long x = s[lo + i];
+                uint32_t j = i;
+                while (j > 0 && s[lo + j - 1] > x) { s[lo + j] = s[lo + j - 1]; j--; }
+                s[lo + j] = x;
             }
-#pragma unroll
-            for (int e = 0; e < E; e++) v[e] = lower ? (v[e] < pv[e] ? v[e] : pv[e]) : (v[e] < pv[e] ? pv[e] : v[e]);
         }
-        for (uint32_t jj = m >> 2; jj >= 1; jj >>= 1) {  // half-cleaners at thread distance jj
-            const bool lower = (t & jj) == 0;
-            if (jj < 32) {
-#pragma unroll
-                for (int e = 0; e < E; e++) pv[e] = __shfl_xor_sync(GSR_FULL, v[e], jj);
-            } else {
-                __syncthreads();
-#pragma unroll
-                for (int e = 0; e < E; e++) s[e * SORT_THREADS + t] = v[e];
-                __syncthreads();
-                const uint32_t pt = t ^ jj;
-#pragma unroll
-                for (int e = 0; e < E; e++) pv[e] = s[e * SORT_THREADS + pt];
-            }
-#pragma unroll
-            for (int e = 0; e < E; e++) v[e] = lower ? (v[e] < pv[e] ? v[e] : pv[e]) : (v[e] < pv[e] ? pv[e] : v[e]);
-        }
-        regs_in_thread_steps<E>(v, E / 2);
     }
-#pragma unroll
-    for (int e = 0; e < E; e++) {
-        const uint32_t i = t * E + e;
-        if (i < n) {
-            out[i] = (uint32_t)v[e];
-            if (gkeep) gkeep[i] = v[e];
-        }
+    __syncthreads();
+    if (fallback) sort_smem(s, n);  // ends with a barrier
+    for (uint32_t i = t; i < n; i += SORT_THREADS) {
+        const unsigned long long x = s[i];
+        out[i] = (uint32_t)x;
+        if (gkeep) gkeep[i] = x;
     }
 }
 
@@ -564,6 +579,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __rest
                                                              const gsr_counters* __restrict__ counters, int keep_pairs) {
     if (counters->overflow) return;
     __shared__ unsigned long long s[SORT_CAP];
+    __shared__ uint32_t hist[SORT_BUCKETS + 1];
     const uint2 rg = ranges[blockIdx.x];
     const uint32_t n = rg.y - rg.x;
     if (n == 0) return;
@@ -571,12 +587,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __rest
     uint32_t* out = point_list + rg.x;
     const uint32_t tid = threadIdx.x;
     if (n <= SORT_CAP) {
-        unsigned long long* gk = keep_pairs ? g : nullptr;
-        if (n <= SORT_THREADS) sort_regs<1>(g, n, out, gk, s);
-        else if (n <= SORT_THREADS * 2) sort_regs<2>(g, n, out, gk, s);
-        else if (n <= SORT_THREADS * 4) sort_regs<4>(g, n, out, gk, s);
-        else if (n <= SORT_THREADS * 8) sort_regs<8>(g, n, out, gk, s);
-        else sort_regs<16>(g, n, out, gk, s);
+        sort_bucket(g, n, out, keep_pairs ? g : nullptr, s, hist);
         return;
     }
     // ---- large tile: chunks sorted in shared memory, cross-chunk steps in global (L2) memory ----
