@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __rest
 //   blend   : the queue is walked by all 32 lanes with the reference's per-pixel arithmetic
 // =====================================================================================================
 constexpr int BLEND_THREADS = 256;
-constexpr int BLEND_QCAP = 96;  // queue entries per warp (flushed when fewer than 32 slots remain)
+constexpr int BLEND_QCAP = 64;  // queue entries per warp (flushed when fewer than 32 slots remain)
 
 __device__ __forceinline__ float4 lds128(uint32_t a) {
     float4 v;
@@ -667,36 +667,37 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
     const int n = (int)(range.y - range.x);
     const int nb = (n + BLEND_THREADS - 1) / BLEND_THREADS;
 
-    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
+    // T is the running transmittance while the pixel is live.  When the pixel terminates (forward.cu:349-354) its
+    // final transmittance moves to T_out and T becomes 0, so that every later splat fails the same `T(1-a) < 1e-4`
+    // test on its own: no separate per-iteration "done" branch is needed.  Pixels outside the image start dead.
+    float T = inside ? 1.0f : 0.0f, T_out = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
     uint32_t last = 0;
-    bool done = !inside;
     int qn = 0;  // entries in this warp's queue (warp-uniform)
 
     // blend every queued splat into this lane's pixel (reference arithmetic, forward.cu:330-366)
     auto drain = [&]() {
         __syncwarp();
         uint32_t qa = q_base;
+#pragma unroll 4
         for (int k = 0; k < qn; k++, qa += 48) {
-            if (!done) {
-                const float4 A = lds128(qa), B = lds128(qa + 16);
-                const float2 d = {A.x - pixx, A.y - pixy};
-                const float power = -0.5f * (A.z * d.x * d.x + B.x * d.y * d.y) - A.w * d.x * d.y;
-                if (power > 0.0f) continue;
-                const float alpha = min(0.99f, B.y * exp(power));
-                if (alpha < 1.0f / 255.0f) continue;
-                const float test_T = T * (1 - alpha);
-                if (test_T < 0.0001f) {
-                    done = true;
-                    continue;
-                }
-                const float4 Cc = lds128(qa + 32);
-                C0 += Cc.x * alpha * T;
-                C1 += Cc.y * alpha * T;
-                C2 += Cc.z * alpha * T;
-                Dp += B.z * alpha * T;
-                T = test_T;
-                last = __float_as_uint(Cc.w);
+            const float4 A = lds128(qa), B = lds128(qa + 16);
+            const float2 d = {A.x - pixx, A.y - pixy};
+            const float power = -0.5f * (A.z * d.x * d.x + B.x * d.y * d.y) - A.w * d.x * d.y;
+            if (power > 0.0f) continue;
+            const float alpha = min(0.99f, B.y * exp(power));
+            if (alpha < 1.0f / 255.0f) continue;
+            const float test_T = T * (1 - alpha);
+            if (test_T < 0.0001f) {
+                if (T != 0.0f) { T_out = T; T = 0.0f; }
+                continue;
             }
+            const float4 Cc = lds128(qa + 32);
+            C0 += Cc.x * alpha * T;
+            C1 += Cc.y * alpha * T;
+            C2 += Cc.z * alpha * T;
+            Dp += B.z * alpha * T;
+            T = test_T;
+            last = __float_as_uint(Cc.w);
         }
         qn = 0;
         __syncwarp();
@@ -715,7 +716,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
 
     for (int b = 0; b < nb; b++) {
         // whole tile finished? (also the barrier that frees the staging buffer)
-        if (__syncthreads_count(done) == BLEND_THREADS) break;
+        if (__syncthreads_count(T == 0.0f) == BLEND_THREADS) break;
         const int cnt = min(BLEND_THREADS, n - b * BLEND_THREADS);
         if (tid < cnt) {
             rc.w = __uint_as_float((uint32_t)(b * BLEND_THREADS + tid + 1));  // 1-based position in the tile list
@@ -750,20 +751,21 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
                 qn += __popc(mask);
                 if (qn > BLEND_QCAP - 32) {
                     drain();
-                    if (__all_sync(GSR_FULL, done)) { warp_done = true; break; }
+                    if (__all_sync(GSR_FULL, T == 0.0f)) { warp_done = true; break; }
                 }
             }
         }
     }
     if (qn) drain();
     if (inside) {
+        if (T != 0.0f) T_out = T;  // pixel still live at the end of the list
         const size_t pid = (size_t)W * pyi + pxi;
         const size_t HW = (size_t)H * W;
-        out_alpha[pid] = 1 - T;
+        out_alpha[pid] = 1 - T_out;
         if (n_contrib) n_contrib[pid] = last;
-        out_color[pid] = C0 + T * bg[0];
-        out_color[HW + pid] = C1 + T * bg[1];
-        out_color[2 * HW + pid] = C2 + T * bg[2];
+        out_color[pid] = C0 + T_out * bg[0];
+        out_color[HW + pid] = C1 + T_out * bg[1];
+        out_color[2 * HW + pid] = C2 + T_out * bg[2];
         out_depth[pid] = Dp;
     }
 }

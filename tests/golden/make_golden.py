@@ -18,7 +18,7 @@ from oracle import ref_cuda  # noqa: E402
 
 CASES = {  # name -> store gradients?
     "config1": ("fw+small_grads",), "small_sh": ("fw+grads",), "small_deg1_m25": ("fw+grads",), "small_precomp": ("fw+grads",),
-    "big_splats": ("fw+grads",), "dense_tile": ("fw",),
+    "big_splats": ("fw+grads",), "dense_tile": ("fw",), "coplanar": ("fw",),
 }
 
 

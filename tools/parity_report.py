@@ -146,7 +146,7 @@ def time_both(a, iters=20):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--big", action="store_true")
-    ap.add_argument("--cases", default="config1,small_sh,small_deg1_m25,small_precomp,big_splats,dense_tile")
+    ap.add_argument("--cases", default="config1,small_sh,small_deg1_m25,small_precomp,big_splats,dense_tile,coplanar")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     print("device:", torch.cuda.get_device_name(0))
