@@ -18,6 +18,7 @@
 //     per-pixel evaluation, which itself uses the reference's fp32 expressions.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "gsr_common.cuh"
 
@@ -74,6 +75,30 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// TMA bulk copy (cp.async.bulk, SASS UBLKCP) of one contiguous row global -> shared, completion on an mbarrier
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 
 // SH -> RGB for one Gaussian from its staged row (forward.cu:20-71).  Like cov3d_ref_rounding below, the
 // roundings are pinned to the instruction sequence nvcc 12.9 emits for the reference (SASS of oracle/_ref):
@@ -161,16 +186,22 @@ __device__ __forceinline__ void cov3d_ref_rounding(float sx, float sy, float sz,
     c3[5] = __fmaf_rn(M22, M22, __fmaf_rn(M20, M20, __fmul_rn(M21, M21)));
 }
 
-// DEG = -1: colours are precomputed.  VEC: SH rows are 16-byte aligned (M % 4 == 0) -> cp.async float4 staging.
-template <int DEG, bool VEC>
+// DEG = -1: colours are precomputed.  VEC: SH rows are 16-byte aligned (M % 4 == 0) -> 16-byte staging, either one TMA
+// bulk copy per visible Gaussian issued by its own lane (BULK) or coalesced cp.async by the whole warp.
+template <int DEG, bool VEC, bool BULK>
 __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
     constexpr int DG = DEG < 0 ? 0 : DEG;
     constexpr int NF = sh_nf(DG);
     constexpr int STRIDE = sh_stride(DG, VEC);
     __shared__ CamConsts cam;
     __shared__ __align__(16) float stage[DEG < 0 ? 4 : PRE_THREADS * STRIDE];
+    __shared__ __align__(8) unsigned long long stage_bar[PRE_THREADS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (BULK && lane == 0) {
+        mbar_init((uint32_t)__cvta_generic_to_shared(&stage_bar[warp]), 1u);
+        mbar_fence_init();
+    }
     if (tid < 16) cam.view[tid] = p.view[tid];
     else if (tid < 32) cam.proj[tid - 16] = p.proj[tid - 16];
     else if (tid < 35) cam.campos[tid - 32] = p.campos[tid - 32];
@@ -286,7 +317,15 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
         float* wstage = stage + warp * 32 * STRIDE;
         const size_t gbase = (size_t)(blockIdx.x * PRE_THREADS + warp * 32);
         const size_t row_floats = (size_t)p.M * 3;
-        if (VEC) {
+        if (VEC && BULK) {
+            constexpr int NV = (NF + 3) / 4;
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar[warp]);
+            if (vismask) {
+                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)__popc(vismask) * NV * 16u);
+                if (vis) bulk_g2s((uint32_t)__cvta_generic_to_shared(wstage + lane * STRIDE), p.shs + (gbase + lane) * row_floats, NV * 16u, bar);
+                mbar_wait(bar, 0u);
+            }
+        } else if (VEC) {
             constexpr int NV = (NF + 3) / 4;
 #pragma unroll
             for (int it = 0; it < NV; it++) {
@@ -820,11 +859,20 @@ int profile_end(float* ms, int* frames) {
 // =====================================================================================================
 // host side
 // =====================================================================================================
+static int sh_bulk_mode() {  // GSR_SH_STAGING=cpasync selects the LDGSTS path, default is the TMA bulk copy
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("GSR_SH_STAGING");
+        mode = (e && strcmp(e, "cpasync") == 0) ? 0 : 1;
+    }
+    return mode;
+}
 template <int DEG>
 static void launch_pre(bool vec, const PreParams& pp, cudaStream_t st) {
     const int grid = (pp.P + PRE_THREADS - 1) / PRE_THREADS;
-    if (vec) k_preprocess<DEG, true><<<grid, PRE_THREADS, 0, st>>>(pp);
-    else k_preprocess<DEG, false><<<grid, PRE_THREADS, 0, st>>>(pp);
+    if (vec && sh_bulk_mode()) k_preprocess<DEG, true, true><<<grid, PRE_THREADS, 0, st>>>(pp);
+    else if (vec) k_preprocess<DEG, true, false><<<grid, PRE_THREADS, 0, st>>>(pp);
+    else k_preprocess<DEG, false, false><<<grid, PRE_THREADS, 0, st>>>(pp);
 }
 
 int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,
