@@ -22,11 +22,47 @@ namespace gsr {
 
 constexpr int BWD_THREADS = 256;
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(GSR_FULL, v, o);
+__device__ __forceinline__ float4 lds128b(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
+__device__ __forceinline__ void sts128b(uint32_t a, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Sum 10 per-lane values over the warp with a reduce-scatter butterfly: at every level each lane keeps the
+// half of the values its group is responsible for and ships the other half, so 5+3+2+1+1 = 12 shuffles replace
+// 10 full butterflies (50).  Afterwards the (even) lane with `valid` holds the warp total of value `vid`.
+__device__ __forceinline__ float reduce10(const float (&v)[10], int lane, int& vid, bool& valid) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+    float w[5], x[3], y[2];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        const float send = b4 ? v[i] : v[i + 5], keep = b4 ? v[i + 5] : v[i];
+        w[i] = keep + __shfl_xor_sync(GSR_FULL, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float hi = (i + 3 < 5) ? w[(i + 3 < 5) ? i + 3 : 0] : 0.f;
+        const float send = b3 ? w[i] : hi, keep = b3 ? hi : w[i];
+        x[i] = keep + __shfl_xor_sync(GSR_FULL, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const float hi = (i + 2 < 3) ? x[(i + 2 < 3) ? i + 2 : 0] : 0.f;
+        const float send = b2 ? x[i] : hi, keep = b2 ? hi : x[i];
+        y[i] = keep + __shfl_xor_sync(GSR_FULL, send, 4);
+    }
+    const float send = b1 ? y[0] : y[1], keep = b1 ? y[1] : y[0];
+    float z = keep + __shfl_xor_sync(GSR_FULL, send, 2);
+    z += __shfl_xor_sync(GSR_FULL, z, 1);
+    valid = !(b2 && (b3 || b1)) && !(lane & 1);
+    vid = (b4 ? 5 : 0) + (b3 ? (b1 ? 4 : 3) : (b2 ? 2 : (b1 ? 1 : 0)));
+    return z;
+}
+
+constexpr int BWD_QCAP = 48;
 
 // One CTA per tile; batches of the tile's list are walked from the back.
 __global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
@@ -35,9 +71,11 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
     const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dpixel_alphas,
     float* __restrict__ dL_dmean2D /*[P,3]*/, float* __restrict__ dL_dconic /*[P,4]*/, float* __restrict__ dL_dopacity,
     float* __restrict__ dL_dcolors /*[P,3]*/, float* __restrict__ dL_ddepths) {
-    __shared__ float4 sA[BWD_THREADS], sB[BWD_THREADS], sC[BWD_THREADS];
+    __shared__ __align__(16) float4 sRec[BWD_THREADS * 3];                    // staged batch, 48 B per splat
+    __shared__ __align__(16) float4 sQ[(BWD_THREADS / 32) * BWD_QCAP * 3];    // per-warp survivor queues (back to front)
     __shared__ uint32_t sId[BWD_THREADS];
     __shared__ float acc[BWD_THREADS][11];  // 10 gradients per staged splat (+1 pad: conflict-free flush)
+    __shared__ uint32_t s_wl[BWD_THREADS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.y * gx + blockIdx.x;
@@ -47,6 +85,9 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
     const float pixx = (float)pxi, pixy = (float)pyi;
     const float fcx = (float)X0 + FOOT_HX, fcy = (float)Y0 + FOOT_HY;
     const size_t pid = (size_t)W * pyi + pxi, HW = (size_t)H * W;
+    const uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(sRec);
+    const uint32_t q_base = (uint32_t)__cvta_generic_to_shared(sQ) + (uint32_t)warp * (BWD_QCAP * 48);
+    const unsigned gt_mask = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
 
     const uint2 range = ranges[tile];
     const int n = (int)(range.y - range.x);
@@ -70,7 +111,6 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
     uint32_t warp_last = last_contributor;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(GSR_FULL, warp_last, o));
-    __shared__ uint32_t s_wl[BWD_THREADS / 32];
     if (lane == 0) s_wl[warp] = warp_last;
     __syncthreads();
     uint32_t tile_last = 0;
@@ -78,13 +118,83 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
     for (int k = 0; k < BWD_THREADS / 32; k++) tile_last = max(tile_last, s_wl[k]);
     if (tile_last == 0) return;  // nothing contributed anywhere in this tile
 
+    int qn = 0;
+    // replay the queued splats (back to front) for this lane's pixel: backward.cu:494-597
+    auto drain = [&](int batch) {
+        __syncwarp();
+        uint32_t qa = q_base;
+        for (int k = 0; k < qn; k++, qa += 48) {
+            const float4 A = lds128b(qa), B = lds128b(qa + 16), Cc = lds128b(qa + 32);
+            const uint32_t pos = __float_as_uint(Cc.w);  // 1-based position in the tile list
+            float g[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // dcolor[3], ddepth, dmean2D.x, .y, dconic.x, .y, .w, dopacity
+            bool contrib = false;
+            if (pos <= last_contributor) {
+                const float2 d = {A.x - pixx, A.y - pixy};
+                const float power = -0.5f * (A.z * d.x * d.x + B.x * d.y * d.y) - A.w * d.x * d.y;
+                if (!(power > 0.0f)) {
+                    const float G = exp(power);
+                    const float alpha = min(0.99f, B.y * G);
+                    if (!(alpha < 1.0f / 255.0f)) {
+                        contrib = true;
+                        T = T / (1.f - alpha);
+                        const float dchannel_dcolor = alpha * T;
+                        float dL_dalpha = 0.0f;
+                        accum_rec0 = last_alpha * last_c0 + (1.f - last_alpha) * accum_rec0;
+                        last_c0 = Cc.x;
+                        dL_dalpha += (Cc.x - accum_rec0) * dLp0;
+                        g[0] = dchannel_dcolor * dLp0;
+                        accum_rec1 = last_alpha * last_c1 + (1.f - last_alpha) * accum_rec1;
+                        last_c1 = Cc.y;
+                        dL_dalpha += (Cc.y - accum_rec1) * dLp1;
+                        g[1] = dchannel_dcolor * dLp1;
+                        accum_rec2 = last_alpha * last_c2 + (1.f - last_alpha) * accum_rec2;
+                        last_c2 = Cc.z;
+                        dL_dalpha += (Cc.z - accum_rec2) * dLp2;
+                        g[2] = dchannel_dcolor * dLp2;
+                        const float dep = B.z;
+                        accum_red = last_alpha * last_depth + (1.f - last_alpha) * accum_red;
+                        last_depth = dep;
+                        dL_dalpha += (dep - accum_red) * dLd;
+                        g[3] = dchannel_dcolor * dLd;
+                        accum_rea = last_alpha + (1.f - last_alpha) * accum_rea;
+                        dL_dalpha += (1 - accum_rea) * dLa;
+                        dL_dalpha *= T;
+                        last_alpha = alpha;
+                        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                        const float dL_dG = B.y * dL_dalpha;
+                        const float gdx = G * d.x, gdy = G * d.y;
+                        const float dG_ddelx = -gdx * A.z - gdy * A.w;
+                        const float dG_ddely = -gdy * B.x - gdx * A.w;
+                        g[4] = dL_dG * dG_ddelx * ddelx_dx;
+                        g[5] = dL_dG * dG_ddely * ddely_dy;
+                        g[6] = -0.5f * gdx * d.x * dL_dG;
+                        g[7] = -0.5f * gdx * d.y * dL_dG;
+                        g[8] = -0.5f * gdy * d.y * dL_dG;
+                        g[9] = G * dL_dalpha;
+                    }
+                }
+            }
+            if (__any_sync(GSR_FULL, contrib)) {
+                int vid;
+                bool valid;
+                const float z = reduce10(g, lane, vid, valid);
+                if (valid) atomicAdd(&acc[(int)pos - 1 - batch * BWD_THREADS][vid], z);
+            }
+        }
+        qn = 0;
+        __syncwarp();
+    };
+
     for (int b = (int)((tile_last - 1) / BWD_THREADS); b >= 0; b--) {
         const int cnt = min(BWD_THREADS, n - b * BWD_THREADS);
         __syncthreads();  // previous batch fully flushed
         if (tid < cnt) {
             const uint32_t id = point_list[range.x + b * BWD_THREADS + tid];
             const float4* r = records + 3 * (size_t)id;
-            sA[tid] = r[0]; sB[tid] = r[1]; sC[tid] = r[2];
+            float4 rc = r[2];
+            rc.w = __uint_as_float((uint32_t)(b * BWD_THREADS + tid + 1));
+            const uint32_t sa = rec_base + (uint32_t)tid * 48;
+            sts128b(sa, r[0]); sts128b(sa + 16, r[1]); sts128b(sa + 32, rc);
             sId[tid] = id;
         }
 #pragma unroll
@@ -94,76 +204,24 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
         if ((uint32_t)(b * BWD_THREADS) < warp_last) {
             for (int base = ((cnt - 1) / 32) * 32; base >= 0; base -= 32) {
                 const int s = base + lane;
-                const bool keep = s < cnt && (uint32_t)(b * BWD_THREADS + s + 1) <= warp_last &&
-                                  footprint_may_touch(sA[s].x - fcx, sA[s].y - fcy, sA[s].z, sA[s].w, sB[s].x, sB[s].w);
-                unsigned mask = __ballot_sync(GSR_FULL, keep);
-                while (mask) {
-                    const int hi = 31 - __clz(mask);
-                    mask &= ~(1u << hi);
-                    const int j = base + hi;
-                    const uint32_t pos = (uint32_t)(b * BWD_THREADS + j + 1);  // 1-based position in the tile list
-                    float g_c0 = 0, g_c1 = 0, g_c2 = 0, g_dep = 0, g_mx = 0, g_my = 0, g_ca = 0, g_cb = 0, g_cc = 0, g_op = 0;
-                    bool contrib = false;
-                    if (pos <= last_contributor) {
-                        const float4 A = sA[j], B = sB[j];
-                        const float2 d = {A.x - pixx, A.y - pixy};
-                        const float power = -0.5f * (A.z * d.x * d.x + B.x * d.y * d.y) - A.w * d.x * d.y;
-                        if (!(power > 0.0f)) {
-                            const float G = exp(power);
-                            const float alpha = min(0.99f, B.y * G);
-                            if (!(alpha < 1.0f / 255.0f)) {
-                                contrib = true;
-                                const float4 Cc = sC[j];
-                                T = T / (1.f - alpha);
-                                const float dchannel_dcolor = alpha * T;
-                                float dL_dalpha = 0.0f;
-                                accum_rec0 = last_alpha * last_c0 + (1.f - last_alpha) * accum_rec0;
-                                last_c0 = Cc.x;
-                                dL_dalpha += (Cc.x - accum_rec0) * dLp0;
-                                g_c0 = dchannel_dcolor * dLp0;
-                                accum_rec1 = last_alpha * last_c1 + (1.f - last_alpha) * accum_rec1;
-                                last_c1 = Cc.y;
-                                dL_dalpha += (Cc.y - accum_rec1) * dLp1;
-                                g_c1 = dchannel_dcolor * dLp1;
-                                accum_rec2 = last_alpha * last_c2 + (1.f - last_alpha) * accum_rec2;
-                                last_c2 = Cc.z;
-                                dL_dalpha += (Cc.z - accum_rec2) * dLp2;
-                                g_c2 = dchannel_dcolor * dLp2;
-                                const float dep = B.z;
-                                accum_red = last_alpha * last_depth + (1.f - last_alpha) * accum_red;
-                                last_depth = dep;
-                                dL_dalpha += (dep - accum_red) * dLd;
-                                g_dep = dchannel_dcolor * dLd;
-                                accum_rea = last_alpha + (1.f - last_alpha) * accum_rea;
-                                dL_dalpha += (1 - accum_rea) * dLa;
-                                dL_dalpha *= T;
-                                last_alpha = alpha;
-                                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-                                const float dL_dG = B.y * dL_dalpha;
-                                const float gdx = G * d.x, gdy = G * d.y;
-                                const float dG_ddelx = -gdx * A.z - gdy * A.w;
-                                const float dG_ddely = -gdy * B.x - gdx * A.w;
-                                g_mx = dL_dG * dG_ddelx * ddelx_dx;
-                                g_my = dL_dG * dG_ddely * ddely_dy;
-                                g_ca = -0.5f * gdx * d.x * dL_dG;
-                                g_cb = -0.5f * gdx * d.y * dL_dG;
-                                g_cc = -0.5f * gdy * d.y * dL_dG;
-                                g_op = G * dL_dalpha;
-                            }
-                        }
+                const uint32_t sa = rec_base + (uint32_t)s * 48;
+                bool keep = false;
+                float4 A, B;
+                if (s < cnt && (uint32_t)(b * BWD_THREADS + s + 1) <= warp_last) {
+                    A = lds128b(sa); B = lds128b(sa + 16);
+                    keep = footprint_may_touch(A.x - fcx, A.y - fcy, A.z, A.w, B.x, B.w);
+                }
+                const unsigned mask = __ballot_sync(GSR_FULL, keep);
+                if (mask) {
+                    if (keep) {  // later list positions (higher lanes) are replayed first
+                        const uint32_t qa = q_base + (uint32_t)(qn + __popc(mask & gt_mask)) * 48;
+                        sts128b(qa, A); sts128b(qa + 16, B); sts128b(qa + 32, lds128b(sa + 32));
                     }
-                    if (__any_sync(GSR_FULL, contrib)) {
-                        g_c0 = warp_sum(g_c0); g_c1 = warp_sum(g_c1); g_c2 = warp_sum(g_c2); g_dep = warp_sum(g_dep);
-                        g_mx = warp_sum(g_mx); g_my = warp_sum(g_my); g_ca = warp_sum(g_ca); g_cb = warp_sum(g_cb);
-                        g_cc = warp_sum(g_cc); g_op = warp_sum(g_op);
-                        if (lane < 10) {
-                            const float v = lane == 0 ? g_c0 : lane == 1 ? g_c1 : lane == 2 ? g_c2 : lane == 3 ? g_dep : lane == 4 ? g_mx
-                                          : lane == 5 ? g_my : lane == 6 ? g_ca : lane == 7 ? g_cb : lane == 8 ? g_cc : g_op;
-                            atomicAdd(&acc[j][lane], v);
-                        }
-                    }
+                    qn += __popc(mask);
+                    if (qn > BWD_QCAP - 32) drain(b);
                 }
             }
+            if (qn) drain(b);
         }
         __syncthreads();
         if (tid < cnt) {
@@ -259,6 +317,8 @@ __device__ float3 sh_backward(int deg, float* sh, float3 pos, const float* campo
     return dnormvdv3(dir_orig, make_float3(ddir[0], ddir[1], ddir[2]));
 }
 
+// M16: shs has exactly 16 coefficients (48 floats, 16-byte aligned rows): rows move as float4 with compile-time indexing
+template <bool M16>
 __global__ void __launch_bounds__(GB_THREADS) k_gaussian_backward(const GBParams p) {
     __shared__ CamConsts cam;
     __shared__ float stage[GB_THREADS * GB_STRIDE];
@@ -280,10 +340,23 @@ __global__ void __launch_bounds__(GB_THREADS) k_gaussian_backward(const GBParams
     const int nf = p.shs ? min(48, (int)row_floats) : 0;
     const unsigned vismask = __ballot_sync(GSR_FULL, vis);
     if (p.shs) {
-        for (int it = 0; it < nf; it++) {
-            const int item = it * 32 + lane;
-            const int gl = item / nf, part = item - gl * nf;
-            if ((vismask >> gl) & 1u) wstage[gl * GB_STRIDE + part] = p.shs[(gbase + gl) * row_floats + part];
+        if (M16) {  // 12 float4 per row, consecutive lanes fetch consecutive 16-byte parts
+#pragma unroll
+            for (int it = 0; it < 12; it++) {
+                const int item = it * 32 + lane;
+                const int gl = item / 12, part = item - gl * 12;
+                if ((vismask >> gl) & 1u) {
+                    const float4 v = reinterpret_cast<const float4*>(p.shs + (gbase + gl) * 48)[part];
+                    float* d = wstage + gl * GB_STRIDE + part * 4;
+                    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                }
+            }
+        } else {
+            for (int it = 0; it < nf; it++) {
+                const int item = it * 32 + lane;
+                const int gl = item / nf, part = item - gl * nf;
+                if ((vismask >> gl) & 1u) wstage[gl * GB_STRIDE + part] = p.shs[(gbase + gl) * row_floats + part];
+            }
         }
         __syncwarp();
     }
@@ -415,13 +488,29 @@ __global__ void __launch_bounds__(GB_THREADS) k_gaussian_backward(const GBParams
     // ---- write dL/dsh rows: coalesced, zeros for culled Gaussians and for coefficients beyond 16 ----
     if (p.shs && p.dL_dsh) {
         __syncwarp();
-        const int rf = (int)row_floats;
         const int valid_rows = min(32, p.P - (int)gbase);
-        for (int item = lane; item < valid_rows * rf; item += 32) {
-            const int gl = item / rf, part = item - gl * rf;
-            float v = 0.f;
-            if (((vismask >> gl) & 1u) && part < nf) v = wstage[gl * GB_STRIDE + part];
-            p.dL_dsh[gbase * row_floats + item] = v;
+        if (M16) {
+#pragma unroll
+            for (int it = 0; it < 12; it++) {
+                const int item = it * 32 + lane;
+                const int gl = item / 12, part = item - gl * 12;
+                if (gl < valid_rows) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if ((vismask >> gl) & 1u) {
+                        const float* s = wstage + gl * GB_STRIDE + part * 4;
+                        v = make_float4(s[0], s[1], s[2], s[3]);
+                    }
+                    reinterpret_cast<float4*>(p.dL_dsh + (gbase + gl) * 48)[part] = v;
+                }
+            }
+        } else {
+            const int rf = (int)row_floats;
+            for (int item = lane; item < valid_rows * rf; item += 32) {
+                const int gl = item / rf, part = item - gl * rf;
+                float v = 0.f;
+                if (((vismask >> gl) & 1u) && part < nf) v = wstage[gl * GB_STRIDE + part];
+                p.dL_dsh[gbase * row_floats + item] = v;
+            }
         }
     }
 }
@@ -470,7 +559,9 @@ int backward_impl(const gsr_frame* f, const gsr_workspace* ws, const int32_t* ra
     gp.dL_dmean2D = g->dL_dmeans2D; gp.dL_dconic = g->dL_dconic; gp.dL_dcolor = g->dL_dcolors; gp.dL_ddepth = g->dL_ddepths;
     gp.dL_dmeans3D = g->dL_dmeans3D; gp.dL_dcov3D = g->dL_dcov3D; gp.dL_dsh = g->dL_dsh;
     gp.dL_dscale = f->scales ? g->dL_dscales : nullptr; gp.dL_drot = f->scales ? g->dL_drotations : nullptr;
-    k_gaussian_backward<<<(f->P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, st>>>(gp);
+    const bool m16 = f->shs && f->M == 16 && (((uintptr_t)f->shs | (uintptr_t)g->dL_dsh) & 15) == 0;
+    if (m16) k_gaussian_backward<true><<<(f->P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, st>>>(gp);
+    else k_gaussian_backward<false><<<(f->P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, st>>>(gp);
     // gradient buffers the reference leaves at zero for the absent parametrisation
     if (!f->scales) {
         if (g->dL_dscales) cudaMemsetAsync(g->dL_dscales, 0, 12 * P, st);
