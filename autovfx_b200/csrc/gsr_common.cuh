@@ -119,18 +119,18 @@ __device__ __forceinline__ void tile_rect(float px, float py, int r, int gx, int
     y1 = min(gy, max(0, (int)((py + r + GSR_TILE - 1) / GSR_TILE)));
 }
 
-// Run op(tile_index, a, b) once for every tile of this lane's rectangle, (a, b) being the lane's payload.
-// Rectangles of up to SMALL tiles are walked by their own lane; larger ones are walked by the whole warp,
-// 32 tiles at a time (payload broadcast by shuffle), so one huge splat does not serialise a warp.
-// Must be called by all 32 lanes (lanes with nothing to do pass an empty rectangle).
-template <int SMALL, typename Op>
-__device__ __forceinline__ void for_each_tile(int x0, int y0, int x1, int y1, int gx, uint32_t a, uint32_t b, Op op) {
+// Run op(tile_index, tx, ty, payload) once for every tile of this lane's rectangle; payload = NW 32-bit words of
+// the lane that owns the rectangle.  Rectangles of up to SMALL tiles are walked by their own lane; larger ones are
+// walked by the whole warp, 32 tiles at a time (the owner's payload is broadcast by shuffles first), so one huge
+// splat does not serialise a warp.  Must be called by all 32 lanes (lanes with nothing to do pass an empty rectangle).
+template <int SMALL, int NW, typename Op>
+__device__ __forceinline__ void for_each_tile(int x0, int y0, int x1, int y1, int gx, const uint32_t (&pay)[NW], Op op) {
     const int w = x1 - x0;
     const int cnt = w * (y1 - y0);
     const int lane = threadIdx.x & 31;
     if (cnt > 0 && cnt <= SMALL) {
         for (int y = y0; y < y1; y++)
-            for (int x = x0; x < x1; x++) op(y * gx + x, a, b);
+            for (int x = x0; x < x1; x++) op(y * gx + x, x, y, pay);
     }
     __syncwarp();
     unsigned big = __ballot_sync(GSR_FULL, cnt > SMALL);
@@ -139,8 +139,13 @@ __device__ __forceinline__ void for_each_tile(int x0, int y0, int x1, int y1, in
         big &= big - 1;
         const int bx0 = __shfl_sync(GSR_FULL, x0, src), by0 = __shfl_sync(GSR_FULL, y0, src);
         const int bw = __shfl_sync(GSR_FULL, w, src), bn = __shfl_sync(GSR_FULL, cnt, src);
-        const uint32_t ba = __shfl_sync(GSR_FULL, a, src), bb = __shfl_sync(GSR_FULL, b, src);
-        for (int t = lane; t < bn; t += 32) op((by0 + t / bw) * gx + bx0 + t % bw, ba, bb);
+        uint32_t bp[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) bp[k] = __shfl_sync(GSR_FULL, pay[k], src);
+        for (int t = lane; t < bn; t += 32) {
+            const int ty = by0 + t / bw, tx = bx0 + t % bw;
+            op(ty * gx + tx, tx, ty, bp);
+        }
         __syncwarp();
     }
 }
@@ -163,18 +168,25 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 __device__ __forceinline__ float footprint_tau(float opacity) { return __logf(255.0f * opacity); }
-// dx, dy: splat centre minus footprint centre
-__device__ __forceinline__ bool footprint_may_touch(float dx, float dy, float a, float b, float c, float tau) {
-    const float uc = dx - fminf(fmaxf(dx, -FOOT_HX), FOOT_HX);  // signed distance of the box from the centre, 0 if it straddles
-    const float vc = dy - fminf(fmaxf(dy, -FOOT_HY), FOOT_HY);
-    const float vs = fminf(fmaxf(-b * uc * rcp_approx(c), dy - FOOT_HY), dy + FOOT_HY);  // minimiser on the face u = uc
-    const float us = fminf(fmaxf(-b * vc * rcp_approx(a), dx - FOOT_HX), dx + FOOT_HX);  // minimiser on the face v = vc
+// dx, dy: splat centre minus box centre; hx, hy: half extents of the box of pixel centres
+__device__ __forceinline__ bool box_may_touch(float dx, float dy, float a, float b, float c, float tau, float hx, float hy) {
+    const float uc = dx - fminf(fmaxf(dx, -hx), hx);  // signed distance of the box from the centre, 0 if it straddles
+    const float vc = dy - fminf(fmaxf(dy, -hy), hy);
+    const float vs = fminf(fmaxf(-b * uc * rcp_approx(c), dy - hy), dy + hy);  // minimiser on the face u = uc
+    const float us = fminf(fmaxf(-b * vc * rcp_approx(a), dx - hx), dx + hx);  // minimiser on the face v = vc
     const float q1 = a * uc * uc + 2.f * b * uc * vs + c * vs * vs;
     const float q2 = a * us * us + 2.f * b * us * vc + c * vc * vc;
-    const float um = fabsf(dx) + FOOT_HX, vm = fabsf(dy) + FOOT_HY;
+    const float um = fabsf(dx) + hx, vm = fabsf(dy) + hy;
     const float mag = a * um * um + c * vm * vm + 2.f * fabsf(b) * um * vm;
     const bool pd = a > 0.f && c > 0.f;
     return !(pd && 0.5f * fminf(q1, q2) > tau + 1.0e-3f + 4.0e-6f * mag);
+}
+__device__ __forceinline__ bool footprint_may_touch(float dx, float dy, float a, float b, float c, float tau) {
+    return box_may_touch(dx, dy, a, b, c, tau, FOOT_HX, FOOT_HY);
+}
+// whole 16x16 tile (tx, ty): pixel centres [16 tx, 16 tx + 15] x [16 ty, 16 ty + 15]
+__device__ __forceinline__ bool tile_may_touch(float px, float py, float a, float b, float c, float tau, int tx, int ty) {
+    return box_may_touch(px - ((float)(tx * GSR_TILE) + 7.5f), py - ((float)(ty * GSR_TILE) + 7.5f), a, b, c, tau, 7.5f, 7.5f);
 }
 
 // SH basis constants (auxiliary.h:22-39)

@@ -48,7 +48,7 @@ int check_launch(const char* what, bool debug, cudaStream_t stream) {
 struct PreParams {
     int P, D, M, W, H, gx, gy;
     float scale_modifier, tanfovx, tanfovy, focal_x, focal_y;
-    int prefiltered, for_backward, rot_vec;
+    int prefiltered, for_backward, rot_vec, tight;
     const float *means3D, *shs, *colors_precomp, *opacities, *scales, *rotations, *cov3D_precomp, *view, *proj, *campos;
     float4* records;
     float* cov3D;
@@ -282,6 +282,10 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
     // Per-tile histogram.  Gaussians touching <= 8 tiles take a ranked ticket per tile (atomic with return; the
     // results are only needed at the end of the kernel, so the round trips overlap the SH work) and store the
     // ranks for k_emit, which then needs no atomics.  Larger rectangles are counted separately, warp-cooperatively.
+    // With p.tight, a tile of the reference's rectangle only receives an instance if the splat can reach
+    // alpha >= 1/255 at one of its pixel centres (tile_may_touch) — instances the reference creates but skips at
+    // every pixel are never emitted (opt-in: the per-tile lists then differ from the reference's, the images do not).
+    const float tau = footprint_tau(opacity);
     uint32_t rk[8];
     const int rect_w = x1 - x0, rect_n = rect_w * (y1 - y0);
     if (rect_n > 0 && rect_n <= 8) {
@@ -289,7 +293,8 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             if (k < rect_n) {
-                rk[k] = atomicAdd(&p.tile_count[ty * p.gx + tx], 1u);
+                rk[k] = 0xffffffffu;
+                if (!p.tight || tile_may_touch(px, py, con_a, con_b, con_c, tau, tx, ty)) rk[k] = atomicAdd(&p.tile_count[ty * p.gx + tx], 1u);
                 if (++tx == x1) { tx = x0; ty++; }
             }
         }
@@ -297,8 +302,14 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
     {
         const bool big = rect_n > 8;
         uint32_t* tb = p.tile_big;
-        for_each_tile<0>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, p.gx, 0u, 0u,
-                         [&](int tile, uint32_t, uint32_t) { atomicAdd(&tb[tile], 1u); });
+        const int tight = p.tight;
+        const uint32_t pay[6] = {__float_as_uint(px), __float_as_uint(py), __float_as_uint(con_a), __float_as_uint(con_b),
+                                 __float_as_uint(con_c), __float_as_uint(tau)};
+        for_each_tile<0, 6>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, p.gx, pay, [&](int tile, int tx, int ty, const uint32_t(&o)[6]) {
+            if (!tight || tile_may_touch(__uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]),
+                                         __uint_as_float(o[4]), __uint_as_float(o[5]), tx, ty))
+                atomicAdd(&tb[tile], 1u);
+        });
     }
 
     // colour
@@ -351,7 +362,7 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
         if (vis) {
             float4* rec = p.records + 3 * (size_t)idx;
             rec[0] = make_float4(px, py, con_a, con_b);
-            rec[1] = make_float4(con_c, opacity, depth, footprint_tau(opacity));
+            rec[1] = make_float4(con_c, opacity, depth, tau);
             rec[2] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
             if (rect_n <= 8) {
                 uint4* rr = reinterpret_cast<uint4*>(p.ranks + 8 * (size_t)idx);
@@ -431,20 +442,23 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
 __global__ void __launch_bounds__(256) k_emit(int P, int gx, int gy, const int* __restrict__ radii,
                                               const float4* __restrict__ records, const uint32_t* __restrict__ ranks,
                                               const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_fill,
-                                              uint2* __restrict__ pairs, const gsr_counters* __restrict__ counters) {
+                                              uint2* __restrict__ pairs, const gsr_counters* __restrict__ counters, int tight) {
     if (counters->overflow) return;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
     uint32_t dbits = 0;
+    float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
     if (idx < P) {
         const int r = radii[idx];
         if (r > 0) {
-            const float4 r0 = records[3 * (size_t)idx];
-            dbits = __float_as_uint(records[3 * (size_t)idx + 1].z);
+            r0 = records[3 * (size_t)idx];
+            r1 = records[3 * (size_t)idx + 1];
+            dbits = __float_as_uint(r1.z);
             tile_rect(r0.x, r0.y, r, gx, gy, x0, y0, x1, y1);
         }
     }
     // <= 8 tiles: the in-tile rank of every instance was drawn by k_preprocess -> plain scatter, no atomics
+    // (rank 0xffffffff = tile culled by the tight-tile test)
     const int w = x1 - x0, cnt = w * (y1 - y0);
     if (cnt > 0 && cnt <= 8) {
         const uint4* rr = reinterpret_cast<const uint4*>(ranks + 8 * (size_t)idx);
@@ -457,15 +471,20 @@ __global__ void __launch_bounds__(256) k_emit(int P, int gx, int gy, const int* 
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             if (k < cnt) {
-                pairs[ranges[ty * gx + tx].x + rk[k]] = pr;
+                if (rk[k] != 0xffffffffu) pairs[ranges[ty * gx + tx].x + rk[k]] = pr;
                 if (++tx == x1) { tx = x0; ty++; }
             }
         }
     }
-    // > 8 tiles: walked by the whole warp, positions from the per-tile cursor initialised by k_tile_scan
+    // > 8 tiles: walked by the whole warp, positions from the per-tile cursor initialised by k_tile_scan; the
+    // tight-tile test is re-evaluated on the same stored values k_preprocess used (bitwise same decision)
     const bool big = cnt > 8;
-    for_each_tile<0>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, (uint32_t)idx, dbits, [&](int tile, uint32_t id, uint32_t d) {
-        pairs[atomicAdd(&tile_fill[tile], 1u)] = make_uint2(id, d);
+    const uint32_t pay[8] = {(uint32_t)idx, dbits, __float_as_uint(r0.x), __float_as_uint(r0.y), __float_as_uint(r0.z),
+                             __float_as_uint(r0.w), __float_as_uint(r1.x), __float_as_uint(r1.w)};
+    for_each_tile<0, 8>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, pay, [&](int tile, int tx, int ty, const uint32_t(&o)[8]) {
+        if (!tight || tile_may_touch(__uint_as_float(o[2]), __uint_as_float(o[3]), __uint_as_float(o[4]), __uint_as_float(o[5]),
+                                     __uint_as_float(o[6]), __uint_as_float(o[7]), tx, ty))
+            pairs[atomicAdd(&tile_fill[tile], 1u)] = make_uint2(o[0], o[1]);
     });
 }
 
@@ -923,6 +942,7 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     pp.focal_y = f->H / (2.0f * f->tanfovy);  // rasterizer_impl.cu:223-224
     pp.focal_x = f->W / (2.0f * f->tanfovx);
     pp.rot_vec = (((uintptr_t)f->rotations & 15) == 0) ? 1 : 0;
+    pp.tight = (flags & GSR_FLAG_TIGHT_TILES) ? 1 : 0;
     pp.prefiltered = f->prefiltered; pp.for_backward = (flags & GSR_FLAG_FOR_BACKWARD) ? 1 : 0;
     pp.means3D = f->means3D; pp.shs = f->shs; pp.colors_precomp = f->colors_precomp; pp.opacities = f->opacities;
     pp.scales = f->scales; pp.rotations = f->rotations; pp.cov3D_precomp = f->cov3D_precomp;
@@ -951,7 +971,7 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     if ((rc = check_launch("gsr_forward/tile_scan", debug, st))) return rc;
 
     k_emit<<<(f->P + 255) / 256, 256, 0, st>>>(f->P, il.gx, il.gy, radii, pp.records, pp.ranks, ranges, (uint32_t*)(img + il.tile_fill),
-                                               (uint2*)(bin + bl.pairs), counters);
+                                               (uint2*)(bin + bl.pairs), counters, pp.tight);
     prof_mark(3, st);
     if ((rc = check_launch("gsr_forward/emit", debug, st))) return rc;
 

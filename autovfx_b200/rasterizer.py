@@ -31,6 +31,7 @@ from . import _lib
 from ._lib import lib as _L
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "set_sync_mode", "get_sync_mode",
+           "set_tight_tiles", "get_tight_tiles",
            "last_frame_stats", "FrameTicket", "forward_raw", "debug_views"]
 
 
@@ -65,6 +66,21 @@ def set_sync_mode(mode: str) -> None:
 
 def get_sync_mode() -> str:
     return _SYNC_MODE
+
+
+_TIGHT_TILES = False
+
+
+def set_tight_tiles(on: bool) -> None:
+    """Opt-in (default off): only emit a (Gaussian, tile) instance if the splat can reach alpha >= 1/255 at a pixel of the
+    tile (GSR_FLAG_TIGHT_TILES).  color / depth / alpha / radii and all gradients are bit-for-bit unchanged; the opaque
+    per-tile lists become sub-sequences of the reference's, so fewer instances are sorted and staged."""
+    global _TIGHT_TILES
+    _TIGHT_TILES = bool(on)
+
+
+def get_tight_tiles() -> bool:
+    return _TIGHT_TILES
 
 
 class FrameTicket:
@@ -190,7 +206,8 @@ def _fill_frame(fr: _lib.gsr_frame, P, D, M, W, H, settings, bg, means3D, shs, c
 
 
 def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, settings: GaussianRasterizationSettings,
-                for_backward: bool = False, sorted_keys: bool = False, sync: Optional[bool] = None, out=None):
+                for_backward: bool = False, sorted_keys: bool = False, sync: Optional[bool] = None, out=None,
+                tight: Optional[bool] = None):
     """One rasterizer forward through the C ABI.  Returns (color, depth, alpha, radii, workspaces, ticket, keepalive).
     ``workspaces`` = (geom, binning, image) byte tensors; fresh allocations when ``for_backward`` (they must outlive
     the call), otherwise per-(device, stream) cached buffers.  ``out`` optionally supplies preallocated
@@ -221,6 +238,8 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
         else:
             color, depth, alpha, radii = out
         flags = (_lib.GSR_FLAG_FOR_BACKWARD if for_backward else 0) | (_lib.GSR_FLAG_SORTED_KEYS if sorted_keys else 0)
+        if _TIGHT_TILES if tight is None else tight:
+            flags |= _lib.GSR_FLAG_TIGHT_TILES
         fr = _lib.gsr_frame()
         _fill_frame(fr, P, int(settings.sh_degree), M, W, H, settings, bg, means3D, shs, colors_precomp, opacities, scales, rotations,
                     cov3D_precomp, view, proj, campos)

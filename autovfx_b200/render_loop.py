@@ -101,7 +101,7 @@ class FrameLoop:
     """Renders a list of cameras for one resident set of Gaussians on one GPU."""
 
     def __init__(self, gaussians: Dict[str, torch.Tensor], sh_degree: int, width: int, height: int, bg=(0.0, 0.0, 0.0),
-                 scale_modifier: float = 1.0, device=None, ring: int = 3, to_host: bool = True):
+                 scale_modifier: float = 1.0, device=None, ring: int = 3, to_host: bool = True, tight_tiles: Optional[bool] = None):
         from . import rasterizer as R  # requires the CUDA library
         self._R = R
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -110,6 +110,7 @@ class FrameLoop:
         self.bg = torch.tensor(bg, dtype=torch.float32, device=self.device)
         self.ring = ring
         self.to_host = to_host
+        self.tight_tiles = tight_tiles  # None: follow rasterizer.set_tight_tiles()
         P = self.g["means3D"].shape[0]
         self.frames = [torch.empty((5, height, width), dtype=torch.float32, device=self.device) for _ in range(ring)]
         self.radii = [torch.empty((P,), dtype=torch.int32, device=self.device) for _ in range(ring)]
@@ -135,7 +136,7 @@ class FrameLoop:
         g = self.g
         out = (f[0:3], f[3:4], f[4:5], self.radii[slot])
         res = self._R.forward_raw(g["means3D"], g["shs"], None, g["opacities"], g["scales"], g["rotations"], None,
-                                  self._settings(slot, float(cam_row[35]), float(cam_row[36])), sync=sync, out=out)
+                                  self._settings(slot, float(cam_row[35]), float(cam_row[36])), sync=sync, out=out, tight=self.tight_tiles)
         return res[5]  # ticket
 
     def render(self, packed_cams: torch.Tensor, consume: Optional[Callable[[int, torch.Tensor, Dict[str, int]], None]] = None) -> List[Dict[str, int]]:

@@ -248,8 +248,9 @@ def main():
     out_ring = [(torch.empty((3, H_IMG, W_IMG), device=dev), torch.empty((1, H_IMG, W_IMG), device=dev), torch.empty((1, H_IMG, W_IMG), device=dev),
                  torch.empty((P,), dtype=torch.int32, device=dev)) for _ in range(2)]
 
-    def frame(s, sync):
-        return R.forward_raw(g["means3D"], g["shs"], None, g["opacities"], g["scales"], g["rotations"], None, all_settings[s], sync=sync, out=out_ring[s % 2])
+    def frame(s, sync, tight=False):
+        return R.forward_raw(g["means3D"], g["shs"], None, g["opacities"], g["scales"], g["rotations"], None, all_settings[s], sync=sync, out=out_ring[s % 2],
+                             tight=tight)
 
     # pre-pass (untimed, synchronous): sizes the binning capacity for every camera of the run and warms everything up
     for s in range(Wm + K):
@@ -309,6 +310,20 @@ def main():
                 "frame_algorithmic_bytes": ab["frame"], "frame_achieved": frame_gbs, "frame_frac": frame_gbs / peak,
                 "note": "blend is FP32/MUFU-bound, not HBM-bound (SURVEY §7); its HBM fraction is reported because the metric names the HBM roofline"}
 
+    # ---- opt-in tight-tile mode (GSR_FLAG_TIGHT_TILES): identical images, shorter per-tile lists; reported separately ----
+    for s in range(Wm):
+        frame(s, True, tight=True)
+    barrier()
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0e.record()
+    tt = [frame(Wm + s, False, tight=True)[5] for s in range(K)]
+    t1e.record()
+    barrier()
+    ms_tight = max_over_ranks(t0e.elapsed_time(t1e))
+    st_t = [t.stats() for t in tt]
+    tight_info = {"value": frames_total / (ms_tight * 1e-3), "unit": "frames/s", "avg_num_rendered": sum(x["num_rendered"] for x in st_t) / len(st_t),
+                  "note": "opt-in GSR_FLAG_TIGHT_TILES: per-tile lists are sub-sequences of the reference's; color/depth/alpha/radii bit-identical"}
+
     # ---- e2e: public frame loop, host camera payload in, finished frame out to pinned host memory, every step ----
     loop = RL.FrameLoop(g, 3, W_IMG, H_IMG, device=dev, ring=3, to_host=True)
     e2e_cams = torch.stack([my_cams_host[cam_of_step(Wm + s)] for s in range(K)])
@@ -348,7 +363,7 @@ def main():
                 "config": {"workload": workload, "gaussians": P, "avg_visible": avg_vis, "avg_num_rendered": avg_R, "frames_per_rank": K,
                            "parallelism": "frame-sharded x%d (round-robin cameras, NCCL only for parameter broadcast + camera scatter)" % world,
                            "l2": "inputs larger than L2 (708 MB of SH read per frame; 126 MB L2)", "sync": "async issue, counters validated after the timed region"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * K * world, "roofline": roofline}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * K * world, "roofline": roofline, "tight_tiles": tight_info}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

@@ -44,6 +44,9 @@ enum {
 enum {
     GSR_FLAG_FOR_BACKWARD = 1, /* also keep cov3D, SH clamp flags and n_contrib for gsr_backward   */
     GSR_FLAG_SORTED_KEYS = 2,  /* also write the sorted 64-bit (tile<<32 | depth bits) keys (parity/debug) */
+    GSR_FLAG_TIGHT_TILES = 4,  /* opt-in: emit a (Gaussian, tile) instance only if the splat can reach alpha >= 1/255 at a
+                                  pixel of the tile; per-tile lists become a sub-sequence of the reference's, num_rendered and
+                                  n_contrib shrink accordingly, color/depth/alpha/radii and all gradients are unchanged */
 };
 
 /* One rasterizer invocation = the argument list of Rasterizer::forward (DGR/cuda_rasterizer/rasterizer.h:33-58). */

@@ -87,12 +87,12 @@ def settings_from(a: Dict, debug=False, prefiltered=False):
                                          sh_degree=a["sh_degree"], campos=a["campos"], prefiltered=prefiltered, debug=debug)
 
 
-def run_ours(a: Dict, for_backward=False, sorted_keys=False, debug=True):
+def run_ours(a: Dict, for_backward=False, sorted_keys=False, debug=True, tight=None):
     from autovfx_b200 import rasterizer as R
     s = settings_from(a, debug=debug)
     color, depth, alpha, radii, ws, ticket, keep = R.forward_raw(a["means3D"], a["shs"], a["colors_precomp"], a["opacities"], a["scales"],
                                                                  a["rotations"], a["cov3D_precomp"], s, for_backward=for_backward,
-                                                                 sorted_keys=sorted_keys, sync=True)
+                                                                 sorted_keys=sorted_keys, sync=True, tight=tight)
     views = R.debug_views(ws, a["means3D"].shape[0], a["W"], a["H"])
     return dict(color=color, depth=depth, alpha=alpha, radii=radii, views=views, stats=ticket.stats(), ws=ws, keep=keep)
 

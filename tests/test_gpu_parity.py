@@ -327,3 +327,40 @@ def test_training_step_through_module_reduces_loss(dev):
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < 0.7 * losses[0]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_tight_tiles_changes_lists_but_not_images_or_gradients(dev, name):
+    """GSR_FLAG_TIGHT_TILES (opt-in): per-tile lists become sub-sequences of the exact-key lists; color/depth/alpha/radii
+    are bitwise identical; gradients agree to summation order."""
+    from autovfx_b200 import rasterizer as R
+    a = Hh.resolve(Hh.case_inputs(name), dev)
+    exact = Hh.run_ours(a, for_backward=True, sorted_keys=True, tight=False)
+    ex_imgs = [exact[k].clone() for k in ("color", "depth", "alpha")]
+    ex_radii = exact["radii"].clone()
+    Re = exact["stats"]["num_rendered"]
+    ex_list = exact["views"]["point_list"][:Re].clone()
+    ex_rg = exact["views"]["ranges"].clone().long()
+    tight = Hh.run_ours(a, for_backward=True, sorted_keys=True, tight=True)
+    Rt = tight["stats"]["num_rendered"]
+    assert Rt <= Re and torch.equal(tight["radii"], ex_radii)
+    for x, k in zip(ex_imgs, ("color", "depth", "alpha")):
+        assert torch.equal(x, tight[k]), k
+    # sub-sequence check per tile (on the host, small cases only)
+    tl = tight["views"]["point_list"][:Rt].cpu().numpy()
+    tr = tight["views"]["ranges"].cpu().numpy().astype(np.int64)
+    el, er = ex_list.cpu().numpy(), ex_rg.cpu().numpy()
+    for t in range(0, er.shape[0], max(1, er.shape[0] // 40)):
+        full = el[er[t, 0]:er[t, 1]].tolist()
+        sub = tl[tr[t, 0]:tr[t, 1]].tolist()
+        it = iter(full)
+        assert all(any(x == y for y in it) for x in sub), t
+    dc, dd, da = Hh.image_grads(a, device=dev)
+    _, g_exact = Hh.ours_backward(a, dc, dd, da)
+    R.set_tight_tiles(True)
+    try:
+        _, g_tight = Hh.ours_backward(a, dc, dd, da)
+    finally:
+        R.set_tight_tiles(False)
+    for k in ("means3D", "means2D", "opacities"):
+        assert Hh.relerr(g_tight[k], g_exact[k]) < 1e-5, k
