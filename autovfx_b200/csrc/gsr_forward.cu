@@ -733,29 +733,31 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
     int qn = 0;  // entries in this warp's queue (warp-uniform)
 
     // blend every queued splat into this lane's pixel (reference arithmetic, forward.cu:330-366)
+    // Branch-free: every lane evaluates every queued splat; the three skip rules of the reference (power > 0,
+    // alpha < 1/255, T(1-alpha) < 1e-4) become predicates, and a skipped splat contributes through a transmittance of
+    // exactly 0 (x + y*0 == x), so the accumulated values are bitwise those of the branching form while two splats can
+    // be in flight per lane.
     auto drain = [&]() {
         __syncwarp();
         uint32_t qa = q_base;
-#pragma unroll 4
+#pragma unroll 2
         for (int k = 0; k < qn; k++, qa += 48) {
-            const float4 A = lds128(qa), B = lds128(qa + 16);
+            const float4 A = lds128(qa), B = lds128(qa + 16), Cc = lds128(qa + 32);
             const float2 d = {A.x - pixx, A.y - pixy};
             const float power = -0.5f * (A.z * d.x * d.x + B.x * d.y * d.y) - A.w * d.x * d.y;
-            if (power > 0.0f) continue;
             const float alpha = min(0.99f, B.y * exp(power));
-            if (alpha < 1.0f / 255.0f) continue;
+            const bool hit = !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
             const float test_T = T * (1 - alpha);
-            if (test_T < 0.0001f) {
-                if (T != 0.0f) { T_out = T; T = 0.0f; }
-                continue;
-            }
-            const float4 Cc = lds128(qa + 32);
-            C0 += Cc.x * alpha * T;
-            C1 += Cc.y * alpha * T;
-            C2 += Cc.z * alpha * T;
-            Dp += B.z * alpha * T;
-            T = test_T;
-            last = __float_as_uint(Cc.w);
+            const bool live = hit && !(test_T < 0.0001f);
+            const bool dies = hit && (test_T < 0.0001f) && T != 0.0f;
+            const float Tw = live ? T : 0.0f;
+            C0 += Cc.x * alpha * Tw;
+            C1 += Cc.y * alpha * Tw;
+            C2 += Cc.z * alpha * Tw;
+            Dp += B.z * alpha * Tw;
+            T_out = dies ? T : T_out;
+            T = live ? test_T : (dies ? 0.0f : T);
+            last = live ? __float_as_uint(Cc.w) : last;
         }
         qn = 0;
         __syncwarp();
