@@ -439,10 +439,11 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
 // Kernel 3: scatter one (depth bits, Gaussian id) pair per (Gaussian, tile) instance into the tile's bucket
 // (the work of duplicateWithKeys, rasterizer_impl.cu:70-111; the tile id is implicit in the bucket)
 // =====================================================================================================
+template <bool TIGHT>
 __global__ void __launch_bounds__(256) k_emit(int P, int gx, int gy, const int* __restrict__ radii,
                                               const float4* __restrict__ records, const uint32_t* __restrict__ ranks,
                                               const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_fill,
-                                              uint2* __restrict__ pairs, const gsr_counters* __restrict__ counters, int tight) {
+                                              uint2* __restrict__ pairs, const gsr_counters* __restrict__ counters) {
     if (counters->overflow) return;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
@@ -452,8 +453,12 @@ __global__ void __launch_bounds__(256) k_emit(int P, int gx, int gy, const int* 
         const int r = radii[idx];
         if (r > 0) {
             r0 = records[3 * (size_t)idx];
-            r1 = records[3 * (size_t)idx + 1];
-            dbits = __float_as_uint(r1.z);
+            if (TIGHT) {
+                r1 = records[3 * (size_t)idx + 1];
+                dbits = __float_as_uint(r1.z);
+            } else {
+                dbits = __float_as_uint(records[3 * (size_t)idx + 1].z);
+            }
             tile_rect(r0.x, r0.y, r, gx, gy, x0, y0, x1, y1);
         }
     }
@@ -471,7 +476,7 @@ __global__ void __launch_bounds__(256) k_emit(int P, int gx, int gy, const int* 
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             if (k < cnt) {
-                if (rk[k] != 0xffffffffu) pairs[ranges[ty * gx + tx].x + rk[k]] = pr;
+                if (!TIGHT || rk[k] != 0xffffffffu) pairs[ranges[ty * gx + tx].x + rk[k]] = pr;
                 if (++tx == x1) { tx = x0; ty++; }
             }
         }
@@ -479,13 +484,20 @@ __global__ void __launch_bounds__(256) k_emit(int P, int gx, int gy, const int* 
     // > 8 tiles: walked by the whole warp, positions from the per-tile cursor initialised by k_tile_scan; the
     // tight-tile test is re-evaluated on the same stored values k_preprocess used (bitwise same decision)
     const bool big = cnt > 8;
-    const uint32_t pay[8] = {(uint32_t)idx, dbits, __float_as_uint(r0.x), __float_as_uint(r0.y), __float_as_uint(r0.z),
-                             __float_as_uint(r0.w), __float_as_uint(r1.x), __float_as_uint(r1.w)};
-    for_each_tile<0, 8>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, pay, [&](int tile, int tx, int ty, const uint32_t(&o)[8]) {
-        if (!tight || tile_may_touch(__uint_as_float(o[2]), __uint_as_float(o[3]), __uint_as_float(o[4]), __uint_as_float(o[5]),
-                                     __uint_as_float(o[6]), __uint_as_float(o[7]), tx, ty))
+    if (TIGHT) {
+        const uint32_t pay[8] = {(uint32_t)idx, dbits, __float_as_uint(r0.x), __float_as_uint(r0.y), __float_as_uint(r0.z),
+                                 __float_as_uint(r0.w), __float_as_uint(r1.x), __float_as_uint(r1.w)};
+        for_each_tile<0, 8>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, pay, [&](int tile, int tx, int ty, const uint32_t(&o)[8]) {
+            if (tile_may_touch(__uint_as_float(o[2]), __uint_as_float(o[3]), __uint_as_float(o[4]), __uint_as_float(o[5]),
+                               __uint_as_float(o[6]), __uint_as_float(o[7]), tx, ty))
+                pairs[atomicAdd(&tile_fill[tile], 1u)] = make_uint2(o[0], o[1]);
+        });
+    } else {
+        const uint32_t pay[2] = {(uint32_t)idx, dbits};
+        for_each_tile<0, 2>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, pay, [&](int tile, int, int, const uint32_t(&o)[2]) {
             pairs[atomicAdd(&tile_fill[tile], 1u)] = make_uint2(o[0], o[1]);
-    });
+        });
+    }
 }
 
 // =====================================================================================================
@@ -707,7 +719,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
                                                          float* __restrict__ out_depth, float* __restrict__ out_alpha,
                                                          uint32_t* __restrict__ n_contrib,
                                                          const gsr_counters* __restrict__ counters) {
-    __shared__ __align__(16) float4 sRec[BLEND_THREADS * 3];                       // staged batch, 48 B per splat
+    __shared__ __align__(16) float4 sRec[2 * BLEND_THREADS * 3];                   // two staged batches, 48 B per splat
     __shared__ __align__(16) float4 sQ[(BLEND_THREADS / 32) * BLEND_QCAP * 3];     // per-warp survivor queues
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.y * gx + blockIdx.x;
@@ -763,57 +775,65 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
         __syncwarp();
     };
 
-    // software pipeline: records of batch b and the list entry of batch b+1 are in registers
+    // Software pipeline over batches of 256 list entries, double-buffered in shared memory with ONE barrier per batch:
+    // while batch b is culled/blended out of buffer b&1, the records of batch b+1 (already in registers, gathered
+    // during batch b-1) are stored into the other buffer and the gather of batch b+2 is issued.
     float4 ra = make_float4(0, 0, 0, 0), rb = ra, rc = ra;
     uint32_t id_next = 0;
-    if (tid < n) {
-        const uint32_t id = point_list[range.x + tid];
-        const float4* r = records + 3 * (size_t)id;
-        ra = r[0]; rb = r[1]; rc = r[2];
-    }
+    auto gather = [&](int batch, uint32_t id) {  // records of list entry (batch, tid) -> registers
+        if (batch * BLEND_THREADS + tid < n) {
+            const float4* r = records + 3 * (size_t)id;
+            ra = r[0]; rb = r[1]; rc = r[2];
+            rc.w = __uint_as_float((uint32_t)(batch * BLEND_THREADS + tid + 1));  // 1-based position in the tile list
+        }
+    };
+    auto stage = [&](int batch) {  // registers -> buffer batch&1
+        if (batch * BLEND_THREADS + tid < n) {
+            const uint32_t sa = rec_base + (uint32_t)((batch & 1) * BLEND_THREADS + tid) * 48;
+            sts128(sa, ra); sts128(sa + 16, rb); sts128(sa + 32, rc);
+        }
+    };
+    if (tid < n) gather(0, point_list[range.x + tid]);
     if (BLEND_THREADS + tid < n) id_next = point_list[range.x + BLEND_THREADS + tid];
+    stage(0);
+    gather(1, id_next);
+    if (2 * BLEND_THREADS + tid < n) id_next = point_list[range.x + 2 * BLEND_THREADS + tid];
+    __syncthreads();
     bool warp_done = false;
 
     for (int b = 0; b < nb; b++) {
-        // whole tile finished? (also the barrier that frees the staging buffer)
-        if (__syncthreads_count(T == 0.0f) == BLEND_THREADS) break;
         const int cnt = min(BLEND_THREADS, n - b * BLEND_THREADS);
-        if (tid < cnt) {
-            rc.w = __uint_as_float((uint32_t)(b * BLEND_THREADS + tid + 1));  // 1-based position in the tile list
-            const uint32_t sa = rec_base + (uint32_t)tid * 48;
-            sts128(sa, ra); sts128(sa + 16, rb); sts128(sa + 32, rc);
-        }
-        __syncthreads();
-        {
-            const int nxt = (b + 1) * BLEND_THREADS + tid;
-            if (nxt < n) {
-                const float4* r = records + 3 * (size_t)id_next;
-                ra = r[0]; rb = r[1]; rc = r[2];
-            }
-            if (nxt + BLEND_THREADS < n) id_next = point_list[range.x + nxt + BLEND_THREADS];
-        }
-        if (warp_done) continue;
-        for (int base = 0; base < cnt; base += 32) {
-            const int s = base + lane;
-            const uint32_t sa = rec_base + (uint32_t)s * 48;
-            bool keep = false;
-            float4 A, B;
-            if (s < cnt) {
-                A = lds128(sa); B = lds128(sa + 16);
-                keep = footprint_may_touch(A.x - cx, A.y - cy, A.z, A.w, B.x, B.w);
-            }
-            const unsigned mask = __ballot_sync(GSR_FULL, keep);
-            if (mask) {
-                if (keep) {
-                    const uint32_t qa = q_base + (uint32_t)(qn + __popc(mask & lt_mask)) * 48;
-                    sts128(qa, A); sts128(qa + 16, B); sts128(qa + 32, lds128(sa + 32));
+        const uint32_t buf = rec_base + (uint32_t)((b & 1) * BLEND_THREADS) * 48;
+        if (!warp_done) {
+            for (int base = 0; base < cnt; base += 32) {
+                const int s = base + lane;
+                const uint32_t sa = buf + (uint32_t)s * 48;
+                bool keep = false;
+                float4 A, B;
+                if (s < cnt) {
+                    A = lds128(sa); B = lds128(sa + 16);
+                    keep = footprint_may_touch(A.x - cx, A.y - cy, A.z, A.w, B.x, B.w);
                 }
-                qn += __popc(mask);
-                if (qn > BLEND_QCAP - 32) {
-                    drain();
-                    if (__all_sync(GSR_FULL, T == 0.0f)) { warp_done = true; break; }
+                const unsigned mask = __ballot_sync(GSR_FULL, keep);
+                if (mask) {
+                    if (keep) {
+                        const uint32_t qa = q_base + (uint32_t)(qn + __popc(mask & lt_mask)) * 48;
+                        sts128(qa, A); sts128(qa + 16, B); sts128(qa + 32, lds128(sa + 32));
+                    }
+                    qn += __popc(mask);
+                    if (qn > BLEND_QCAP - 32) {
+                        drain();
+                        if (__all_sync(GSR_FULL, T == 0.0f)) { warp_done = true; break; }
+                    }
                 }
             }
+        }
+        if (b + 1 < nb) {
+            stage(b + 1);
+            gather(b + 2, id_next);
+            if ((b + 3) * BLEND_THREADS + tid < n) id_next = point_list[range.x + (b + 3) * BLEND_THREADS + tid];
+            // whole tile finished?  (also publishes buffer (b+1)&1 and retires buffer b&1)
+            if (__syncthreads_count(T == 0.0f) == BLEND_THREADS) break;
         }
     }
     if (qn) drain();
@@ -972,8 +992,12 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     prof_mark(2, st);
     if ((rc = check_launch("gsr_forward/tile_scan", debug, st))) return rc;
 
-    k_emit<<<(f->P + 255) / 256, 256, 0, st>>>(f->P, il.gx, il.gy, radii, pp.records, pp.ranks, ranges, (uint32_t*)(img + il.tile_fill),
-                                               (uint2*)(bin + bl.pairs), counters, pp.tight);
+    if (pp.tight)
+        k_emit<true><<<(f->P + 255) / 256, 256, 0, st>>>(f->P, il.gx, il.gy, radii, pp.records, pp.ranks, ranges, (uint32_t*)(img + il.tile_fill),
+                                                         (uint2*)(bin + bl.pairs), counters);
+    else
+        k_emit<false><<<(f->P + 255) / 256, 256, 0, st>>>(f->P, il.gx, il.gy, radii, pp.records, pp.ranks, ranges, (uint32_t*)(img + il.tile_fill),
+                                                          (uint2*)(bin + bl.pairs), counters);
     prof_mark(3, st);
     if ((rc = check_launch("gsr_forward/emit", debug, st))) return rc;
 
