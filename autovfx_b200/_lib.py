@@ -47,6 +47,7 @@ class gsr_views(C.Structure):
 GSR_FLAG_FOR_BACKWARD = 1
 GSR_FLAG_SORTED_KEYS = 2
 GSR_FLAG_TIGHT_TILES = 4
+GSR_FLAG_REUSE_GEOMETRY = 8
 ABI_VERSION = 1
 
 EXPORTS = ("gsr_abi_version", "gsr_last_error", "gsr_geom_bytes", "gsr_binning_bytes", "gsr_binning_capacity", "gsr_image_bytes",

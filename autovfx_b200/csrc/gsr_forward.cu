@@ -851,6 +851,20 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
 }
 
 // =====================================================================================================
+// Second pass over identical geometry (GSR_FLAG_REUSE_GEOMETRY): the product frame renders every camera twice with
+// the same Gaussians — SH colours, then colors_precomp = normals (gaussian_renderer/__init__.py:151-185,
+// sugar_model.py:2141-2183).  Projection, binning and sorting of the first pass stay valid; only the colour slot of
+// the visible records is rewritten before the blend.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_recolor(int P, const int* __restrict__ radii, const float* __restrict__ colors_precomp,
+                                                 float4* __restrict__ records) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P || radii[idx] <= 0) return;
+    records[3 * (size_t)idx + 2] = make_float4(colors_precomp[3 * (size_t)idx], colors_precomp[3 * (size_t)idx + 1],
+                                               colors_precomp[3 * (size_t)idx + 2], 0.0f);
+}
+
+// =====================================================================================================
 // optional per-kernel timing (bench.py roofline): CUDA events recorded around each forward kernel on the
 // launching stream; no effect unless gsr_profile_begin() was called.  Not thread safe (one profiled stream).
 // =====================================================================================================
@@ -954,6 +968,19 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     const BinLayout bl(cap);
     char* geo = (char*)ws->geom;
     char* bin = (char*)ws->binning;
+
+    if (flags & GSR_FLAG_REUSE_GEOMETRY) {
+        // `radii` is an INPUT here: the radii of the pass whose workspaces are being reused
+        if (!f->colors_precomp) { set_error("gsr_forward: GSR_FLAG_REUSE_GEOMETRY needs colors_precomp"); return GSR_ERR_INVALID; }
+        if (flags & GSR_FLAG_FOR_BACKWARD) { set_error("gsr_forward: GSR_FLAG_REUSE_GEOMETRY cannot be combined with GSR_FLAG_FOR_BACKWARD"); return GSR_ERR_INVALID; }
+        k_recolor<<<(f->P + 255) / 256, 256, 0, st>>>(f->P, radii, f->colors_precomp, (float4*)(geo + gl.records));
+        int rc0 = check_launch("gsr_forward/recolor", debug, st);
+        if (rc0) return rc0;
+        k_blend<<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>((const uint2*)(img + il.ranges), (const uint32_t*)(bin + bl.point_list),
+                                                              (const float4*)(geo + gl.records), f->W, f->H, il.gx, f->bg, out_color, out_depth,
+                                                              out_alpha, nullptr, counters);
+        return check_launch("gsr_forward/blend(reuse)", debug, st);
+    }
 
     cudaMemsetAsync(img, 0, il.zero_bytes(), st);
     prof_mark(0, st);

@@ -31,7 +31,7 @@ from . import _lib
 from ._lib import lib as _L
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "set_sync_mode", "get_sync_mode",
-           "set_tight_tiles", "get_tight_tiles",
+           "set_tight_tiles", "get_tight_tiles", "set_geometry_reuse",
            "last_frame_stats", "FrameTicket", "forward_raw", "debug_views"]
 
 
@@ -69,6 +69,17 @@ def get_sync_mode() -> str:
 
 
 _TIGHT_TILES = False
+_REUSE_GEOMETRY = True
+
+
+def set_geometry_reuse(on: bool) -> None:
+    """The product frame calls the rasterizer twice per camera with identical geometry (SH pass, then
+    ``colors_precomp`` = normals; reference gaussian_renderer/__init__.py:151-185).  When enabled (default) a
+    ``colors_precomp`` forward under ``torch.no_grad()`` whose geometry tensors, camera and settings are the very same
+    (same storage, same version counters) as the previous forward on that stream skips projection, binning and sorting
+    and only re-blends (GSR_FLAG_REUSE_GEOMETRY).  Outputs are bit-identical to a full forward."""
+    global _REUSE_GEOMETRY
+    _REUSE_GEOMETRY = bool(on)
 
 
 def set_tight_tiles(on: bool) -> None:
@@ -119,6 +130,8 @@ class _DeviceState:
         self.cursor = 0
         self.cache: Dict[Tuple, torch.Tensor] = {}
         self.last_ticket: Optional[FrameTicket] = None
+        # geometry of the last full (non-autograd) forward per stream: (key, tensors kept alive, radii)
+        self.geom_cache: Dict[int, Tuple] = {}
 
     def grow(self, needed: int) -> None:
         self.capacity = max(self.capacity, int(needed * 1.25) + 4096)
@@ -249,6 +262,35 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
         st.ensure_capacity(P)
         do_sync = (_SYNC_MODE == "safe") if sync is None else sync
         stream = torch.cuda.current_stream(device)
+        use_tight = _TIGHT_TILES if tight is None else tight
+
+        def tk(t):
+            return None if t is None else (t.data_ptr(), t._version, tuple(t.shape))
+        gkey = (tk(means3D), tk(opacities), tk(scales), tk(rotations), tk(cov3D_precomp), tk(view), tk(proj), tk(campos), W, H,
+                float(settings.tanfovx), float(settings.tanfovy), float(settings.scale_modifier), bool(settings.prefiltered),
+                bool(use_tight), geom.data_ptr(), image.data_ptr())
+        cached = st.geom_cache.get(stream.cuda_stream)
+        if (_REUSE_GEOMETRY and not for_backward and not sorted_keys and colors_precomp is not None and P > 0 and cached is not None
+                and cached[0] == gkey):
+            # second pass over the same geometry: recolour + blend only
+            _, _, radii_prev, binning = cached
+            ws = _lib.gsr_workspace(geom.data_ptr(), geom.numel(), binning.data_ptr(), binning.numel(), image.data_ptr(), image.numel())
+            rc = _L.gsr_forward(C.byref(fr), C.byref(ws), color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), radii_prev.data_ptr(),
+                                flags | _lib.GSR_FLAG_REUSE_GEOMETRY, C.c_void_p(stream.cuda_stream))
+            _lib.check(rc, "gsr_forward(reuse)")
+            if out is None:
+                radii = radii_prev.clone()
+            elif radii.data_ptr() != radii_prev.data_ptr():
+                radii.copy_(radii_prev)
+            slot, ev = st.next_slot()
+            slot.copy_(image[:32].view(torch.int32), non_blocking=True)
+            ev.record(stream)
+            ticket = FrameTicket(ev, slot, _L.gsr_binning_capacity(binning.numel()), st)
+            st.last_ticket = ticket
+            if do_sync and ticket.stats()["overflow"]:
+                raise RuntimeError("autovfx_b200: reused geometry pass found an overflowed first pass")
+            keep = (means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, view, proj, campos)
+            return color, depth, alpha, radii, (geom, binning, image), ticket, keep
         while True:
             cap = st.capacity
             binning = st.workspace("binning", _L.gsr_binning_bytes(cap), for_backward)
@@ -269,6 +311,9 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
             if not s["overflow"]:
                 break
             st.grow(s["num_rendered"])  # rare: first frames of a new scene; re-run with a larger binning buffer
+        if not for_backward and P > 0:
+            # remember which geometry the shared workspaces now hold (tensors kept alive so their storage cannot be recycled)
+            st.geom_cache[stream.cuda_stream] = (gkey, (means3D, opacities, scales, rotations, cov3D_precomp, view, proj, campos), radii, binning)
     keep = (means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, view, proj, campos)
     return color, depth, alpha, radii, (geom, binning, image), ticket, keep
 

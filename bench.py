@@ -324,6 +324,24 @@ def main():
     tight_info = {"value": frames_total / (ms_tight * 1e-3), "unit": "frames/s", "avg_num_rendered": sum(x["num_rendered"] for x in st_t) / len(st_t),
                   "note": "opt-in GSR_FLAG_TIGHT_TILES: per-tile lists are sub-sequences of the reference's; color/depth/alpha/radii bit-identical"}
 
+    # ---- product frame: SH pass + colors_precomp (normals) pass per camera, second pass reuses the geometry ----
+    normals = (torch.nn.functional.normalize(g["means3D"]) * 0.5 + 0.5).contiguous()
+
+    def product_frame(s):
+        R.forward_raw(g["means3D"], g["shs"], None, g["opacities"], g["scales"], g["rotations"], None, all_settings[s], sync=False, out=out_ring[0])
+        return R.forward_raw(g["means3D"], None, normals, g["opacities"], g["scales"], g["rotations"], None, all_settings[s], sync=False, out=out_ring[1])[5]
+    for s in range(Wm):
+        product_frame(s)
+    barrier()
+    p0e, p1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0e.record()
+    pt = [product_frame(Wm + s) for s in range(K)]
+    p1e.record()
+    barrier()
+    ms_prod = max_over_ranks(p0e.elapsed_time(p1e))
+    product_info = {"value": frames_total / (ms_prod * 1e-3), "unit": "product frames/s (2 rasterizer passes each)", "overflowed": sum(t.stats()["overflow"] for t in pt),
+                    "note": "second pass (colors_precomp) reuses projection+binning of the first (GSR_FLAG_REUSE_GEOMETRY), bit-identical outputs"}
+
     # ---- e2e: public frame loop, host camera payload in, finished frame out to pinned host memory, every step ----
     loop = RL.FrameLoop(g, 3, W_IMG, H_IMG, device=dev, ring=3, to_host=True)
     e2e_cams = torch.stack([my_cams_host[cam_of_step(Wm + s)] for s in range(K)])
@@ -363,7 +381,7 @@ def main():
                 "config": {"workload": workload, "gaussians": P, "avg_visible": avg_vis, "avg_num_rendered": avg_R, "frames_per_rank": K,
                            "parallelism": "frame-sharded x%d (round-robin cameras, NCCL only for parameter broadcast + camera scatter)" % world,
                            "l2": "inputs larger than L2 (708 MB of SH read per frame; 126 MB L2)", "sync": "async issue, counters validated after the timed region"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * K * world, "roofline": roofline, "tight_tiles": tight_info}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * K * world, "roofline": roofline, "tight_tiles": tight_info, "product_frame": product_info}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

@@ -47,6 +47,9 @@ enum {
     GSR_FLAG_TIGHT_TILES = 4,  /* opt-in: emit a (Gaussian, tile) instance only if the splat can reach alpha >= 1/255 at a
                                   pixel of the tile; per-tile lists become a sub-sequence of the reference's, num_rendered and
                                   n_contrib shrink accordingly, color/depth/alpha/radii and all gradients are unchanged */
+    GSR_FLAG_REUSE_GEOMETRY = 8, /* second pass of a frame: the workspaces still hold the projection + binning of the previous
+                                  gsr_forward on the SAME geometry / camera / image size; only colors_precomp is re-read and the
+                                  blend re-run.  `radii` must point to the radii written by that previous call (input). */
 };
 
 /* One rasterizer invocation = the argument list of Rasterizer::forward (DGR/cuda_rasterizer/rasterizer.h:33-58). */

@@ -364,3 +364,35 @@ def test_tight_tiles_changes_lists_but_not_images_or_gradients(dev, name):
         R.set_tight_tiles(False)
     for k in ("means3D", "means2D", "opacities"):
         assert Hh.relerr(g_tight[k], g_exact[k]) < 1e-5, k
+
+
+def test_geometry_reuse_second_pass_is_bit_identical_to_a_full_forward(dev):
+    """§8f(1): the colors_precomp pass that follows an SH pass on the same geometry/camera skips projection+binning
+    (GSR_FLAG_REUSE_GEOMETRY).  Its outputs must equal a full forward bit for bit; changing the geometry must miss."""
+    from autovfx_b200 import rasterizer as R
+    from autovfx_b200.rasterizer import GaussianRasterizer
+    a = Hh.resolve(Hh.case_inputs("config1"), dev)
+    rast = GaussianRasterizer(Hh.settings_from(a))
+    m2 = torch.zeros_like(a["means3D"])
+    normals = (torch.nn.functional.normalize(a["means3D"]) * 0.5 + 0.5).contiguous()
+    with torch.no_grad():
+        R.set_geometry_reuse(False)
+        full = rast(a["means3D"], m2, a["opacities"], colors_precomp=normals, scales=a["scales"], rotations=a["rotations"])
+        R.set_geometry_reuse(True)
+        first = rast(a["means3D"], m2, a["opacities"], shs=a["shs"], scales=a["scales"], rotations=a["rotations"])
+        calls_before = R._state(dev).geom_cache[torch.cuda.current_stream(dev).cuda_stream][0]
+        second = rast(a["means3D"], m2, a["opacities"], colors_precomp=normals, scales=a["scales"], rotations=a["rotations"])
+        assert R._state(dev).geom_cache[torch.cuda.current_stream(dev).cuda_stream][0] == calls_before  # hit: cache untouched
+        for x, y in zip(full, second):
+            assert torch.equal(x, y)
+        assert torch.equal(first[1], second[1]) and torch.equal(first[3], second[3])
+        # in-place change of the geometry bumps the version counter -> the next precomp pass is a full forward again
+        moved = a["means3D"].clone()
+        rast(moved, m2, a["opacities"], shs=a["shs"], scales=a["scales"], rotations=a["rotations"])
+        moved.add_(0.01)
+        third = rast(moved, m2, a["opacities"], colors_precomp=normals, scales=a["scales"], rotations=a["rotations"])
+        R.set_geometry_reuse(False)
+        want = rast(moved, m2, a["opacities"], colors_precomp=normals, scales=a["scales"], rotations=a["rotations"])
+        R.set_geometry_reuse(True)
+        for x, y in zip(third, want):
+            assert torch.equal(x, y)
