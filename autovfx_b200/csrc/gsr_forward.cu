@@ -644,13 +644,10 @@ __device__ void sort_bucket(const unsigned long long* __restrict__ g, uint32_t n
     }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __restrict__ ranges, unsigned long long* __restrict__ pairs,
-                                                             uint32_t* __restrict__ point_list,
-                                                             const gsr_counters* __restrict__ counters, int keep_pairs) {
-    if (counters->overflow) return;
-    __shared__ unsigned long long s[SORT_CAP];
-    __shared__ uint32_t hist[SORT_BUCKETS + 1];
-    const uint2 rg = ranges[blockIdx.x];
+// Sorts the bucket of one tile (pairs[rg.x..rg.y) by (depth bits, id)) and writes the ids to point_list.
+// s: SORT_CAP u64 of shared memory, hist: SORT_BUCKETS+1 u32.  Block-wide (SORT_THREADS threads), ends without a barrier.
+__device__ void sort_tile(const uint2 rg, unsigned long long* __restrict__ pairs, uint32_t* __restrict__ point_list, int keep_pairs,
+                          unsigned long long* s, uint32_t* hist) {
     const uint32_t n = rg.y - rg.x;
     if (n == 0) return;
     unsigned long long* g = pairs + rg.x;
@@ -693,6 +690,16 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __rest
     for (uint32_t i = tid; i < n; i += SORT_THREADS) out[i] = (uint32_t)g[i];
 }
 
+// stand-alone sort kernel (GSR_FUSE_SORT=0); by default the sort runs as the prologue of k_blend
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __restrict__ ranges, unsigned long long* __restrict__ pairs,
+                                                             uint32_t* __restrict__ point_list,
+                                                             const gsr_counters* __restrict__ counters, int keep_pairs) {
+    if (counters->overflow) return;
+    __shared__ unsigned long long s[SORT_CAP];
+    __shared__ uint32_t hist[SORT_BUCKETS + 1];
+    sort_tile(ranges[blockIdx.x], pairs, point_list, keep_pairs, s, hist);
+}
+
 // =====================================================================================================
 // Kernel 5: per-tile front-to-back alpha blend (forward.cu:261-378)
 // One CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel footprint.
@@ -702,7 +709,12 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __rest
 //   blend   : the queue is walked by all 32 lanes with the reference's per-pixel arithmetic
 // =====================================================================================================
 constexpr int BLEND_THREADS = 256;
-constexpr int BLEND_QCAP = 64;  // queue entries per warp (flushed when fewer than 32 slots remain)
+constexpr int BLEND_QCAP = 62;  // queue entries per warp (flushed when fewer than 32 slots remain)
+constexpr int BLEND_REC_BYTES = 2 * BLEND_THREADS * 48;                    // two staged batches, 48 B per splat
+constexpr int BLEND_Q_BYTES = (BLEND_THREADS / 32) * BLEND_QCAP * 48;       // per-warp survivor queues
+constexpr int SORT_SMEM_BYTES = SORT_CAP * 8 + (SORT_BUCKETS + 1) * 4;
+constexpr int BLEND_SMEM_BYTES = BLEND_REC_BYTES + BLEND_Q_BYTES > SORT_SMEM_BYTES ? BLEND_REC_BYTES + BLEND_Q_BYTES : SORT_SMEM_BYTES;
+static_assert(BLEND_THREADS == SORT_THREADS, "the fused sort prologue uses the blend CTA");
 
 __device__ __forceinline__ float4 lds128(uint32_t a) {
     float4 v;
@@ -713,14 +725,27 @@ __device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-__global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+// SORT: the CTA first sorts its tile's bucket (sort_tile) in the same shared memory, then blends it.  The sort is
+// latency/barrier bound and the blend issue bound, so running them in one kernel lets the sort phases of some CTAs
+// overlap the blend phases of others, and saves a launch.  point_list is written and then read by the same CTA,
+// hence no __restrict__/read-only path on it.
+template <bool SORT>
+__global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict__ ranges, uint32_t* point_list,
+                                                         unsigned long long* pairs, int keep_pairs,
                                                          const float4* __restrict__ records, int W, int H, int gx,
                                                          const float* __restrict__ bg, float* __restrict__ out_color,
                                                          float* __restrict__ out_depth, float* __restrict__ out_alpha,
                                                          uint32_t* __restrict__ n_contrib,
                                                          const gsr_counters* __restrict__ counters) {
-    __shared__ __align__(16) float4 sRec[2 * BLEND_THREADS * 3];                   // two staged batches, 48 B per splat
-    __shared__ __align__(16) float4 sQ[(BLEND_THREADS / 32) * BLEND_QCAP * 3];     // per-warp survivor queues
+    __shared__ __align__(16) unsigned char smem_raw[BLEND_SMEM_BYTES];
+    float4* sRec = reinterpret_cast<float4*>(smem_raw);
+    float4* sQ = reinterpret_cast<float4*>(smem_raw + BLEND_REC_BYTES);
+    if (SORT) {
+        if (!counters->overflow)
+            sort_tile(ranges[blockIdx.y * gx + blockIdx.x], pairs, point_list, keep_pairs, reinterpret_cast<unsigned long long*>(smem_raw),
+                      reinterpret_cast<uint32_t*>(smem_raw + SORT_CAP * 8));
+        __syncthreads();  // point_list of this tile is complete and visible to the whole CTA; shared memory is free again
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.y * gx + blockIdx.x;
     const int X0 = blockIdx.x * GSR_TILE + (warp & 1) * 8, Y0 = blockIdx.y * GSR_TILE + (warp >> 1) * 4;
@@ -914,6 +939,14 @@ int profile_end(float* ms, int* frames) {
 // =====================================================================================================
 // host side
 // =====================================================================================================
+static int fuse_sort_mode() {  // GSR_FUSE_SORT=0 runs the tile sort as its own kernel
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("GSR_FUSE_SORT");
+        mode = (e && strcmp(e, "0") == 0) ? 0 : 1;
+    }
+    return mode;
+}
 static int sh_bulk_mode() {  // GSR_SH_STAGING=cpasync selects the LDGSTS path, default is the TMA bulk copy
     static int mode = -1;
     if (mode < 0) {
@@ -976,9 +1009,9 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
         k_recolor<<<(f->P + 255) / 256, 256, 0, st>>>(f->P, radii, f->colors_precomp, (float4*)(geo + gl.records));
         int rc0 = check_launch("gsr_forward/recolor", debug, st);
         if (rc0) return rc0;
-        k_blend<<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>((const uint2*)(img + il.ranges), (const uint32_t*)(bin + bl.point_list),
-                                                              (const float4*)(geo + gl.records), f->W, f->H, il.gx, f->bg, out_color, out_depth,
-                                                              out_alpha, nullptr, counters);
+        k_blend<false><<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>((const uint2*)(img + il.ranges), (uint32_t*)(bin + bl.point_list), nullptr, 0,
+                                                                     (const float4*)(geo + gl.records), f->W, f->H, il.gx, f->bg, out_color,
+                                                                     out_depth, out_alpha, nullptr, counters);
         return check_launch("gsr_forward/blend(reuse)", debug, st);
     }
 
@@ -1028,15 +1061,21 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     prof_mark(3, st);
     if ((rc = check_launch("gsr_forward/emit", debug, st))) return rc;
 
-    k_sort_tiles<<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list),
-                                                   counters, (flags & GSR_FLAG_SORTED_KEYS) ? 1 : 0);
-    prof_mark(4, st);
-    if ((rc = check_launch("gsr_forward/sort", debug, st))) return rc;
-
-    k_blend<<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>(ranges, (const uint32_t*)(bin + bl.point_list), pp.records, f->W, f->H, il.gx,
-                                                          f->bg, out_color, out_depth, out_alpha,
-                                                          (flags & GSR_FLAG_FOR_BACKWARD) ? (uint32_t*)(img + il.n_contrib) : nullptr,
-                                                          counters);
+    const int keep_pairs = (flags & GSR_FLAG_SORTED_KEYS) ? 1 : 0;
+    uint32_t* n_contrib = (flags & GSR_FLAG_FOR_BACKWARD) ? (uint32_t*)(img + il.n_contrib) : nullptr;
+    if (fuse_sort_mode()) {
+        prof_mark(4, st);  // the sort runs inside k_blend: its slot in the per-kernel timing stays empty
+        k_blend<true><<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>(ranges, (uint32_t*)(bin + bl.point_list), (unsigned long long*)(bin + bl.pairs),
+                                                                    keep_pairs, pp.records, f->W, f->H, il.gx, f->bg, out_color, out_depth,
+                                                                    out_alpha, n_contrib, counters);
+    } else {
+        k_sort_tiles<<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters,
+                                                       keep_pairs);
+        prof_mark(4, st);
+        if ((rc = check_launch("gsr_forward/sort", debug, st))) return rc;
+        k_blend<false><<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>(ranges, (uint32_t*)(bin + bl.point_list), nullptr, 0, pp.records, f->W, f->H,
+                                                                     il.gx, f->bg, out_color, out_depth, out_alpha, n_contrib, counters);
+    }
     prof_mark(5, st);
     if (g_prof.on && g_prof.frames < g_prof.max_frames) g_prof.frames++;
     return check_launch("gsr_forward/blend", debug, st);
