@@ -690,7 +690,7 @@ __device__ void sort_tile(const uint2 rg, unsigned long long* __restrict__ pairs
     for (uint32_t i = tid; i < n; i += SORT_THREADS) out[i] = (uint32_t)g[i];
 }
 
-// stand-alone sort kernel (GSR_FUSE_SORT=0); by default the sort runs as the prologue of k_blend
+// stand-alone sort kernel (default); GSR_FUSE_SORT=1 runs the sort as the prologue of k_blend instead
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __restrict__ ranges, unsigned long long* __restrict__ pairs,
                                                              uint32_t* __restrict__ point_list,
                                                              const gsr_counters* __restrict__ counters, int keep_pairs) {
@@ -725,10 +725,10 @@ __device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// SORT: the CTA first sorts its tile's bucket (sort_tile) in the same shared memory, then blends it.  The sort is
-// latency/barrier bound and the blend issue bound, so running them in one kernel lets the sort phases of some CTAs
-// overlap the blend phases of others, and saves a launch.  point_list is written and then read by the same CTA,
-// hence no __restrict__/read-only path on it.
+// SORT (experiment, GSR_FUSE_SORT=1): the CTA first sorts its tile's bucket (sort_tile) in the same shared memory, then
+// blends it.  Measured on B200 (profiles/r01_experiments.md): fused 0.689 ms vs 0.101 + 0.582 ms separate — the blend
+// already issues 86 % of its cycles, so the sort's instructions simply add; kept off.  point_list is written and
+// then read by the same CTA, hence no __restrict__/read-only path on it.
 template <bool SORT>
 __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict__ ranges, uint32_t* point_list,
                                                          unsigned long long* pairs, int keep_pairs,
@@ -939,11 +939,11 @@ int profile_end(float* ms, int* frames) {
 // =====================================================================================================
 // host side
 // =====================================================================================================
-static int fuse_sort_mode() {  // GSR_FUSE_SORT=0 runs the tile sort as its own kernel
+static int fuse_sort_mode() {  // GSR_FUSE_SORT=1 runs the tile sort as the prologue of k_blend (measured: no gain, off by default)
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("GSR_FUSE_SORT");
-        mode = (e && strcmp(e, "0") == 0) ? 0 : 1;
+        mode = (e && strcmp(e, "1") == 0) ? 1 : 0;
     }
     return mode;
 }
