@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __rest
 //   blend   : the queue is walked by all 32 lanes with the reference's per-pixel arithmetic
 // =====================================================================================================
 constexpr int BLEND_THREADS = 256;
-constexpr int BLEND_QCAP = 62;  // queue entries per warp (flushed when fewer than 32 slots remain)
+constexpr int BLEND_QCAP = 62;  // queue entries per warp, an even number (flushed when fewer than 32 slots remain)
 constexpr int BLEND_REC_BYTES = 2 * BLEND_THREADS * 48;                    // two staged batches, 48 B per splat
 constexpr int BLEND_Q_BYTES = (BLEND_THREADS / 32) * BLEND_QCAP * 48;       // per-warp survivor queues
 constexpr int SORT_SMEM_BYTES = SORT_CAP * 8 + (SORT_BUCKETS + 1) * 4;
@@ -723,6 +723,37 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
 }
 __device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+
+// Blackwell packed fp32: one FFMA2 / FMUL2 / FADD2 performs two IEEE round-to-nearest operations, one per 32-bit half
+// of a 64-bit register pair.  The blend evaluates TWO queued splats per iteration in the two halves.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
 }
 
 // SORT (experiment, GSR_FUSE_SORT=1): the CTA first sorts its tile's bucket (sort_tile) in the same shared memory, then
@@ -769,32 +800,68 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
     uint32_t last = 0;
     int qn = 0;  // entries in this warp's queue (warp-uniform)
 
-    // blend every queued splat into this lane's pixel (reference arithmetic, forward.cu:330-366)
-    // Branch-free: every lane evaluates every queued splat; the three skip rules of the reference (power > 0,
-    // alpha < 1/255, T(1-alpha) < 1e-4) become predicates, and a skipped splat contributes through a transmittance of
-    // exactly 0 (x + y*0 == x), so the accumulated values are bitwise those of the branching form while two splats can
-    // be in flight per lane.
+    // Blend every queued splat into this lane's pixel (reference arithmetic, forward.cu:330-366), two splats per
+    // iteration.  The queue stores splats pair-interleaved ({x0,x1},{y0,y1},{a0,a1},{-b0,-b1},{c0,c1},{o0,o1},{r0,r1},
+    // {g0,g1},{b0,b1},{depth0,depth1},{pos0,pos1}, 96 B per pair) so that the per-splat arithmetic that does not depend
+    // on the running transmittance — power, alpha, 1-alpha, colour*alpha — runs on both halves of packed fp32
+    // registers (FFMA2/FMUL2/FADD2: two IEEE-rn results per instruction, bit-identical to the scalar ops; the sign of b
+    // is folded into the stored -b so the reference's `... - b*dx*dy` needs no negation).  Only expf, the 0.99 clamp
+    // and the serial transmittance updates stay scalar.  Branch-free: the three skip rules (power > 0, alpha < 1/255,
+    // T(1-alpha) < 1e-4) are predicates and a skipped splat contributes through a transmittance of exactly 0.
+    const f32x2 npx2 = pk2(-pixx, -pixx), npy2 = pk2(-pixy, -pixy), mhalf2 = pk2(-0.5f, -0.5f), mone2 = pk2(-1.0f, -1.0f),
+                one2 = pk2(1.0f, 1.0f);
     auto drain = [&]() {
+        if (qn & 1) {  // complete the last pair with a splat that can never hit (opacity 0)
+            if (lane < 11) sts32(q_base + (uint32_t)(qn >> 1) * 96 + 4 + lane * 8, 0.0f);
+        }
         __syncwarp();
         uint32_t qa = q_base;
-#pragma unroll 2
-        for (int k = 0; k < qn; k++, qa += 48) {
-            const float4 A = lds128(qa), B = lds128(qa + 16), Cc = lds128(qa + 32);
-            const float2 d = {A.x - pixx, A.y - pixy};
-            const float power = -0.5f * (A.z * d.x * d.x + B.x * d.y * d.y) - A.w * d.x * d.y;
-            const float alpha = min(0.99f, B.y * exp(power));
-            const bool hit = !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            const float test_T = T * (1 - alpha);
-            const bool live = hit && !(test_T < 0.0001f);
-            const bool dies = hit && (test_T < 0.0001f) && T != 0.0f;
-            const float Tw = live ? T : 0.0f;
-            C0 += Cc.x * alpha * Tw;
-            C1 += Cc.y * alpha * Tw;
-            C2 += Cc.z * alpha * Tw;
-            Dp += B.z * alpha * Tw;
-            T_out = dies ? T : T_out;
-            T = live ? test_T : (dies ? 0.0f : T);
-            last = live ? __float_as_uint(Cc.w) : last;
+        const int np = (qn + 1) >> 1;
+        for (int k = 0; k < np; k++, qa += 96) {
+            const float4 L0 = lds128(qa), L1 = lds128(qa + 16), L2 = lds128(qa + 32), L3 = lds128(qa + 48), L4 = lds128(qa + 64);
+            const float2 L5 = lds64(qa + 80);
+            const f32x2 dx = add2(pk2(L0.x, L0.y), npx2), dy = add2(pk2(L0.z, L0.w), npy2);
+            const f32x2 t1 = mul2(pk2(L2.x, L2.y), dy);   // c * dy
+            const f32x2 t3 = mul2(pk2(L1.x, L1.y), dx);   // a * dx
+            const f32x2 t2 = mul2(pk2(L1.z, L1.w), dx);   // (-b) * dx
+            const f32x2 t4 = mul2(dy, t1);                // dy * (c dy)
+            const f32x2 t5 = mul2(dy, t2);                // -(dy * (b dx))
+            const f32x2 t6 = fma2(dx, t3, t4);            // a dx^2 + c dy^2
+            float p0, p1;
+            upk2(fma2(t6, mhalf2, t5), p0, p1);           // power = -0.5 (a dx^2 + c dy^2) - b dx dy
+            float a0, a1;
+            upk2(mul2(pk2(L2.z, L2.w), pk2(exp(p0), exp(p1))), a0, a1);  // opacity * exp(power)
+            a0 = min(0.99f, a0);
+            a1 = min(0.99f, a1);
+            const bool hit0 = !(p0 > 0.0f) && !(a0 < 1.0f / 255.0f), hit1 = !(p1 > 0.0f) && !(a1 < 1.0f / 255.0f);
+            const f32x2 al = pk2(a0, a1);
+            float om0, om1;
+            upk2(fma2(al, mone2, one2), om0, om1);        // 1 - alpha
+            float cr0, cr1, cg0, cg1, cb0, cb1, cd0, cd1;
+            upk2(mul2(pk2(L3.x, L3.y), al), cr0, cr1);    // colour * alpha
+            upk2(mul2(pk2(L3.z, L3.w), al), cg0, cg1);
+            upk2(mul2(pk2(L4.x, L4.y), al), cb0, cb1);
+            upk2(mul2(pk2(L4.z, L4.w), al), cd0, cd1);
+            {   // first splat of the pair
+                const float test_T = T * om0;
+                const bool live = hit0 && !(test_T < 0.0001f);
+                const bool dies = hit0 && (test_T < 0.0001f) && T != 0.0f;
+                const float Tw = live ? T : 0.0f;
+                C0 = fmaf(Tw, cr0, C0); C1 = fmaf(Tw, cg0, C1); C2 = fmaf(Tw, cb0, C2); Dp = fmaf(Tw, cd0, Dp);
+                T_out = dies ? T : T_out;
+                T = live ? test_T : (dies ? 0.0f : T);
+                last = live ? __float_as_uint(L5.x) : last;
+            }
+            {   // second splat of the pair
+                const float test_T = T * om1;
+                const bool live = hit1 && !(test_T < 0.0001f);
+                const bool dies = hit1 && (test_T < 0.0001f) && T != 0.0f;
+                const float Tw = live ? T : 0.0f;
+                C0 = fmaf(Tw, cr1, C0); C1 = fmaf(Tw, cg1, C1); C2 = fmaf(Tw, cb1, C2); Dp = fmaf(Tw, cd1, Dp);
+                T_out = dies ? T : T_out;
+                T = live ? test_T : (dies ? 0.0f : T);
+                last = live ? __float_as_uint(L5.y) : last;
+            }
         }
         qn = 0;
         __syncwarp();
@@ -842,8 +909,12 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
                 const unsigned mask = __ballot_sync(GSR_FULL, keep);
                 if (mask) {
                     if (keep) {
-                        const uint32_t qa = q_base + (uint32_t)(qn + __popc(mask & lt_mask)) * 48;
-                        sts128(qa, A); sts128(qa + 16, B); sts128(qa + 32, lds128(sa + 32));
+                        const uint32_t q = (uint32_t)(qn + __popc(mask & lt_mask));
+                        const uint32_t qa = q_base + (q >> 1) * 96 + (q & 1) * 4;
+                        const float4 Cc = lds128(sa + 32);
+                        sts32(qa, A.x); sts32(qa + 8, A.y); sts32(qa + 16, A.z); sts32(qa + 24, -A.w);
+                        sts32(qa + 32, B.x); sts32(qa + 40, B.y); sts32(qa + 48, Cc.x); sts32(qa + 56, Cc.y);
+                        sts32(qa + 64, Cc.z); sts32(qa + 72, B.z); sts32(qa + 80, Cc.w);
                     }
                     qn += __popc(mask);
                     if (qn > BLEND_QCAP - 32) {
