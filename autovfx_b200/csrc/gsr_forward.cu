@@ -755,6 +755,28 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+// expf() of both halves, bit-identical to CUDA's scalar expf (the sequence nvcc 12.9 emits for it: saturating range
+// reduction, round-down magic-number trick, two-constant log2(e) split, ex2.approx, scale by 2^n), with the middle steps
+// packed.  Verified against expf over a dense sweep of the blend's input range by gsr_selftest (tests/test_gpu_parity.py).
+__device__ __forceinline__ f32x2 exp2x(f32x2 x) {
+    float x0, x1;
+    upk2(x, x0, x1);
+    float t0, t1;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(t0) : "f"(x0), "f"(__uint_as_float(0x3bbb989du)), "f"(0.5f));
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(t1) : "f"(x1), "f"(__uint_as_float(0x3bbb989du)), "f"(0.5f));
+    f32x2 r;
+    asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(t0, t1)), "l"(pk2(252.0f, 252.0f)), "l"(pk2(12582913.0f, 12582913.0f)));
+    const f32x2 nu = fma2(r, pk2(-1.0f, -1.0f), pk2(12583039.0f, 12583039.0f));  // -(r - 12583039), exact
+    float r0, r1;
+    upk2(r, r0, r1);
+    f32x2 v = fma2(x, pk2(__uint_as_float(0x3fb8aa3bu), __uint_as_float(0x3fb8aa3bu)), nu);
+    v = fma2(x, pk2(__uint_as_float(0x32a57060u), __uint_as_float(0x32a57060u)), v);
+    float v0, v1, e0, e1;
+    upk2(v, v0, v1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(v0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(v1));
+    return mul2(pk2(__uint_as_float(__float_as_uint(r0) << 23), __uint_as_float(__float_as_uint(r1) << 23)), pk2(e0, e1));
+}
 
 // SORT (experiment, GSR_FUSE_SORT=1): the CTA first sorts its tile's bucket (sort_tile) in the same shared memory, then
 // blends it.  Measured on B200 (profiles/r01_experiments.md): fused 0.689 ms vs 0.101 + 0.582 ms separate — the blend
@@ -827,10 +849,11 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
             const f32x2 t4 = mul2(dy, t1);                // dy * (c dy)
             const f32x2 t5 = mul2(dy, t2);                // -(dy * (b dx))
             const f32x2 t6 = fma2(dx, t3, t4);            // a dx^2 + c dy^2
+            const f32x2 pw = fma2(t6, mhalf2, t5);        // power = -0.5 (a dx^2 + c dy^2) - b dx dy
             float p0, p1;
-            upk2(fma2(t6, mhalf2, t5), p0, p1);           // power = -0.5 (a dx^2 + c dy^2) - b dx dy
+            upk2(pw, p0, p1);
             float a0, a1;
-            upk2(mul2(pk2(L2.z, L2.w), pk2(exp(p0), exp(p1))), a0, a1);  // opacity * exp(power)
+            upk2(mul2(pk2(L2.z, L2.w), exp2x(pw)), a0, a1);  // opacity * exp(power)
             a0 = min(0.99f, a0);
             a1 = min(0.99f, a1);
             const bool hit0 = !(p0 > 0.0f) && !(a0 < 1.0f / 255.0f), hit1 = !(p1 > 0.0f) && !(a1 < 1.0f / 255.0f);
@@ -944,6 +967,33 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
         out_color[2 * HW + pid] = C2 + T_out * bg[2];
         out_depth[pid] = Dp;
     }
+}
+
+// =====================================================================================================
+// self test: exp2x (packed expf used by the blend) against expf, bit for bit, over a sweep of float bit patterns
+// =====================================================================================================
+__global__ void k_selftest_exp(uint32_t lo_bits, uint32_t hi_bits, uint32_t stride, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long b = lo_bits + (unsigned long long)(blockIdx.x * blockDim.x + threadIdx.x) * stride; b <= hi_bits;
+         b += (unsigned long long)gridDim.x * blockDim.x * stride) {
+        const float x0 = __uint_as_float((uint32_t)b), x1 = __uint_as_float((uint32_t)b ^ 0x00000155u);
+        float e0, e1;
+        upk2(exp2x(pk2(x0, x1)), e0, e1);
+        bad += (__float_as_uint(e0) != __float_as_uint(expf(x0))) + (__float_as_uint(e1) != __float_as_uint(expf(x1)));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+int selftest_impl(unsigned long long* mismatches_host) {
+    unsigned long long* d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) { set_error("gsr_selftest: cudaMalloc failed"); return GSR_ERR_CUDA; }
+    cudaMemset(d, 0, 8);
+    // negative floats from -0 down to -120 (every 16th bit pattern), and positive floats up to 2.0 (every 16th)
+    k_selftest_exp<<<1184, 256>>>(0x80000000u, 0xC2F00000u, 16u, d);
+    k_selftest_exp<<<1184, 256>>>(0x00000000u, 0x40000000u, 16u, d);
+    cudaError_t e = cudaMemcpy(mismatches_host, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { set_error("gsr_selftest: %s", cudaGetErrorString(e)); return GSR_ERR_CUDA; }
+    return GSR_OK;
 }
 
 // =====================================================================================================
