@@ -782,7 +782,7 @@ __device__ __forceinline__ f32x2 exp2x(f32x2 x) {
 // blends it.  Measured on B200 (profiles/r01_experiments.md): fused 0.689 ms vs 0.101 + 0.582 ms separate — the blend
 // already issues 86 % of its cycles, so the sort's instructions simply add; kept off.  point_list is written and
 // then read by the same CTA, hence no __restrict__/read-only path on it.
-template <bool SORT>
+template <bool SORT, bool PEXP>
 __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict__ ranges, uint32_t* point_list,
                                                          unsigned long long* pairs, int keep_pairs,
                                                          const float4* __restrict__ records, int W, int H, int gx,
@@ -853,7 +853,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
             float p0, p1;
             upk2(pw, p0, p1);
             float a0, a1;
-            upk2(mul2(pk2(L2.z, L2.w), exp2x(pw)), a0, a1);  // opacity * exp(power)
+            upk2(mul2(pk2(L2.z, L2.w), PEXP ? exp2x(pw) : pk2(exp(p0), exp(p1))), a0, a1);  // opacity * exp(power)
             a0 = min(0.99f, a0);
             a1 = min(0.99f, a1);
             const bool hit0 = !(p0 > 0.0f) && !(a0 < 1.0f / 255.0f), hit1 = !(p1 > 0.0f) && !(a1 < 1.0f / 255.0f);
@@ -1068,6 +1068,14 @@ static int fuse_sort_mode() {  // GSR_FUSE_SORT=1 runs the tile sort as the prol
     }
     return mode;
 }
+static int packed_exp_mode() {  // GSR_BLEND_EXP=scalar uses two scalar expf per splat pair instead of the packed exp2x
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("GSR_BLEND_EXP");
+        mode = (e && strcmp(e, "scalar") == 0) ? 0 : 1;
+    }
+    return mode;
+}
 static int sh_bulk_mode() {  // GSR_SH_STAGING=cpasync selects the LDGSTS path, default is the TMA bulk copy
     static int mode = -1;
     if (mode < 0) {
@@ -1130,7 +1138,7 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
         k_recolor<<<(f->P + 255) / 256, 256, 0, st>>>(f->P, radii, f->colors_precomp, (float4*)(geo + gl.records));
         int rc0 = check_launch("gsr_forward/recolor", debug, st);
         if (rc0) return rc0;
-        k_blend<false><<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>((const uint2*)(img + il.ranges), (uint32_t*)(bin + bl.point_list), nullptr, 0,
+        k_blend<false, true><<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>((const uint2*)(img + il.ranges), (uint32_t*)(bin + bl.point_list), nullptr, 0,
                                                                      (const float4*)(geo + gl.records), f->W, f->H, il.gx, f->bg, out_color,
                                                                      out_depth, out_alpha, nullptr, counters);
         return check_launch("gsr_forward/blend(reuse)", debug, st);
@@ -1186,7 +1194,7 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     uint32_t* n_contrib = (flags & GSR_FLAG_FOR_BACKWARD) ? (uint32_t*)(img + il.n_contrib) : nullptr;
     if (fuse_sort_mode()) {
         prof_mark(4, st);  // the sort runs inside k_blend: its slot in the per-kernel timing stays empty
-        k_blend<true><<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>(ranges, (uint32_t*)(bin + bl.point_list), (unsigned long long*)(bin + bl.pairs),
+        k_blend<true, true><<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>(ranges, (uint32_t*)(bin + bl.point_list), (unsigned long long*)(bin + bl.pairs),
                                                                     keep_pairs, pp.records, f->W, f->H, il.gx, f->bg, out_color, out_depth,
                                                                     out_alpha, n_contrib, counters);
     } else {
@@ -1194,8 +1202,12 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
                                                        keep_pairs);
         prof_mark(4, st);
         if ((rc = check_launch("gsr_forward/sort", debug, st))) return rc;
-        k_blend<false><<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>(ranges, (uint32_t*)(bin + bl.point_list), nullptr, 0, pp.records, f->W, f->H,
-                                                                     il.gx, f->bg, out_color, out_depth, out_alpha, n_contrib, counters);
+        if (packed_exp_mode())
+            k_blend<false, true><<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>(ranges, (uint32_t*)(bin + bl.point_list), nullptr, 0, pp.records, f->W,
+                                                                               f->H, il.gx, f->bg, out_color, out_depth, out_alpha, n_contrib, counters);
+        else
+            k_blend<false, false><<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>(ranges, (uint32_t*)(bin + bl.point_list), nullptr, 0, pp.records, f->W,
+                                                                                f->H, il.gx, f->bg, out_color, out_depth, out_alpha, n_contrib, counters);
     }
     prof_mark(5, st);
     if (g_prof.on && g_prof.frames < g_prof.max_frames) g_prof.frames++;
