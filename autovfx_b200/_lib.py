@@ -48,11 +48,12 @@ GSR_FLAG_FOR_BACKWARD = 1
 GSR_FLAG_SORTED_KEYS = 2
 GSR_FLAG_TIGHT_TILES = 4
 GSR_FLAG_REUSE_GEOMETRY = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = ("gsr_abi_version", "gsr_last_error", "gsr_geom_bytes", "gsr_binning_bytes", "gsr_binning_capacity", "gsr_image_bytes",
            "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_dist2_bytes", "gsr_dist2", "gsr_get_views",
-           "gsr_profile_begin", "gsr_profile_end", "gsr_selftest")
+           "gsr_profile_begin", "gsr_profile_end", "gsr_selftest", "gsr_forward_multi", "gsr_axis_normals", "gsr_normal_maps",
+           "gsr_pack_frame")
 
 
 def _load() -> C.CDLL:
@@ -83,6 +84,17 @@ def _load() -> C.CDLL:
     lib.gsr_forward.restype = C.c_int
     lib.gsr_forward.argtypes = [C.POINTER(gsr_frame), C.POINTER(gsr_workspace), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_void_p]
+    lib.gsr_forward_multi.restype = C.c_int
+    lib.gsr_forward_multi.argtypes = [C.POINTER(gsr_frame), C.POINTER(gsr_workspace), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.gsr_axis_normals.restype = C.c_int
+    lib.gsr_axis_normals.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.gsr_normal_maps.restype = C.c_int
+    lib.gsr_normal_maps.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gsr_pack_frame.restype = C.c_int
+    lib.gsr_pack_frame.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
     lib.gsr_backward.restype = C.c_int
     lib.gsr_backward.argtypes = [C.POINTER(gsr_frame), C.POINTER(gsr_workspace), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.POINTER(gsr_grads), C.c_void_p]

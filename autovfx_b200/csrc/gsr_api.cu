@@ -3,7 +3,13 @@
 
 namespace gsr {
 int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,
-                 int32_t* radii, int flags, cudaStream_t st);
+                 int32_t* radii, const float* extra_colors, float* out_extra, int flags, cudaStream_t st);
+int axis_normals_impl(int P, const float* means3D, const float* scales, const float* rotations, const float* campos, int remap01,
+                      float* out, cudaStream_t st);
+int normal_maps_impl(int W, int H, const float* normal_img, const float* depth, const float* c2w, float fx, float fy, float cx, float cy,
+                     float* out_normal, float* out_pseudo, cudaStream_t st);
+int pack_frame_impl(int W, int H, const float* rgb, const float* alpha, const float* depth, const float* normal_hwc, float depth_scale,
+                    uint8_t* rgba8, uint8_t* normal8, uint8_t* depth8, cudaStream_t st);
 int backward_impl(const gsr_frame* f, const gsr_workspace* ws, const int32_t* radii, const float* out_alpha, const float* dL_dc,
                   const float* dL_dd, const float* dL_da, const gsr_grads* g, cudaStream_t st);
 int dist2_impl(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -34,7 +40,27 @@ size_t gsr_image_bytes(int32_t W, int32_t H) { return gsr::ImageLayout(W < 1 ? 1
 
 int gsr_forward(const gsr_frame* frame, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,
                 int32_t* radii, int flags, void* stream) {
-    return gsr::forward_impl(frame, ws, out_color, out_depth, out_alpha, radii, flags, (cudaStream_t)stream);
+    return gsr::forward_impl(frame, ws, out_color, out_depth, out_alpha, radii, nullptr, nullptr, flags, (cudaStream_t)stream);
+}
+
+int gsr_forward_multi(const gsr_frame* frame, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,
+                      int32_t* radii, const float* extra_colors, float* out_extra, int flags, void* stream) {
+    return gsr::forward_impl(frame, ws, out_color, out_depth, out_alpha, radii, extra_colors, out_extra, flags, (cudaStream_t)stream);
+}
+
+int gsr_axis_normals(int32_t P, const float* means3D, const float* scales, const float* rotations, const float* campos, int remap01,
+                     float* out, void* stream) {
+    return gsr::axis_normals_impl(P, means3D, scales, rotations, campos, remap01, out, (cudaStream_t)stream);
+}
+
+int gsr_normal_maps(int32_t W, int32_t H, const float* normal_img, const float* depth, const float* c2w, float fx, float fy, float cx,
+                    float cy, float* out_normal, float* out_pseudo, void* stream) {
+    return gsr::normal_maps_impl(W, H, normal_img, depth, c2w, fx, fy, cx, cy, out_normal, out_pseudo, (cudaStream_t)stream);
+}
+
+int gsr_pack_frame(int32_t W, int32_t H, const float* rgb, const float* alpha, const float* depth, const float* normal_hwc,
+                   float depth_scale, uint8_t* rgba8, uint8_t* normal8, uint8_t* depth8, void* stream) {
+    return gsr::pack_frame_impl(W, H, rgb, alpha, depth, normal_hwc, depth_scale, rgba8, normal8, depth8, (cudaStream_t)stream);
 }
 
 int gsr_backward(const gsr_frame* frame, const gsr_workspace* ws, const int32_t* radii, const float* out_alpha,

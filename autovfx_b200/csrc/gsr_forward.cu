@@ -690,7 +690,7 @@ __device__ void sort_tile(const uint2 rg, unsigned long long* __restrict__ pairs
     for (uint32_t i = tid; i < n; i += SORT_THREADS) out[i] = (uint32_t)g[i];
 }
 
-// stand-alone sort kernel (default); GSR_FUSE_SORT=1 runs the sort as the prologue of k_blend instead
+// stand-alone per-tile sort kernel (fusing it into the blend prologue was measured and dropped, profiles/r01_experiments.md)
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __restrict__ ranges, unsigned long long* __restrict__ pairs,
                                                              uint32_t* __restrict__ point_list,
                                                              const gsr_counters* __restrict__ counters, int keep_pairs) {
@@ -709,12 +709,17 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __rest
 //   blend   : the queue is walked by all 32 lanes with the reference's per-pixel arithmetic
 // =====================================================================================================
 constexpr int BLEND_THREADS = 256;
-constexpr int BLEND_QCAP = 62;  // queue entries per warp, an even number (flushed when fewer than 32 slots remain)
-constexpr int BLEND_REC_BYTES = 2 * BLEND_THREADS * 48;                    // two staged batches, 48 B per splat
-constexpr int BLEND_Q_BYTES = (BLEND_THREADS / 32) * BLEND_QCAP * 48;       // per-warp survivor queues
-constexpr int SORT_SMEM_BYTES = SORT_CAP * 8 + (SORT_BUCKETS + 1) * 4;
-constexpr int BLEND_SMEM_BYTES = BLEND_REC_BYTES + BLEND_Q_BYTES > SORT_SMEM_BYTES ? BLEND_REC_BYTES + BLEND_Q_BYTES : SORT_SMEM_BYTES;
-static_assert(BLEND_THREADS == SORT_THREADS, "the fused sort prologue uses the blend CTA");
+// NX = number of extra colour channels blended with the same weights (0, or 3 for the product frame's second image)
+template <int NX>
+struct BlendCfg {
+    static constexpr int REC = NX ? 64 : 48;     // staged bytes per splat (48-byte record + 16 bytes of extra colours)
+    static constexpr int PAIR = NX ? 112 : 96;   // queue bytes per splat pair
+    static constexpr int QCAP = 62;              // queue entries per warp, an even number (flushed when fewer than 32 slots remain)
+    static constexpr int REC_BYTES = 2 * BLEND_THREADS * REC;                  // two staged batches
+    static constexpr int Q_BYTES = (BLEND_THREADS / 32) * (QCAP / 2) * PAIR;   // per-warp survivor queues
+    static constexpr int SMEM = REC_BYTES + Q_BYTES;                           // dynamic shared memory of k_blend<.., NX>
+};
+static_assert(BlendCfg<0>::SMEM <= 48 * 1024, "k_blend<.,0> must fit the default dynamic shared memory limit");
 
 __device__ __forceinline__ float4 lds128(uint32_t a) {
     float4 v;
@@ -778,27 +783,23 @@ __device__ __forceinline__ f32x2 exp2x(f32x2 x) {
     return mul2(pk2(__uint_as_float(__float_as_uint(r0) << 23), __uint_as_float(__float_as_uint(r1) << 23)), pk2(e0, e1));
 }
 
-// SORT (experiment, GSR_FUSE_SORT=1): the CTA first sorts its tile's bucket (sort_tile) in the same shared memory, then
-// blends it.  Measured on B200 (profiles/r01_experiments.md): fused 0.689 ms vs 0.101 + 0.582 ms separate — the blend
-// already issues 86 % of its cycles, so the sort's instructions simply add; kept off.  point_list is written and
-// then read by the same CTA, hence no __restrict__/read-only path on it.
-template <bool SORT, bool PEXP>
-__global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict__ ranges, uint32_t* point_list,
-                                                         unsigned long long* pairs, int keep_pairs,
-                                                         const float4* __restrict__ records, int W, int H, int gx,
-                                                         const float* __restrict__ bg, float* __restrict__ out_color,
-                                                         float* __restrict__ out_depth, float* __restrict__ out_alpha,
+// PEXP: packed expf (exp2x) instead of two scalar expf per pair (same bits; measured 4.5 % slower, off by default).
+// NX  : extra colour channels `extra[P,NX]` accumulated with the same per-splat weights into `out_extra[NX,H,W]`
+//       (+ T_final * bg like the colour image) — what a second rasterizer pass with colors_precomp = extra would
+//       return (gaussian_renderer/__init__.py:151-185), without re-running projection, binning, sort and the alpha math.
+template <bool PEXP, int NX>
+__global__ void __launch_bounds__(BLEND_THREADS, (PEXP && !NX) ? 4 : 0) k_blend(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                                                         const float4* __restrict__ records, const float* __restrict__ extra,
+                                                         int W, int H, int gx, const float* __restrict__ bg,
+                                                         float* __restrict__ out_color, float* __restrict__ out_depth,
+                                                         float* __restrict__ out_alpha, float* __restrict__ out_extra,
                                                          uint32_t* __restrict__ n_contrib,
                                                          const gsr_counters* __restrict__ counters) {
-    __shared__ __align__(16) unsigned char smem_raw[BLEND_SMEM_BYTES];
+    typedef BlendCfg<NX> Cfg;
+    constexpr int REC = Cfg::REC, PAIR = Cfg::PAIR, BLEND_QCAP = Cfg::QCAP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* sRec = reinterpret_cast<float4*>(smem_raw);
-    float4* sQ = reinterpret_cast<float4*>(smem_raw + BLEND_REC_BYTES);
-    if (SORT) {
-        if (!counters->overflow)
-            sort_tile(ranges[blockIdx.y * gx + blockIdx.x], pairs, point_list, keep_pairs, reinterpret_cast<unsigned long long*>(smem_raw),
-                      reinterpret_cast<uint32_t*>(smem_raw + SORT_CAP * 8));
-        __syncthreads();  // point_list of this tile is complete and visible to the whole CTA; shared memory is free again
-    }
+    float4* sQ = reinterpret_cast<float4*>(smem_raw + Cfg::REC_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.y * gx + blockIdx.x;
     const int X0 = blockIdx.x * GSR_TILE + (warp & 1) * 8, Y0 = blockIdx.y * GSR_TILE + (warp >> 1) * 4;
@@ -807,7 +808,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
     const float pixx = (float)pxi, pixy = (float)pyi;
     const float cx = (float)X0 + FOOT_HX, cy = (float)Y0 + FOOT_HY;  // footprint centre
     const uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(sRec);
-    const uint32_t q_base = (uint32_t)__cvta_generic_to_shared(sQ) + (uint32_t)warp * (BLEND_QCAP * 48);
+    const uint32_t q_base = (uint32_t)__cvta_generic_to_shared(sQ) + (uint32_t)warp * ((BLEND_QCAP / 2) * PAIR);
     const unsigned lt_mask = (1u << lane) - 1u;
 
     uint2 range = ranges[tile];
@@ -818,13 +819,13 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
     // T is the running transmittance while the pixel is live.  When the pixel terminates (forward.cu:349-354) its
     // final transmittance moves to T_out and T becomes 0, so that every later splat fails the same `T(1-a) < 1e-4`
     // test on its own: no separate per-iteration "done" branch is needed.  Pixels outside the image start dead.
-    float T = inside ? 1.0f : 0.0f, T_out = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
+    float T = inside ? 1.0f : 0.0f, T_out = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f, E0 = 0.f, E1 = 0.f, E2 = 0.f;
     uint32_t last = 0;
     int qn = 0;  // entries in this warp's queue (warp-uniform)
 
     // Blend every queued splat into this lane's pixel (reference arithmetic, forward.cu:330-366), two splats per
     // iteration.  The queue stores splats pair-interleaved ({x0,x1},{y0,y1},{a0,a1},{-b0,-b1},{c0,c1},{o0,o1},{r0,r1},
-    // {g0,g1},{b0,b1},{depth0,depth1},{pos0,pos1}, 96 B per pair) so that the per-splat arithmetic that does not depend
+    // {g0,g1},{b0,b1},{depth0,depth1},{pos0,pos1}[,{e0,e0'},{e1,e1'},{e2,e2'}], 96 [112] B per pair) so that the per-splat arithmetic that does not depend
     // on the running transmittance — power, alpha, 1-alpha, colour*alpha — runs on both halves of packed fp32
     // registers (FFMA2/FMUL2/FADD2: two IEEE-rn results per instruction, bit-identical to the scalar ops; the sign of b
     // is folded into the stored -b so the reference's `... - b*dx*dy` needs no negation).  Only expf, the 0.99 clamp
@@ -834,14 +835,16 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
                 one2 = pk2(1.0f, 1.0f);
     auto drain = [&]() {
         if (qn & 1) {  // complete the last pair with a splat that can never hit (opacity 0)
-            if (lane < 11) sts32(q_base + (uint32_t)(qn >> 1) * 96 + 4 + lane * 8, 0.0f);
+            if (lane < 11 + NX) sts32(q_base + (uint32_t)(qn >> 1) * PAIR + 4 + lane * 8, 0.0f);
         }
         __syncwarp();
         uint32_t qa = q_base;
         const int np = (qn + 1) >> 1;
-        for (int k = 0; k < np; k++, qa += 96) {
+        for (int k = 0; k < np; k++, qa += PAIR) {
             const float4 L0 = lds128(qa), L1 = lds128(qa + 16), L2 = lds128(qa + 32), L3 = lds128(qa + 48), L4 = lds128(qa + 64);
-            const float2 L5 = lds64(qa + 80);
+            float4 L5, L6;  // {pos0,pos1[,e0,e0']}, {e1,e1',e2,e2'}
+            if (NX) { L5 = lds128(qa + 80); L6 = lds128(qa + 96); }
+            else { const float2 t = lds64(qa + 80); L5 = make_float4(t.x, t.y, 0.f, 0.f); L6 = L5; }
             const f32x2 dx = add2(pk2(L0.x, L0.y), npx2), dy = add2(pk2(L0.z, L0.w), npy2);
             const f32x2 t1 = mul2(pk2(L2.x, L2.y), dy);   // c * dy
             const f32x2 t3 = mul2(pk2(L1.x, L1.y), dx);   // a * dx
@@ -865,12 +868,19 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
             upk2(mul2(pk2(L3.z, L3.w), al), cg0, cg1);
             upk2(mul2(pk2(L4.x, L4.y), al), cb0, cb1);
             upk2(mul2(pk2(L4.z, L4.w), al), cd0, cd1);
+            float ex0 = 0.f, ex1 = 0.f, ey0 = 0.f, ey1 = 0.f, ez0 = 0.f, ez1 = 0.f;
+            if (NX) {
+                upk2(mul2(pk2(L5.z, L5.w), al), ex0, ex1);
+                upk2(mul2(pk2(L6.x, L6.y), al), ey0, ey1);
+                upk2(mul2(pk2(L6.z, L6.w), al), ez0, ez1);
+            }
             {   // first splat of the pair
                 const float test_T = T * om0;
                 const bool live = hit0 && !(test_T < 0.0001f);
                 const bool dies = hit0 && (test_T < 0.0001f) && T != 0.0f;
                 const float Tw = live ? T : 0.0f;
                 C0 = fmaf(Tw, cr0, C0); C1 = fmaf(Tw, cg0, C1); C2 = fmaf(Tw, cb0, C2); Dp = fmaf(Tw, cd0, Dp);
+                if (NX) { E0 = fmaf(Tw, ex0, E0); E1 = fmaf(Tw, ey0, E1); E2 = fmaf(Tw, ez0, E2); }
                 T_out = dies ? T : T_out;
                 T = live ? test_T : (dies ? 0.0f : T);
                 last = live ? __float_as_uint(L5.x) : last;
@@ -881,6 +891,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
                 const bool dies = hit1 && (test_T < 0.0001f) && T != 0.0f;
                 const float Tw = live ? T : 0.0f;
                 C0 = fmaf(Tw, cr1, C0); C1 = fmaf(Tw, cg1, C1); C2 = fmaf(Tw, cb1, C2); Dp = fmaf(Tw, cd1, Dp);
+                if (NX) { E0 = fmaf(Tw, ex1, E0); E1 = fmaf(Tw, ey1, E1); E2 = fmaf(Tw, ez1, E2); }
                 T_out = dies ? T : T_out;
                 T = live ? test_T : (dies ? 0.0f : T);
                 last = live ? __float_as_uint(L5.y) : last;
@@ -893,19 +904,24 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
     // Software pipeline over batches of 256 list entries, double-buffered in shared memory with ONE barrier per batch:
     // while batch b is culled/blended out of buffer b&1, the records of batch b+1 (already in registers, gathered
     // during batch b-1) are stored into the other buffer and the gather of batch b+2 is issued.
-    float4 ra = make_float4(0, 0, 0, 0), rb = ra, rc = ra;
+    float4 ra = make_float4(0, 0, 0, 0), rb = ra, rc = ra, rd = ra;
     uint32_t id_next = 0;
     auto gather = [&](int batch, uint32_t id) {  // records of list entry (batch, tid) -> registers
         if (batch * BLEND_THREADS + tid < n) {
             const float4* r = records + 3 * (size_t)id;
             ra = r[0]; rb = r[1]; rc = r[2];
             rc.w = __uint_as_float((uint32_t)(batch * BLEND_THREADS + tid + 1));  // 1-based position in the tile list
+            if (NX) {
+                const float* e = extra + 3 * (size_t)id;
+                rd = make_float4(e[0], e[1], e[2], 0.0f);
+            }
         }
     };
     auto stage = [&](int batch) {  // registers -> buffer batch&1
         if (batch * BLEND_THREADS + tid < n) {
-            const uint32_t sa = rec_base + (uint32_t)((batch & 1) * BLEND_THREADS + tid) * 48;
+            const uint32_t sa = rec_base + (uint32_t)((batch & 1) * BLEND_THREADS + tid) * REC;
             sts128(sa, ra); sts128(sa + 16, rb); sts128(sa + 32, rc);
+            if (NX) sts128(sa + 48, rd);
         }
     };
     if (tid < n) gather(0, point_list[range.x + tid]);
@@ -918,11 +934,11 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
 
     for (int b = 0; b < nb; b++) {
         const int cnt = min(BLEND_THREADS, n - b * BLEND_THREADS);
-        const uint32_t buf = rec_base + (uint32_t)((b & 1) * BLEND_THREADS) * 48;
+        const uint32_t buf = rec_base + (uint32_t)((b & 1) * BLEND_THREADS) * REC;
         if (!warp_done) {
             for (int base = 0; base < cnt; base += 32) {
                 const int s = base + lane;
-                const uint32_t sa = buf + (uint32_t)s * 48;
+                const uint32_t sa = buf + (uint32_t)s * REC;
                 bool keep = false;
                 float4 A, B;
                 if (s < cnt) {
@@ -933,11 +949,15 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
                 if (mask) {
                     if (keep) {
                         const uint32_t q = (uint32_t)(qn + __popc(mask & lt_mask));
-                        const uint32_t qa = q_base + (q >> 1) * 96 + (q & 1) * 4;
+                        const uint32_t qa = q_base + (q >> 1) * PAIR + (q & 1) * 4;
                         const float4 Cc = lds128(sa + 32);
                         sts32(qa, A.x); sts32(qa + 8, A.y); sts32(qa + 16, A.z); sts32(qa + 24, -A.w);
                         sts32(qa + 32, B.x); sts32(qa + 40, B.y); sts32(qa + 48, Cc.x); sts32(qa + 56, Cc.y);
                         sts32(qa + 64, Cc.z); sts32(qa + 72, B.z); sts32(qa + 80, Cc.w);
+                        if (NX) {
+                            const float4 Dd = lds128(sa + 48);
+                            sts32(qa + 88, Dd.x); sts32(qa + 96, Dd.y); sts32(qa + 104, Dd.z);
+                        }
                     }
                     qn += __popc(mask);
                     if (qn > BLEND_QCAP - 32) {
@@ -966,6 +986,11 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict
         out_color[HW + pid] = C1 + T_out * bg[1];
         out_color[2 * HW + pid] = C2 + T_out * bg[2];
         out_depth[pid] = Dp;
+        if (NX) {
+            out_extra[pid] = E0 + T_out * bg[0];
+            out_extra[HW + pid] = E1 + T_out * bg[1];
+            out_extra[2 * HW + pid] = E2 + T_out * bg[2];
+        }
     }
 }
 
@@ -1060,19 +1085,11 @@ int profile_end(float* ms, int* frames) {
 // =====================================================================================================
 // host side
 // =====================================================================================================
-static int fuse_sort_mode() {  // GSR_FUSE_SORT=1 runs the tile sort as the prologue of k_blend (measured: no gain, off by default)
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("GSR_FUSE_SORT");
-        mode = (e && strcmp(e, "1") == 0) ? 1 : 0;
-    }
-    return mode;
-}
-static int packed_exp_mode() {  // GSR_BLEND_EXP=scalar uses two scalar expf per splat pair instead of the packed exp2x
-    static int mode = -1;
+static int packed_exp_mode() {  // GSR_BLEND_EXP=packed: exp2x (two expf in packed fp32) instead of two scalar expf per splat pair;
+    static int mode = -1;       // same bits, measured 4.5 % slower in k_blend (FMA-pipe pressure), so off by default
     if (mode < 0) {
         const char* e = getenv("GSR_BLEND_EXP");
-        mode = (e && strcmp(e, "scalar") == 0) ? 0 : 1;
+        mode = (e && strcmp(e, "packed") == 0) ? 1 : 0;
     }
     return mode;
 }
@@ -1092,11 +1109,38 @@ static void launch_pre(bool vec, const PreParams& pp, cudaStream_t st) {
     else k_preprocess<DEG, false, false><<<grid, PRE_THREADS, 0, st>>>(pp);
 }
 
+struct BlendArgs {
+    const uint2* ranges; const uint32_t* point_list; const float4* records; const float* extra;
+    int W, H, gx, gy; const float* bg; float *out_color, *out_depth, *out_alpha, *out_extra; uint32_t* n_contrib;
+    const gsr_counters* counters;
+};
+template <bool PEXP, int NX>
+static void launch_blend_t(const BlendArgs& a, cudaStream_t st) {
+    if (NX) {  // 60 KB of dynamic shared memory: opt in once per device
+        static bool configured[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !configured[dev]) {
+            cudaFuncSetAttribute(k_blend<PEXP, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlendCfg<NX>::SMEM);
+            configured[dev] = true;
+        }
+    }
+    k_blend<PEXP, NX><<<dim3(a.gx, a.gy), BLEND_THREADS, BlendCfg<NX>::SMEM, st>>>(a.ranges, a.point_list, a.records, a.extra, a.W, a.H, a.gx, a.bg,
+                                                                                  a.out_color, a.out_depth, a.out_alpha, a.out_extra,
+                                                                                  a.n_contrib, a.counters);
+}
+static void launch_blend(const BlendArgs& a, cudaStream_t st) {
+    const bool px = packed_exp_mode() != 0;
+    if (a.extra) { if (px) launch_blend_t<true, 3>(a, st); else launch_blend_t<false, 3>(a, st); }
+    else         { if (px) launch_blend_t<true, 0>(a, st); else launch_blend_t<false, 0>(a, st); }
+}
+
 int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,
-                 int32_t* radii, int flags, cudaStream_t st) {
+                 int32_t* radii, const float* extra_colors, float* out_extra, int flags, cudaStream_t st) {
     if (!f || !ws) { set_error("gsr_forward: null frame/workspace"); return GSR_ERR_INVALID; }
     if (f->P < 0 || f->W <= 0 || f->H <= 0) { set_error("gsr_forward: bad sizes P=%d W=%d H=%d", f->P, f->W, f->H); return GSR_ERR_INVALID; }
     if (!out_color || !out_depth || !out_alpha) { set_error("gsr_forward: null output image"); return GSR_ERR_INVALID; }
+    if ((extra_colors == nullptr) != (out_extra == nullptr)) { set_error("gsr_forward_multi: extra_colors and out_extra go together"); return GSR_ERR_INVALID; }
     const size_t HW = (size_t)f->W * f->H;
     const ImageLayout il(f->W, f->H);
     if (!ws->image || ws->image_bytes < il.total) { set_error("gsr_forward: image workspace too small (%zu < %zu)", ws->image_bytes, il.total); return GSR_ERR_WORKSPACE; }
@@ -1107,6 +1151,7 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
         cudaMemsetAsync(out_color, 0, 12 * HW, st);
         cudaMemsetAsync(out_depth, 0, 4 * HW, st);
         cudaMemsetAsync(out_alpha, 0, 4 * HW, st);
+        if (out_extra) cudaMemsetAsync(out_extra, 0, 12 * HW, st);
         cudaMemsetAsync(img, 0, il.zero_bytes(), st);
         cudaMemsetAsync(img + il.ranges, 0, 8 * (size_t)il.tiles, st);
         return check_launch("gsr_forward(P=0)", debug, st);
@@ -1138,9 +1183,9 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
         k_recolor<<<(f->P + 255) / 256, 256, 0, st>>>(f->P, radii, f->colors_precomp, (float4*)(geo + gl.records));
         int rc0 = check_launch("gsr_forward/recolor", debug, st);
         if (rc0) return rc0;
-        k_blend<false, true><<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>((const uint2*)(img + il.ranges), (uint32_t*)(bin + bl.point_list), nullptr, 0,
-                                                                     (const float4*)(geo + gl.records), f->W, f->H, il.gx, f->bg, out_color,
-                                                                     out_depth, out_alpha, nullptr, counters);
+        BlendArgs ba{(const uint2*)(img + il.ranges), (const uint32_t*)(bin + bl.point_list), (const float4*)(geo + gl.records), extra_colors,
+                     f->W, f->H, il.gx, il.gy, f->bg, out_color, out_depth, out_alpha, out_extra, nullptr, counters};
+        launch_blend(ba, st);
         return check_launch("gsr_forward/blend(reuse)", debug, st);
     }
 
@@ -1192,23 +1237,12 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
 
     const int keep_pairs = (flags & GSR_FLAG_SORTED_KEYS) ? 1 : 0;
     uint32_t* n_contrib = (flags & GSR_FLAG_FOR_BACKWARD) ? (uint32_t*)(img + il.n_contrib) : nullptr;
-    if (fuse_sort_mode()) {
-        prof_mark(4, st);  // the sort runs inside k_blend: its slot in the per-kernel timing stays empty
-        k_blend<true, true><<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>(ranges, (uint32_t*)(bin + bl.point_list), (unsigned long long*)(bin + bl.pairs),
-                                                                    keep_pairs, pp.records, f->W, f->H, il.gx, f->bg, out_color, out_depth,
-                                                                    out_alpha, n_contrib, counters);
-    } else {
-        k_sort_tiles<<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters,
-                                                       keep_pairs);
-        prof_mark(4, st);
-        if ((rc = check_launch("gsr_forward/sort", debug, st))) return rc;
-        if (packed_exp_mode())
-            k_blend<false, true><<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>(ranges, (uint32_t*)(bin + bl.point_list), nullptr, 0, pp.records, f->W,
-                                                                               f->H, il.gx, f->bg, out_color, out_depth, out_alpha, n_contrib, counters);
-        else
-            k_blend<false, false><<<dim3(il.gx, il.gy), BLEND_THREADS, 0, st>>>(ranges, (uint32_t*)(bin + bl.point_list), nullptr, 0, pp.records, f->W,
-                                                                                f->H, il.gx, f->bg, out_color, out_depth, out_alpha, n_contrib, counters);
-    }
+    k_sort_tiles<<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters, keep_pairs);
+    prof_mark(4, st);
+    if ((rc = check_launch("gsr_forward/sort", debug, st))) return rc;
+    BlendArgs ba{ranges, (const uint32_t*)(bin + bl.point_list), pp.records, extra_colors, f->W, f->H, il.gx, il.gy, f->bg,
+                 out_color, out_depth, out_alpha, out_extra, n_contrib, counters};
+    launch_blend(ba, st);
     prof_mark(5, st);
     if (g_prof.on && g_prof.frames < g_prof.max_frames) g_prof.frames++;
     return check_launch("gsr_forward/blend", debug, st);

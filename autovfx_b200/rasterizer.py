@@ -32,7 +32,7 @@ from ._lib import lib as _L
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "set_sync_mode", "get_sync_mode",
            "set_tight_tiles", "get_tight_tiles", "set_geometry_reuse",
-           "last_frame_stats", "FrameTicket", "forward_raw", "debug_views"]
+           "last_frame_stats", "FrameTicket", "forward_raw", "forward_multi", "debug_views"]
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -220,11 +220,14 @@ def _fill_frame(fr: _lib.gsr_frame, P, D, M, W, H, settings, bg, means3D, shs, c
 
 def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, settings: GaussianRasterizationSettings,
                 for_backward: bool = False, sorted_keys: bool = False, sync: Optional[bool] = None, out=None,
-                tight: Optional[bool] = None):
+                tight: Optional[bool] = None, extra: Optional[torch.Tensor] = None, extra_out: Optional[torch.Tensor] = None):
     """One rasterizer forward through the C ABI.  Returns (color, depth, alpha, radii, workspaces, ticket, keepalive).
     ``workspaces`` = (geom, binning, image) byte tensors; fresh allocations when ``for_backward`` (they must outlive
     the call), otherwise per-(device, stream) cached buffers.  ``out`` optionally supplies preallocated
-    (color, depth, alpha, radii) tensors (used by the frame loop to render straight into its ring)."""
+    (color, depth, alpha, radii) tensors (used by the frame loop to render straight into its ring).  ``extra`` ([P,3]
+    colours) + ``extra_out`` ([3,H,W]) blend a second colour set in the same pass (gsr_forward_multi, see ``forward_multi``)."""
+    if (extra is None) != (extra_out is None):
+        raise ValueError("extra and extra_out go together")
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:57-59
     if not means3D.is_cuda:
@@ -238,6 +241,10 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
         shs, colors_precomp = _opt(shs, device), _opt(colors_precomp, device)
         scales, rotations, cov3D_precomp = _opt(scales, device), _opt(rotations, device), _opt(cov3D_precomp, device)
         opacities = _dev_f32(opacities, device)
+        if extra is not None:
+            extra = _dev_f32(extra, device)
+            if extra.shape != (P, 3) or extra_out.shape != (3, H, W) or extra_out.dtype != torch.float32 or not extra_out.is_contiguous():
+                raise ValueError("extra must be [P,3] and extra_out a contiguous float32 [3,H,W]")
         bg = _dev_f32(settings.bg, device)
         view = _dev_f32(settings.viewmatrix, device)
         proj = _dev_f32(settings.projmatrix, device)
@@ -275,8 +282,9 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
             # second pass over the same geometry: recolour + blend only
             _, _, radii_prev, binning = cached
             ws = _lib.gsr_workspace(geom.data_ptr(), geom.numel(), binning.data_ptr(), binning.numel(), image.data_ptr(), image.numel())
-            rc = _L.gsr_forward(C.byref(fr), C.byref(ws), color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), radii_prev.data_ptr(),
-                                flags | _lib.GSR_FLAG_REUSE_GEOMETRY, C.c_void_p(stream.cuda_stream))
+            rc = _L.gsr_forward_multi(C.byref(fr), C.byref(ws), color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), radii_prev.data_ptr(),
+                                      _ptr(extra) if P > 0 else None, _ptr(extra_out) if extra is not None and P > 0 else None,
+                                      flags | _lib.GSR_FLAG_REUSE_GEOMETRY, C.c_void_p(stream.cuda_stream))
             _lib.check(rc, "gsr_forward(reuse)")
             if out is None:
                 radii = radii_prev.clone()
@@ -289,14 +297,17 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
             st.last_ticket = ticket
             if do_sync and ticket.stats()["overflow"]:
                 raise RuntimeError("autovfx_b200: reused geometry pass found an overflowed first pass")
-            keep = (means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, view, proj, campos)
+            keep = (means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, view, proj, campos, extra)
             return color, depth, alpha, radii, (geom, binning, image), ticket, keep
         while True:
             cap = st.capacity
             binning = st.workspace("binning", _L.gsr_binning_bytes(cap), for_backward)
             ws = _lib.gsr_workspace(geom.data_ptr(), geom.numel(), binning.data_ptr(), binning.numel(), image.data_ptr(), image.numel())
-            rc = _L.gsr_forward(C.byref(fr), C.byref(ws), color.data_ptr(), depth.data_ptr(), alpha.data_ptr(),
-                                radii.data_ptr() if P > 0 else None, flags, C.c_void_p(stream.cuda_stream))
+            if extra is not None and P == 0:
+                extra_out.zero_()
+            rc = _L.gsr_forward_multi(C.byref(fr), C.byref(ws), color.data_ptr(), depth.data_ptr(), alpha.data_ptr(),
+                                      radii.data_ptr() if P > 0 else None, _ptr(extra) if P > 0 else None,
+                                      _ptr(extra_out) if extra is not None and P > 0 else None, flags, C.c_void_p(stream.cuda_stream))
             _lib.check(rc, "gsr_forward")
             slot, ev = st.next_slot()
             slot.copy_(image[:32].view(torch.int32), non_blocking=True)
@@ -314,8 +325,24 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
         if not for_backward and P > 0:
             # remember which geometry the shared workspaces now hold (tensors kept alive so their storage cannot be recycled)
             st.geom_cache[stream.cuda_stream] = (gkey, (means3D, opacities, scales, rotations, cov3D_precomp, view, proj, campos), radii, binning)
-    keep = (means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, view, proj, campos)
+    keep = (means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, view, proj, campos, extra)
     return color, depth, alpha, radii, (geom, binning, image), ticket, keep
+
+
+def forward_multi(means3D, shs, colors_precomp, extra_colors, opacities, scales, rotations, cov3D_precomp,
+                  settings: GaussianRasterizationSettings, sync: Optional[bool] = None, out=None, extra_out=None,
+                  tight: Optional[bool] = None):
+    """Both rasterizer passes of one product frame in ONE pass (forward only): ``(color, depth, alpha, extra_image, radii,
+    ticket)`` where ``extra_image`` [3,H,W] is bit-identical to the colour image a second
+    ``GaussianRasterizer(...)(colors_precomp=extra_colors, ...)`` call would return
+    (reference: gaussian_renderer/__init__.py:134-166 runs the whole pipeline twice)."""
+    H, W = int(settings.image_height), int(settings.image_width)
+    if extra_out is None:
+        extra_out = torch.empty((3, H, W), dtype=torch.float32, device=means3D.device)
+    color, depth, alpha, radii, _ws, ticket, _keep = forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                                               settings, sync=sync, out=out, tight=tight, extra=extra_colors,
+                                                               extra_out=extra_out)
+    return color, depth, alpha, extra_out, radii, ticket
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
@@ -333,7 +360,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.ticket = ticket
         ctx.has = (sh.numel() != 0, colors_precomp.numel() != 0, scales.numel() != 0, cov3Ds_precomp.numel() != 0)
         ctx.needs = need_bw
-        k_means3D, k_shs, k_colors, _k_op, k_scales, k_rot, k_cov, k_bg, k_view, k_proj, k_campos = keep
+        k_means3D, k_shs, k_colors, _k_op, k_scales, k_rot, k_cov, k_bg, k_view, k_proj, k_campos, _k_extra = keep
         e = torch.empty(0, device=means3D.device)
         ctx.save_for_backward(k_colors if k_colors is not None else e, k_means3D, k_scales if k_scales is not None else e,
                               k_rot if k_rot is not None else e, k_cov if k_cov is not None else e, radii,

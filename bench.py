@@ -291,10 +291,6 @@ def main():
     kms = {k: float(ms_k[i]) for i, k in enumerate(kernels)}
     ab = algorithmic_bytes(P, avg_vis, avg_R)
     stage_bytes = {"preprocess": ab["preprocess"], "tile_scan": 0, "emit": ab["binning"] / 2, "sort_tiles": ab["binning"] / 2, "blend": ab["blend"]}
-    fused_sort = kms["sort_tiles"] < 0.005  # default build: the tile sort is the prologue of k_blend
-    if fused_sort:
-        stage_bytes["blend"] += stage_bytes["sort_tiles"]
-        stage_bytes["sort_tiles"] = 0
     dom = max(kms, key=kms.get)
     dom_bytes = stage_bytes[dom]
     dom_gbs = dom_bytes / (kms[dom] * 1e-3) / 1e9 if kms[dom] > 0 else 0.0
@@ -307,7 +303,7 @@ def main():
         except Exception:  # noqa: BLE001
             traffic = None
     frame_gbs = ab["frame"] / (ms_local / K * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": ("k_blend<SORT> (tile sort + blend)" if (dom == "blend" and fused_sort) else "k_" + dom), "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": traffic,
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": kms,
                 "kernel_share": {k: (v / sum(kms.values()) if sum(kms.values()) else 0) for k, v in kms.items()},
                 "per_kernel_gbs": {k: (stage_bytes[k] / (v * 1e-3) / 1e9 if v > 0 else 0) for k, v in kms.items()},
@@ -328,23 +324,47 @@ def main():
     tight_info = {"value": frames_total / (ms_tight * 1e-3), "unit": "frames/s", "avg_num_rendered": sum(x["num_rendered"] for x in st_t) / len(st_t),
                   "note": "opt-in GSR_FLAG_TIGHT_TILES: per-tile lists are sub-sequences of the reference's; color/depth/alpha/radii bit-identical"}
 
-    # ---- product frame: SH pass + colors_precomp (normals) pass per camera, second pass reuses the geometry ----
-    normals = (torch.nn.functional.normalize(g["means3D"]) * 0.5 + 0.5).contiguous()
+    # ---- product frame: what the reference's render() does per camera — SH pass + normals pass + normal maps.
+    #      fused: gsr_axis_normals -> ONE 6-channel forward -> gsr_normal_maps; two_pass: two forwards, the second reusing the geometry ----
+    from autovfx_b200 import renderer as RD
+    normals_buf = torch.empty((P, 3), dtype=torch.float32, device=dev)
+    extra_img = torch.empty((3, H_IMG, W_IMG), dtype=torch.float32, device=dev)
+    c2w_dev = [torch.linalg.inv_ex(s_.viewmatrix.view(4, 4))[0].contiguous() for s_ in all_settings]
+    fx_, fy_ = W_IMG / (2 * all_settings[0].tanfovx), H_IMG / (2 * all_settings[0].tanfovy)
 
-    def product_frame(s):
-        R.forward_raw(g["means3D"], g["shs"], None, g["opacities"], g["scales"], g["rotations"], None, all_settings[s], sync=False, out=out_ring[0])
-        return R.forward_raw(g["means3D"], None, normals, g["opacities"], g["scales"], g["rotations"], None, all_settings[s], sync=False, out=out_ring[1])[5]
-    for s in range(Wm):
-        product_frame(s)
-    barrier()
-    p0e, p1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0e.record()
-    pt = [product_frame(Wm + s) for s in range(K)]
-    p1e.record()
-    barrier()
-    ms_prod = max_over_ranks(p0e.elapsed_time(p1e))
-    product_info = {"value": frames_total / (ms_prod * 1e-3), "unit": "product frames/s (2 rasterizer passes each)", "overflowed": sum(t.stats()["overflow"] for t in pt),
-                    "note": "second pass (colors_precomp) reuses projection+binning of the first (GSR_FLAG_REUSE_GEOMETRY), bit-identical outputs"}
+    def product_fused(s):
+        st_ = all_settings[s]
+        RD.axis_normals(g["means3D"], g["scales"], g["rotations"], st_.campos, remap01=True, out=normals_buf)
+        res = R.forward_multi(g["means3D"], g["shs"], None, normals_buf, g["opacities"], g["scales"], g["rotations"], None, st_, sync=False,
+                              out=out_ring[0], extra_out=extra_img)
+        RD.normal_maps(extra_img, out_ring[0][1][0], c2w_dev[s], fx_, fy_, W_IMG / 2, H_IMG / 2)
+        return res[5]
+
+    def product_two_pass(s):
+        st_ = all_settings[s]
+        RD.axis_normals(g["means3D"], g["scales"], g["rotations"], st_.campos, remap01=True, out=normals_buf)
+        R.forward_raw(g["means3D"], g["shs"], None, g["opacities"], g["scales"], g["rotations"], None, st_, sync=False, out=out_ring[0])
+        t_ = R.forward_raw(g["means3D"], None, normals_buf, g["opacities"], g["scales"], g["rotations"], None, st_, sync=False, out=out_ring[1])[5]
+        RD.normal_maps(out_ring[1][0], out_ring[0][1][0], c2w_dev[s], fx_, fy_, W_IMG / 2, H_IMG / 2)
+        return t_
+
+    def time_product(fn):
+        for s in range(Wm):
+            fn(s)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tk = [fn(Wm + s) for s in range(K)]
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), sum(t.stats()["overflow"] for t in tk)
+    ms_prod, ovf_prod = time_product(product_fused)
+    ms_prod2, _ = time_product(product_two_pass)
+    product_info = {"value": frames_total / (ms_prod * 1e-3), "unit": "product frames/s", "overflowed": ovf_prod,
+                    "two_pass_value": frames_total / (ms_prod2 * 1e-3),
+                    "note": "one product frame = the reference's render(): SH image + normal image + normal/pseudo-normal maps. value: "
+                            "axis_normals + one 6-channel forward (gsr_forward_multi) + normal_maps; two_pass_value: two forwards, the "
+                            "second re-blending on the first one's geometry (GSR_FLAG_REUSE_GEOMETRY). Images bit-identical either way"}
 
     # ---- e2e: public frame loop, host camera payload in, finished frame out to pinned host memory, every step ----
     loop = RL.FrameLoop(g, 3, W_IMG, H_IMG, device=dev, ring=3, to_host=True)
@@ -385,7 +405,7 @@ def main():
                 "config": {"workload": workload, "gaussians": P, "avg_visible": avg_vis, "avg_num_rendered": avg_R, "frames_per_rank": K,
                            "parallelism": "frame-sharded x%d (round-robin cameras, NCCL only for parameter broadcast + camera scatter)" % world,
                            "l2": "inputs larger than L2 (708 MB of SH read per frame; 126 MB L2)", "sync": "async issue, counters validated after the timed region"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": (4 if fused_sort else 5) * K * world, "roofline": roofline, "tight_tiles": tight_info, "product_frame": product_info}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * K * world, "roofline": roofline, "tight_tiles": tight_info, "product_frame": product_info}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

@@ -11,6 +11,13 @@
  *   gsr_mark_visible  replaces  _C.mark_visible                  DGR/rasterize_points.cu:211-230
  *   gsr_dist2         replaces  simple_knn._C.distCUDA2          KNN/spatial.cu:15-26 (SimpleKNN::knn, KNN/simple_knn.cu:185-220)
  *
+ * and, for the render() wrapper around the two rasterizer passes ("GR/" = sugar/gaussian_splatting/gaussian_renderer/__init__.py):
+ *
+ *   gsr_forward_multi replaces  both rasterizer(...) calls of one frame           GR/:134-166 (same geometry, second colour set)
+ *   gsr_axis_normals  replaces  pc.get_normal(dir_pp_normalized) * 0.5 + 0.5      GR/:131-132,146-147; scene/gaussian_model.py:120-128
+ *   gsr_normal_maps   replaces  normal normalisation + depth pseudo normal        GR/:168-191 (depth_pcd2normal GR/:23-38)
+ *   gsr_pack_frame    replaces  the per-frame 8-bit conversions before encoding   scene_representation.py:424-438, sugar/render.py:18-22
+ *
  * Conventions (same as the reference's C++ layer):
  *   - every pointer is a DEVICE pointer to contiguous fp32 / int32 data unless it says "host";
  *   - a NULL pointer means "input absent" (the reference encodes None as an empty tensor whose
@@ -31,7 +38,7 @@
 extern "C" {
 #endif
 
-#define GSR_ABI_VERSION 1
+#define GSR_ABI_VERSION 2
 
 enum {
     GSR_OK = 0,
@@ -109,6 +116,33 @@ size_t gsr_binning_capacity(size_t bytes);
  * (reference: rasterize_points.cu:68-71,82).  Asynchronous on `stream`. */
 int gsr_forward(const gsr_frame* frame, const gsr_workspace* ws, float* out_color, float* out_depth,
                 float* out_alpha, int32_t* radii, int flags, void* stream);
+
+/* gsr_forward plus a second colour set blended with the SAME per-pixel weights: out_extra [3,H,W] is what a second
+ * gsr_forward with colors_precomp = extra_colors ([P,3]) would write to out_color (bit for bit), at the cost of three
+ * more accumulators in the blend instead of a second pass.  extra_colors == NULL && out_extra == NULL is gsr_forward.
+ * With GSR_FLAG_REUSE_GEOMETRY, colors_precomp recolours the cached records and extra_colors is blended alongside. */
+int gsr_forward_multi(const gsr_frame* frame, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,
+                      int32_t* radii, const float* extra_colors, float* out_extra, int flags, void* stream);
+
+/* Per-Gaussian shading normal of the reference's GaussianModel.get_normal: the rotation-matrix column of the smallest
+ * scale (ties: lowest index), flipped so that it faces the camera, normalised; remap01 != 0 stores normal*0.5+0.5.
+ * out [P,3]. */
+int gsr_axis_normals(int32_t P, const float* means3D, const float* scales, const float* rotations, const float* campos,
+                     int remap01, float* out, void* stream);
+
+/* normal_img [3,H,W] (a rendered normal*0.5+0.5 image) -> out_normal [H,W,3] = normalize((img - 0.5) * 2);
+ * depth [H,W] -> out_pseudo [H,W,3] = normalised cross product of central differences of the unprojected depth map,
+ * zero on the 1-pixel border.  c2w: DEVICE pointer to >= 12 floats, rows 0..2 of the 4x4 the reference calls c2w
+ * (world_view_transform.inverse(), row-major); fx, fy, cx, cy as in GR/:180-184.  Either pair may be NULL. */
+int gsr_normal_maps(int32_t W, int32_t H, const float* normal_img, const float* depth, const float* c2w, float fx, float fy,
+                    float cx, float cy, float* out_normal, float* out_pseudo, void* stream);
+
+/* 8-bit hand-off of a finished frame (any output may be NULL):
+ *   rgba8   [H,W,4] = clamp(v*255+0.5, 0, 255) of rgb [3,H,W] and alpha [H,W] (alpha NULL -> 255)
+ *   normal8 [H,W,3] = trunc((n+1)/2*255) of normal_hwc [H,W,3]
+ *   depth8  [H,W]   = trunc(clip(depth/depth_scale, 0, 1)*255), the colormap index */
+int gsr_pack_frame(int32_t W, int32_t H, const float* rgb, const float* alpha, const float* depth, const float* normal_hwc,
+                   float depth_scale, uint8_t* rgba8, uint8_t* normal8, uint8_t* depth8, void* stream);
 
 /* Gradient buffers, all caller-allocated; the library zero-fills what it accumulates into (the
  * reference's torch::zeros, rasterize_points.cu:158-168).  dL_dsh may be NULL when shs is NULL,

@@ -1,0 +1,111 @@
+"""Torch restatement, op for op, of the reference's render() wrapper helpers — test infrastructure.
+
+The originals cannot be imported (gaussian_renderer/__init__.py imports kornia; utils/general_utils.py:83 hard-codes
+device='cuda'), so they are restated here with a ``device`` that follows the inputs.  Executed with torch's CUDA kernels on
+the GPU box they are the closest available stand-in for "the reference run here" for this row; on CPU they pin
+oracle/render_oracle.py.  "GR/" = sugar/gaussian_splatting/gaussian_renderer/__init__.py, "GU/" = .../utils/general_utils.py.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+def build_rotation(r):  # GU/:78-99
+    norm = torch.sqrt(r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1] + r[:, 2] * r[:, 2] + r[:, 3] * r[:, 3])
+    q = r / norm[:, None]
+    R = torch.zeros((q.size(0), 3, 3), device=r.device, dtype=r.dtype)
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z)
+    R[:, 0, 1] = 2 * (x * y - w * z)
+    R[:, 0, 2] = 2 * (x * z + w * y)
+    R[:, 1, 0] = 2 * (x * y + w * z)
+    R[:, 1, 1] = 1 - 2 * (x * x + z * z)
+    R[:, 1, 2] = 2 * (y * z - w * x)
+    R[:, 2, 0] = 2 * (x * z - w * y)
+    R[:, 2, 1] = 2 * (y * z + w * x)
+    R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def get_minimum_axis(scales, rotations):  # GU/:136-141
+    sorted_idx = torch.argsort(scales, descending=False, dim=-1)
+    R = build_rotation(rotations)
+    R_sorted = torch.gather(R, dim=2, index=sorted_idx[:, None, :].repeat(1, 3, 1)).squeeze()
+    return R_sorted[:, :, 0]
+
+
+def flip_align_view(normal, viewdir):  # GU/:151-157
+    dotprod = torch.sum(normal * -viewdir, dim=-1, keepdims=True)
+    non_flip = dotprod >= 0
+    return normal * torch.where(non_flip, 1, -1), non_flip
+
+
+def get_normal(xyz, scales, rotations, campos):  # scene/gaussian_model.py:120-124 + GR/:131-132
+    dir_pp = xyz - campos.repeat(xyz.shape[0], 1)
+    dir_pp_normalized = dir_pp / dir_pp.norm(dim=1, keepdim=True)
+    normal_axis = get_minimum_axis(scales, rotations)
+    normal_axis, _ = flip_align_view(normal_axis, dir_pp_normalized)
+    return normal_axis / normal_axis.norm(dim=1, keepdim=True)
+
+
+def fov2focal(fov, pixels):  # utils/graphics_utils.py:74-75
+    return pixels / (2 * math.tan(fov / 2))
+
+
+def get_ray_directions(H, W, K, device):  # GR/:41-80, create_meshgrid(H, W, False): x = column, y = row, pixel units
+    xs = torch.linspace(0, W - 1, W, device=device, dtype=torch.float32)
+    ys = torch.linspace(0, H - 1, H, device=device, dtype=torch.float32)
+    v, u = torch.meshgrid(ys, xs, indexing="ij")
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    return torch.stack([(u - cx + 0.5) / fx, (v - cy + 0.5) / fy, torch.ones_like(u)], -1)
+
+
+def depth_pcd2normal(xyz):  # GR/:23-38
+    hd, wd, _ = xyz.shape
+    bottom_point = xyz[..., 2:hd, 1:wd - 1, :]
+    top_point = xyz[..., 0:hd - 2, 1:wd - 1, :]
+    right_point = xyz[..., 1:hd - 1, 2:wd, :]
+    left_point = xyz[..., 1:hd - 1, 0:wd - 2, :]
+    left_to_right = right_point - left_point
+    bottom_to_top = top_point - bottom_point
+    xyz_normal = torch.cross(left_to_right, bottom_to_top, dim=-1)
+    xyz_normal = torch.nn.functional.normalize(xyz_normal, p=2, dim=-1)
+    return torch.nn.functional.pad(xyz_normal.permute(2, 0, 1), (1, 1, 1, 1), mode="constant").permute(1, 2, 0)
+
+
+def normal_image(normal_img_chw):  # GR/:168-176
+    n = (normal_img_chw - 0.5) * 2.
+    return torch.nn.functional.normalize(n.permute(1, 2, 0), p=2, dim=-1)
+
+
+def pseudo_normal(depth_hw, world_view_transform, FoVx, FoVy):  # GR/:178-191
+    h, w = depth_hw.shape
+    fx, fy = fov2focal(FoVx, w), fov2focal(FoVy, h)
+    cx, cy = w / 2, h / 2
+    c2w = world_view_transform.inverse()
+    directions = get_ray_directions(h, w, torch.FloatTensor([[fx, 0, cx], [0, fy, cy], [0, 0, 1]]), depth_hw.device)
+    rays_d = directions @ c2w[:3, :3].T
+    rays_o = c2w[:3, 3].expand_as(rays_d)
+    points3D = rays_o + rays_d * depth_hw.unsqueeze(-1)
+    return depth_pcd2normal(points3D)
+
+
+def save_image_bytes(img_chw):  # torchvision.utils.save_image for one image: mul(255).add_(0.5).clamp_(0,255).permute(1,2,0).to(uint8)
+    return img_chw.mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to(torch.uint8)
+
+
+def render_two_pass(rasterize, xyz, shs, opacity, scales, rotations, sh_degree, cam, bg):
+    """GR/:83-218 with ``rasterize(shs=..., colors_precomp=...) -> (color, depth, alpha, radii)`` standing for the
+    reference's GaussianRasterizer call (tests bind it to the compiled reference rasterizer)."""
+    campos = cam["campos"]
+    normal = get_normal(xyz, scales, rotations, campos)
+    normal_normed = normal * 0.5 + 0.5
+    rendered_image, depth_image, alpha_image, radii = rasterize(shs=shs, colors_precomp=None)
+    rendered_image = torch.cat((rendered_image, alpha_image), dim=0)
+    depth_image = depth_image.squeeze(0)
+    nimg = rasterize(shs=None, colors_precomp=normal_normed)[0]
+    return {"render": rendered_image, "depth": depth_image, "normal": normal_image(nimg),
+            "pseudo_normal": pseudo_normal(depth_image, cam["viewmatrix"], cam["FoVx"], cam["FoVy"]),
+            "normal_normed": normal_normed, "normal_raw_image": nimg, "radii": radii}
