@@ -52,7 +52,7 @@ ABI_VERSION = 2
 
 EXPORTS = ("gsr_abi_version", "gsr_last_error", "gsr_geom_bytes", "gsr_binning_bytes", "gsr_binning_capacity", "gsr_image_bytes",
            "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_dist2_bytes", "gsr_dist2", "gsr_get_views",
-           "gsr_profile_begin", "gsr_profile_end", "gsr_selftest", "gsr_forward_multi", "gsr_axis_normals", "gsr_normal_maps",
+           "gsr_profile_begin", "gsr_profile_end", "gsr_forward_multi", "gsr_axis_normals", "gsr_normal_maps",
            "gsr_pack_frame")
 
 
@@ -108,8 +108,6 @@ def _load() -> C.CDLL:
     lib.gsr_profile_begin.argtypes = [C.c_int]
     lib.gsr_profile_end.restype = C.c_int
     lib.gsr_profile_end.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
-    lib.gsr_selftest.restype = C.c_int
-    lib.gsr_selftest.argtypes = [C.POINTER(C.c_ulonglong)]
     return lib
 
 

@@ -14,7 +14,6 @@ int backward_impl(const gsr_frame* f, const gsr_workspace* ws, const int32_t* ra
                   const float* dL_dd, const float* dL_da, const gsr_grads* g, cudaStream_t st);
 int dist2_impl(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t dist2_bytes(int P);
-int selftest_impl(unsigned long long* mismatches_host);
 int profile_begin(int max_frames);
 int profile_end(float* ms, int* frames);
 
@@ -85,11 +84,6 @@ int gsr_dist2(int32_t P, const float* points, float* mean_dists, void* workspace
 
 int gsr_profile_begin(int max_frames) { return gsr::profile_begin(max_frames); }
 int gsr_profile_end(float* ms_per_kernel, int* frames) { return gsr::profile_end(ms_per_kernel, frames); }
-
-int gsr_selftest(unsigned long long* mismatches) {
-    if (!mismatches) { gsr::set_error("gsr_selftest: null pointer"); return GSR_ERR_INVALID; }
-    return gsr::selftest_impl(mismatches);
-}
 
 int gsr_get_views(const gsr_workspace* ws, int32_t P, int32_t W, int32_t H, gsr_views* out) {
     if (!ws || !out) { gsr::set_error("gsr_get_views: null argument"); return GSR_ERR_INVALID; }

@@ -760,35 +760,12 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
-// expf() of both halves, bit-identical to CUDA's scalar expf (the sequence nvcc 12.9 emits for it: saturating range
-// reduction, round-down magic-number trick, two-constant log2(e) split, ex2.approx, scale by 2^n), with the middle steps
-// packed.  Verified against expf over a dense sweep of the blend's input range by gsr_selftest (tests/test_gpu_parity.py).
-__device__ __forceinline__ f32x2 exp2x(f32x2 x) {
-    float x0, x1;
-    upk2(x, x0, x1);
-    float t0, t1;
-    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(t0) : "f"(x0), "f"(__uint_as_float(0x3bbb989du)), "f"(0.5f));
-    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(t1) : "f"(x1), "f"(__uint_as_float(0x3bbb989du)), "f"(0.5f));
-    f32x2 r;
-    asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(t0, t1)), "l"(pk2(252.0f, 252.0f)), "l"(pk2(12582913.0f, 12582913.0f)));
-    const f32x2 nu = fma2(r, pk2(-1.0f, -1.0f), pk2(12583039.0f, 12583039.0f));  // -(r - 12583039), exact
-    float r0, r1;
-    upk2(r, r0, r1);
-    f32x2 v = fma2(x, pk2(__uint_as_float(0x3fb8aa3bu), __uint_as_float(0x3fb8aa3bu)), nu);
-    v = fma2(x, pk2(__uint_as_float(0x32a57060u), __uint_as_float(0x32a57060u)), v);
-    float v0, v1, e0, e1;
-    upk2(v, v0, v1);
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(v0));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(v1));
-    return mul2(pk2(__uint_as_float(__float_as_uint(r0) << 23), __uint_as_float(__float_as_uint(r1) << 23)), pk2(e0, e1));
-}
-
-// PEXP: packed expf (exp2x) instead of two scalar expf per pair (same bits; measured 4.5 % slower, off by default).
 // NX  : extra colour channels `extra[P,NX]` accumulated with the same per-splat weights into `out_extra[NX,H,W]`
 //       (+ T_final * bg like the colour image) — what a second rasterizer pass with colors_precomp = extra would
 //       return (gaussian_renderer/__init__.py:151-185), without re-running projection, binning, sort and the alpha math.
-template <bool PEXP, int NX>
-__global__ void __launch_bounds__(BLEND_THREADS, (PEXP && !NX) ? 4 : 0) k_blend(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+// NC  : also record n_contrib (the 1-based list position of the last blended splat) for the backward pass.
+template <int NX, bool NC>
+__global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                                                          const float4* __restrict__ records, const float* __restrict__ extra,
                                                          int W, int H, int gx, const float* __restrict__ bg,
                                                          float* __restrict__ out_color, float* __restrict__ out_depth,
@@ -816,10 +793,10 @@ __global__ void __launch_bounds__(BLEND_THREADS, (PEXP && !NX) ? 4 : 0) k_blend(
     const int n = (int)(range.y - range.x);
     const int nb = (n + BLEND_THREADS - 1) / BLEND_THREADS;
 
-    // T is the running transmittance while the pixel is live.  When the pixel terminates (forward.cu:349-354) its
-    // final transmittance moves to T_out and T becomes 0, so that every later splat fails the same `T(1-a) < 1e-4`
-    // test on its own: no separate per-iteration "done" branch is needed.  Pixels outside the image start dead.
-    float T = inside ? 1.0f : 0.0f, T_out = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f, E0 = 0.f, E1 = 0.f, E2 = 0.f;
+    // T is the running transmittance while the pixel is live.  When the pixel terminates (forward.cu:349-354) T flips
+    // its sign: the magnitude keeps the final transmittance, and every later splat fails the `T(1-a) < 1e-4` test on its own
+    // (the product is negative), so there is no per-iteration "done" branch.  Pixels outside the image start dead.
+    float T = inside ? 1.0f : -1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f, E0 = 0.f, E1 = 0.f, E2 = 0.f;
     uint32_t last = 0;
     int qn = 0;  // entries in this warp's queue (warp-uniform)
 
@@ -830,7 +807,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, (PEXP && !NX) ? 4 : 0) k_blend(
     // registers (FFMA2/FMUL2/FADD2: two IEEE-rn results per instruction, bit-identical to the scalar ops; the sign of b
     // is folded into the stored -b so the reference's `... - b*dx*dy` needs no negation).  Only expf, the 0.99 clamp
     // and the serial transmittance updates stay scalar.  Branch-free: the three skip rules (power > 0, alpha < 1/255,
-    // T(1-alpha) < 1e-4) are predicates and a skipped splat contributes through a transmittance of exactly 0.
+    // T(1-alpha) < 1e-4) are predicates and a skipped splat contributes through a weight of exactly 0.
     const f32x2 npx2 = pk2(-pixx, -pixx), npy2 = pk2(-pixy, -pixy), mhalf2 = pk2(-0.5f, -0.5f), mone2 = pk2(-1.0f, -1.0f),
                 one2 = pk2(1.0f, 1.0f);
     auto drain = [&]() {
@@ -856,7 +833,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, (PEXP && !NX) ? 4 : 0) k_blend(
             float p0, p1;
             upk2(pw, p0, p1);
             float a0, a1;
-            upk2(mul2(pk2(L2.z, L2.w), PEXP ? exp2x(pw) : pk2(exp(p0), exp(p1))), a0, a1);  // opacity * exp(power)
+            upk2(mul2(pk2(L2.z, L2.w), pk2(exp(p0), exp(p1))), a0, a1);  // opacity * exp(power); a packed expf was measured slower
             a0 = min(0.99f, a0);
             a1 = min(0.99f, a1);
             const bool hit0 = !(p0 > 0.0f) && !(a0 < 1.0f / 255.0f), hit1 = !(p1 > 0.0f) && !(a1 < 1.0f / 255.0f);
@@ -877,24 +854,22 @@ __global__ void __launch_bounds__(BLEND_THREADS, (PEXP && !NX) ? 4 : 0) k_blend(
             {   // first splat of the pair
                 const float test_T = T * om0;
                 const bool live = hit0 && !(test_T < 0.0001f);
-                const bool dies = hit0 && (test_T < 0.0001f) && T != 0.0f;
+                const bool dies = hit0 && (test_T < 0.0001f) && T > 0.0f;
                 const float Tw = live ? T : 0.0f;
                 C0 = fmaf(Tw, cr0, C0); C1 = fmaf(Tw, cg0, C1); C2 = fmaf(Tw, cb0, C2); Dp = fmaf(Tw, cd0, Dp);
                 if (NX) { E0 = fmaf(Tw, ex0, E0); E1 = fmaf(Tw, ey0, E1); E2 = fmaf(Tw, ez0, E2); }
-                T_out = dies ? T : T_out;
-                T = live ? test_T : (dies ? 0.0f : T);
-                last = live ? __float_as_uint(L5.x) : last;
+                T = live ? test_T : (dies ? -T : T);
+                if (NC) last = live ? __float_as_uint(L5.x) : last;
             }
             {   // second splat of the pair
                 const float test_T = T * om1;
                 const bool live = hit1 && !(test_T < 0.0001f);
-                const bool dies = hit1 && (test_T < 0.0001f) && T != 0.0f;
+                const bool dies = hit1 && (test_T < 0.0001f) && T > 0.0f;
                 const float Tw = live ? T : 0.0f;
                 C0 = fmaf(Tw, cr1, C0); C1 = fmaf(Tw, cg1, C1); C2 = fmaf(Tw, cb1, C2); Dp = fmaf(Tw, cd1, Dp);
                 if (NX) { E0 = fmaf(Tw, ex1, E0); E1 = fmaf(Tw, ey1, E1); E2 = fmaf(Tw, ez1, E2); }
-                T_out = dies ? T : T_out;
-                T = live ? test_T : (dies ? 0.0f : T);
-                last = live ? __float_as_uint(L5.y) : last;
+                T = live ? test_T : (dies ? -T : T);
+                if (NC) last = live ? __float_as_uint(L5.y) : last;
             }
         }
         qn = 0;
@@ -962,7 +937,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, (PEXP && !NX) ? 4 : 0) k_blend(
                     qn += __popc(mask);
                     if (qn > BLEND_QCAP - 32) {
                         drain();
-                        if (__all_sync(GSR_FULL, T == 0.0f)) { warp_done = true; break; }
+                        if (__all_sync(GSR_FULL, T < 0.0f)) { warp_done = true; break; }
                     }
                 }
             }
@@ -972,16 +947,16 @@ __global__ void __launch_bounds__(BLEND_THREADS, (PEXP && !NX) ? 4 : 0) k_blend(
             gather(b + 2, id_next);
             if ((b + 3) * BLEND_THREADS + tid < n) id_next = point_list[range.x + (b + 3) * BLEND_THREADS + tid];
             // whole tile finished?  (also publishes buffer (b+1)&1 and retires buffer b&1)
-            if (__syncthreads_count(T == 0.0f) == BLEND_THREADS) break;
+            if (__syncthreads_count(T < 0.0f) == BLEND_THREADS) break;
         }
     }
     if (qn) drain();
     if (inside) {
-        if (T != 0.0f) T_out = T;  // pixel still live at the end of the list
+        const float T_out = fabsf(T);  // final transmittance, whether the pixel terminated or the list ran out
         const size_t pid = (size_t)W * pyi + pxi;
         const size_t HW = (size_t)H * W;
         out_alpha[pid] = 1 - T_out;
-        if (n_contrib) n_contrib[pid] = last;
+        if (NC) n_contrib[pid] = last;
         out_color[pid] = C0 + T_out * bg[0];
         out_color[HW + pid] = C1 + T_out * bg[1];
         out_color[2 * HW + pid] = C2 + T_out * bg[2];
@@ -992,33 +967,6 @@ __global__ void __launch_bounds__(BLEND_THREADS, (PEXP && !NX) ? 4 : 0) k_blend(
             out_extra[2 * HW + pid] = E2 + T_out * bg[2];
         }
     }
-}
-
-// =====================================================================================================
-// self test: exp2x (packed expf used by the blend) against expf, bit for bit, over a sweep of float bit patterns
-// =====================================================================================================
-__global__ void k_selftest_exp(uint32_t lo_bits, uint32_t hi_bits, uint32_t stride, unsigned long long* mismatches) {
-    unsigned long long bad = 0;
-    for (unsigned long long b = lo_bits + (unsigned long long)(blockIdx.x * blockDim.x + threadIdx.x) * stride; b <= hi_bits;
-         b += (unsigned long long)gridDim.x * blockDim.x * stride) {
-        const float x0 = __uint_as_float((uint32_t)b), x1 = __uint_as_float((uint32_t)b ^ 0x00000155u);
-        float e0, e1;
-        upk2(exp2x(pk2(x0, x1)), e0, e1);
-        bad += (__float_as_uint(e0) != __float_as_uint(expf(x0))) + (__float_as_uint(e1) != __float_as_uint(expf(x1)));
-    }
-    if (bad) atomicAdd(mismatches, bad);
-}
-int selftest_impl(unsigned long long* mismatches_host) {
-    unsigned long long* d = nullptr;
-    if (cudaMalloc(&d, 8) != cudaSuccess) { set_error("gsr_selftest: cudaMalloc failed"); return GSR_ERR_CUDA; }
-    cudaMemset(d, 0, 8);
-    // negative floats from -0 down to -120 (every 16th bit pattern), and positive floats up to 2.0 (every 16th)
-    k_selftest_exp<<<1184, 256>>>(0x80000000u, 0xC2F00000u, 16u, d);
-    k_selftest_exp<<<1184, 256>>>(0x00000000u, 0x40000000u, 16u, d);
-    cudaError_t e = cudaMemcpy(mismatches_host, d, 8, cudaMemcpyDeviceToHost);
-    cudaFree(d);
-    if (e != cudaSuccess) { set_error("gsr_selftest: %s", cudaGetErrorString(e)); return GSR_ERR_CUDA; }
-    return GSR_OK;
 }
 
 // =====================================================================================================
@@ -1085,14 +1033,6 @@ int profile_end(float* ms, int* frames) {
 // =====================================================================================================
 // host side
 // =====================================================================================================
-static int packed_exp_mode() {  // GSR_BLEND_EXP=packed: exp2x (two expf in packed fp32) instead of two scalar expf per splat pair;
-    static int mode = -1;       // same bits, measured 4.5 % slower in k_blend (FMA-pipe pressure), so off by default
-    if (mode < 0) {
-        const char* e = getenv("GSR_BLEND_EXP");
-        mode = (e && strcmp(e, "packed") == 0) ? 1 : 0;
-    }
-    return mode;
-}
 static int sh_bulk_mode() {  // GSR_SH_STAGING=cpasync selects the LDGSTS path, default is the TMA bulk copy
     static int mode = -1;
     if (mode < 0) {
@@ -1114,25 +1054,24 @@ struct BlendArgs {
     int W, H, gx, gy; const float* bg; float *out_color, *out_depth, *out_alpha, *out_extra; uint32_t* n_contrib;
     const gsr_counters* counters;
 };
-template <bool PEXP, int NX>
+template <int NX, bool NC>
 static void launch_blend_t(const BlendArgs& a, cudaStream_t st) {
     if (NX) {  // 60 KB of dynamic shared memory: opt in once per device
         static bool configured[64] = {};
         int dev = 0;
         cudaGetDevice(&dev);
         if (dev >= 0 && dev < 64 && !configured[dev]) {
-            cudaFuncSetAttribute(k_blend<PEXP, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlendCfg<NX>::SMEM);
+            cudaFuncSetAttribute(k_blend<NX, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlendCfg<NX>::SMEM);
             configured[dev] = true;
         }
     }
-    k_blend<PEXP, NX><<<dim3(a.gx, a.gy), BLEND_THREADS, BlendCfg<NX>::SMEM, st>>>(a.ranges, a.point_list, a.records, a.extra, a.W, a.H, a.gx, a.bg,
-                                                                                  a.out_color, a.out_depth, a.out_alpha, a.out_extra,
-                                                                                  a.n_contrib, a.counters);
+    k_blend<NX, NC><<<dim3(a.gx, a.gy), BLEND_THREADS, BlendCfg<NX>::SMEM, st>>>(a.ranges, a.point_list, a.records, a.extra, a.W, a.H, a.gx, a.bg,
+                                                                                a.out_color, a.out_depth, a.out_alpha, a.out_extra, a.n_contrib,
+                                                                                a.counters);
 }
 static void launch_blend(const BlendArgs& a, cudaStream_t st) {
-    const bool px = packed_exp_mode() != 0;
-    if (a.extra) { if (px) launch_blend_t<true, 3>(a, st); else launch_blend_t<false, 3>(a, st); }
-    else         { if (px) launch_blend_t<true, 0>(a, st); else launch_blend_t<false, 0>(a, st); }
+    if (a.extra) { if (a.n_contrib) launch_blend_t<3, true>(a, st); else launch_blend_t<3, false>(a, st); }
+    else         { if (a.n_contrib) launch_blend_t<0, true>(a, st); else launch_blend_t<0, false>(a, st); }
 }
 
 int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,

@@ -98,12 +98,25 @@ def gather_stats(local: torch.Tensor, group=None) -> Optional[List[torch.Tensor]
 
 # ----------------------------------------------------------------------------- the loop
 class FrameLoop:
-    """Renders a list of cameras for one resident set of Gaussians on one GPU."""
+    """Renders a list of cameras for one resident set of Gaussians on one GPU.
+
+    ``product=False``: one rasterizer forward per camera; the finished frame is ``[5,H,W]`` (rgb | depth | alpha).
+    ``product=True`` : the reference's whole ``render()`` per camera (gaussian_renderer/__init__.py:83-218): SH image, normal
+                       image and the normal / pseudo-normal maps, as gsr_axis_normals -> one 6-channel forward ->
+                       gsr_normal_maps; the finished frame is a dict ``{"frame" [5,H,W], "normal" [H,W,3], "pseudo_normal"
+                       [H,W,3]}``.
+    ``pack8=True``   : (with ``product``) hand the frame off as the bytes the reference's loop gives its encoders
+                       (scene_representation.py:424-438): ``{"rgba8" [H,W,4], "depth" [H,W] f32, "depth8" [H,W], "normal8"
+                       [H,W,3]}`` — 24.9 MB instead of 66 MB of fp32 over PCIe per 1080p frame.
+    """
 
     def __init__(self, gaussians: Dict[str, torch.Tensor], sh_degree: int, width: int, height: int, bg=(0.0, 0.0, 0.0),
-                 scale_modifier: float = 1.0, device=None, ring: int = 3, to_host: bool = True, tight_tiles: Optional[bool] = None):
+                 scale_modifier: float = 1.0, device=None, ring: int = 3, to_host: bool = True, tight_tiles: Optional[bool] = None,
+                 product: bool = False, pack8: bool = False, depth_scale: float = 3.0):
         from . import rasterizer as R  # requires the CUDA library
         self._R = R
+        if pack8 and not product:
+            raise ValueError("pack8 needs product=True (it packs the normal map as well)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.g = {k: v.to(self.device).float().contiguous() for k, v in gaussians.items()}
         self.sh_degree, self.W, self.H, self.scale_modifier = sh_degree, width, height, scale_modifier
@@ -111,15 +124,35 @@ class FrameLoop:
         self.ring = ring
         self.to_host = to_host
         self.tight_tiles = tight_tiles  # None: follow rasterizer.set_tight_tiles()
+        self.product, self.pack8, self.depth_scale = product, pack8, depth_scale
         P = self.g["means3D"].shape[0]
-        self.frames = [torch.empty((5, height, width), dtype=torch.float32, device=self.device) for _ in range(ring)]
-        self.radii = [torch.empty((P,), dtype=torch.int32, device=self.device) for _ in range(ring)]
-        self.host = [torch.empty((5, height, width), dtype=torch.float32).pin_memory() for _ in range(ring)] if to_host else None
+        H, W = height, width
+        dev = self.device
+        self.frames = [torch.empty((5, H, W), dtype=torch.float32, device=dev) for _ in range(ring)]
+        self.radii = [torch.empty((P,), dtype=torch.int32, device=dev) for _ in range(ring)]
+        self.outputs: List[Dict[str, torch.Tensor]] = []  # per slot: what a finished frame consists of (device side)
+        if product:
+            from . import renderer as RD
+            self._RD = RD
+            self.normals = torch.empty((P, 3), dtype=torch.float32, device=dev)  # per-Gaussian normal*0.5+0.5 of the current frame
+            self.extra = [torch.empty((3, H, W), dtype=torch.float32, device=dev) for _ in range(ring)]
+            self.nmaps = [(torch.empty((H, W, 3), dtype=torch.float32, device=dev), torch.empty((H, W, 3), dtype=torch.float32, device=dev))
+                          for _ in range(ring)]
+        for s in range(ring):
+            if not product:
+                self.outputs.append({"frame": self.frames[s]})
+            elif not pack8:
+                self.outputs.append({"frame": self.frames[s], "normal": self.nmaps[s][0], "pseudo_normal": self.nmaps[s][1]})
+            else:
+                self.outputs.append({"rgba8": torch.empty((H, W, 4), dtype=torch.uint8, device=dev), "depth": self.frames[s][3],
+                                     "depth8": torch.empty((H, W), dtype=torch.uint8, device=dev),
+                                     "normal8": torch.empty((H, W, 3), dtype=torch.uint8, device=dev)})
+        self.host = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in self.outputs[s].items()} for s in range(ring)] if to_host else None
         self.copy_stream = torch.cuda.Stream(self.device) if to_host else None
         self.cam_pinned = torch.empty((ring, CAM_FLOATS), dtype=torch.float32).pin_memory()
         self.cam_dev = torch.empty((ring, CAM_FLOATS), dtype=torch.float32, device=self.device)
         self.h2d_bytes_per_frame = CAM_FLOATS * 4
-        self.d2h_bytes_per_frame = 5 * height * width * 4 if to_host else 0
+        self.d2h_bytes_per_frame = sum(v.numel() * v.element_size() for v in self.outputs[0].values()) if to_host else 0
         self.rerendered = 0
 
     def _settings(self, slot: int, tanfovx: float, tanfovy: float):
@@ -129,20 +162,44 @@ class FrameLoop:
             viewmatrix=c[0:16], projmatrix=c[16:32], sh_degree=self.sh_degree, campos=c[32:35], prefiltered=False, debug=False)
 
     def _issue(self, slot: int, cam_row: torch.Tensor, sync: bool):
-        """host camera row -> pinned -> device (H2D inside the frame), then the forward into ring slot ``slot``."""
+        """host camera row -> pinned -> device (H2D inside the frame), then the frame's kernels into ring slot ``slot``."""
         self.cam_pinned[slot].copy_(cam_row)
         self.cam_dev[slot].copy_(self.cam_pinned[slot], non_blocking=True)
         f = self.frames[slot]
         g = self.g
         out = (f[0:3], f[3:4], f[4:5], self.radii[slot])
-        res = self._R.forward_raw(g["means3D"], g["shs"], None, g["opacities"], g["scales"], g["rotations"], None,
-                                  self._settings(slot, float(cam_row[35]), float(cam_row[36])), sync=sync, out=out, tight=self.tight_tiles)
-        return res[5]  # ticket
+        tfx, tfy = float(cam_row[35]), float(cam_row[36])
+        st = self._settings(slot, tfx, tfy)
+        if not self.product:
+            res = self._R.forward_raw(g["means3D"], g["shs"], None, g["opacities"], g["scales"], g["rotations"], None, st, sync=sync, out=out,
+                                      tight=self.tight_tiles)
+            return res[5]  # ticket
+        RD = self._RD
+        cam = self.cam_dev[slot]
+        RD.axis_normals(g["means3D"], g["scales"], g["rotations"], cam[32:35], remap01=True, out=self.normals)
+        res = self._R.forward_multi(g["means3D"], g["shs"], None, self.normals, g["opacities"], g["scales"], g["rotations"], None, st, sync=sync,
+                                    out=out, extra_out=self.extra[slot], tight=self.tight_tiles)
+        c2w = torch.linalg.inv_ex(cam[0:16].view(4, 4))[0]  # the reference's world_view_transform.inverse(), no host sync
+        n_out, p_out = self.nmaps[slot]
+        RD.normal_maps(self.extra[slot], f[3], c2w, self.W / (2 * tfx), self.H / (2 * tfy), self.W / 2, self.H / 2, out=(n_out, p_out))
+        if self.pack8:
+            o = self.outputs[slot]
+            RD.pack_frame(f[0:3], f[4], f[3], n_out, self.depth_scale, out=o)
+        return res[5]
 
-    def render(self, packed_cams: torch.Tensor, consume: Optional[Callable[[int, torch.Tensor, Dict[str, int]], None]] = None) -> List[Dict[str, int]]:
+    def _copy_out(self, slot: int):
+        for k, v in self.outputs[slot].items():
+            self.host[slot][k].copy_(v, non_blocking=True)
+
+    def _finished(self, slot: int):
+        src = self.host[slot] if self.to_host else self.outputs[slot]
+        return src["frame"] if not self.product else src
+
+    def render(self, packed_cams: torch.Tensor, consume: Optional[Callable] = None) -> List[Dict[str, int]]:
         """Render every row of ``packed_cams`` ([N,37] host tensor).  ``consume(i, frame, stats)`` receives the finished
-        frame ``[5,H,W]`` (pinned host tensor if ``to_host`` else the device ring slot) — valid until ``ring-1`` further
-        frames have been issued.  Returns the per-frame statistics."""
+        frame (pinned host memory if ``to_host`` else the device ring slot; a ``[5,H,W]`` tensor, or the dict described in
+        the class docstring when ``product``) — valid until ``ring-1`` further frames have been issued.  Returns the
+        per-frame statistics."""
         n = packed_cams.shape[0]
         stats: List[Optional[Dict[str, int]]] = [None] * n
         inflight = []  # (frame index, slot, ticket, copy_done_event)
@@ -154,13 +211,13 @@ class FrameLoop:
                 self.rerendered += 1
                 ticket = self._issue(slot, packed_cams[i], sync=True)
                 if self.to_host:
-                    self.host[slot].copy_(self.frames[slot], non_blocking=True)
+                    self._copy_out(slot)
                     cur.synchronize()
             elif ev is not None:
                 ev.synchronize()
             stats[i] = ticket.stats()
             if consume is not None:
-                consume(i, self.host[slot] if self.to_host else self.frames[slot], stats[i])
+                consume(i, self._finished(slot), stats[i])
 
         for i in range(n):
             slot = i % self.ring
@@ -169,9 +226,13 @@ class FrameLoop:
             ticket = self._issue(slot, packed_cams[i], sync=False)
             ev = None
             if self.to_host:
-                self.copy_stream.wait_event(ticket.event)
+                done = ticket.event
+                if self.product:  # the ticket's event was recorded after the forward; the post kernels come later on the stream
+                    done = torch.cuda.Event()
+                    done.record(cur)
+                self.copy_stream.wait_event(done)
                 with torch.cuda.stream(self.copy_stream):
-                    self.host[slot].copy_(self.frames[slot], non_blocking=True)
+                    self._copy_out(slot)
                     ev = torch.cuda.Event()
                     ev.record(self.copy_stream)
             inflight.append((i, slot, ticket, ev))

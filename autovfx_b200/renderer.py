@@ -71,7 +71,8 @@ def axis_normals(means3D: torch.Tensor, scales: torch.Tensor, rotations: torch.T
 
 
 def normal_maps(normal_img: Optional[torch.Tensor], depth: Optional[torch.Tensor], c2w: Optional[torch.Tensor], fx: float, fy: float,
-                cx: float, cy: float) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+                cx: float, cy: float, out: Optional[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]] = None
+                ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """(normal [H,W,3], pseudo_normal [H,W,3]) from the rendered ``normal*0.5+0.5`` image [3,H,W] and the depth map [H,W]
     (GR/:168-191).  ``c2w`` is the 4x4 the reference calls c2w (``world_view_transform.inverse()``)."""
     src = normal_img if normal_img is not None else depth
@@ -83,13 +84,13 @@ def normal_maps(normal_img: Optional[torch.Tensor], depth: Optional[torch.Tensor
         H, W = src.shape[-2], src.shape[-1]
         if normal_img is not None:
             normal_img = _f32c(normal_img, device)
-            out_n = torch.empty((H, W, 3), dtype=torch.float32, device=device)
+            out_n = out[0] if out is not None and out[0] is not None else torch.empty((H, W, 3), dtype=torch.float32, device=device)
         if depth is not None:
             depth = _f32c(depth, device)
             c2w = _f32c(c2w, device)
             if c2w.numel() < 12:
                 raise ValueError("normal_maps: c2w must hold at least 3x4 floats")
-            out_p = torch.empty((H, W, 3), dtype=torch.float32, device=device)
+            out_p = out[1] if out is not None and out[1] is not None else torch.empty((H, W, 3), dtype=torch.float32, device=device)
         rc = _L.gsr_normal_maps(W, H, R._ptr(normal_img), R._ptr(depth), R._ptr(c2w) if depth is not None else None, fx, fy, cx, cy,
                                 R._ptr(out_n), R._ptr(out_p), _stream(device))
         _lib.check(rc, "gsr_normal_maps")

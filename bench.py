@@ -384,6 +384,29 @@ def main():
     e2e = {"value": frames_total / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": loop.h2d_bytes_per_frame, "d2h_bytes_per_step": loop.d2h_bytes_per_frame,
            "api": "autovfx_b200.render_loop.FrameLoop.render (GaussianRasterizer forward per frame, async D2H ring)", "rerendered": loop.rerendered}
 
+    # ---- product e2e: FrameLoop(product=True, pack8=True) — render() per camera + 8-bit hand-off to pinned host memory ----
+    product_e2e = None
+    try:
+        ploop = RL.FrameLoop(g, 3, W_IMG, H_IMG, device=dev, ring=3, to_host=True, product=True, pack8=True)
+        ploop.render(e2e_cams[:min(K, 6)])
+        barrier()
+        t_start = time.perf_counter()
+        pck = [0]
+
+        def pconsume(i, fr, stats):
+            pck[0] += int(fr["rgba8"][H_IMG // 2, W_IMG // 2, 0])
+
+        ploop.render(e2e_cams, pconsume)
+        torch.cuda.synchronize()
+        pe2e_s = max_over_ranks(time.perf_counter() - t_start)
+        product_e2e = {"value": frames_total / pe2e_s, "unit": "product frames/s", "h2d_bytes_per_step": ploop.h2d_bytes_per_frame,
+                       "d2h_bytes_per_step": ploop.d2h_bytes_per_frame, "rerendered": ploop.rerendered,
+                       "api": "FrameLoop(product=True, pack8=True): render() per camera, RGBA8 + depth f32 + depth8 + normal8 to pinned host memory"}
+        del ploop
+    except Exception as ex:  # noqa: BLE001
+        product_e2e = {"value": None, "error": str(ex)}
+    product_info["e2e"] = product_e2e
+
     # ---- CPU baseline: the oracle port on one frame of the same workload (rank 0, N=1 only) ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -197,10 +197,6 @@ int gsr_get_views(const gsr_workspace* ws, int32_t P, int32_t W, int32_t H, gsr_
 int gsr_profile_begin(int max_frames);
 int gsr_profile_end(float* ms_per_kernel, int* frames);
 
-/* Device self test (synchronous, test hook): compares the packed expf used inside the blend kernel with CUDA's expf,
- * bit for bit, over ~70M inputs; writes the number of mismatching results (must be 0) to the HOST pointer. */
-int gsr_selftest(unsigned long long* mismatches);
-
 const char* gsr_last_error(void);
 int gsr_abi_version(void);
 

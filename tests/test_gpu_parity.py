@@ -396,13 +396,3 @@ def test_geometry_reuse_second_pass_is_bit_identical_to_a_full_forward(dev):
         R.set_geometry_reuse(True)
         for x, y in zip(third, want):
             assert torch.equal(x, y)
-
-
-def test_packed_expf_matches_cuda_expf_bit_for_bit(dev):
-    """The blend evaluates expf for two splats at once with packed fp32 instructions (exp2x in gsr_forward.cu); the library's
-    self test sweeps ~70M inputs covering the blend's range and counts results that differ from expf()."""
-    import ctypes as C
-    from autovfx_b200 import _lib
-    bad = C.c_ulonglong(123)
-    _lib.check(_lib.lib.gsr_selftest(C.byref(bad)), "gsr_selftest")
-    assert bad.value == 0
