@@ -44,6 +44,11 @@ class gsr_views(C.Structure):
                                           "tile_count", "tile_big", "counters")]
 
 
+class gsr_object_xform(C.Structure):
+    _fields_ = [("rotation", C.c_float * 9), ("quat", C.c_float * 4), ("center", C.c_float * 3), ("initial_center", C.c_float * 3),
+                ("scaling", C.c_float), ("log_scaling", C.c_float)]
+
+
 GSR_FLAG_FOR_BACKWARD = 1
 GSR_FLAG_SORTED_KEYS = 2
 GSR_FLAG_TIGHT_TILES = 4
@@ -53,7 +58,7 @@ ABI_VERSION = 2
 EXPORTS = ("gsr_abi_version", "gsr_last_error", "gsr_geom_bytes", "gsr_binning_bytes", "gsr_binning_capacity", "gsr_image_bytes",
            "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_dist2_bytes", "gsr_dist2", "gsr_get_views",
            "gsr_profile_begin", "gsr_profile_end", "gsr_forward_multi", "gsr_axis_normals", "gsr_normal_maps",
-           "gsr_pack_frame")
+           "gsr_pack_frame", "gsr_activate_gaussians")
 
 
 def _load() -> C.CDLL:
@@ -95,6 +100,8 @@ def _load() -> C.CDLL:
     lib.gsr_pack_frame.restype = C.c_int
     lib.gsr_pack_frame.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]
+    lib.gsr_activate_gaussians.restype = C.c_int
+    lib.gsr_activate_gaussians.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 6 + [C.POINTER(gsr_object_xform)] + [C.c_void_p] * 6
     lib.gsr_backward.restype = C.c_int
     lib.gsr_backward.argtypes = [C.POINTER(gsr_frame), C.POINTER(gsr_workspace), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.POINTER(gsr_grads), C.c_void_p]

@@ -12,6 +12,9 @@ int pack_frame_impl(int W, int H, const float* rgb, const float* alpha, const fl
                     uint8_t* rgba8, uint8_t* normal8, uint8_t* depth8, cudaStream_t st);
 int backward_impl(const gsr_frame* f, const gsr_workspace* ws, const int32_t* radii, const float* out_alpha, const float* dL_dc,
                   const float* dL_dd, const float* dL_da, const gsr_grads* g, cudaStream_t st);
+int compose_impl(int N, int M, const float* xyz, const float* f_dc, const float* f_rest, const float* opacity_raw, const float* scaling_raw,
+                 const float* rotation_raw, const gsr_object_xform* xform, float* means3D, float* shs, float* opacities, float* scales,
+                 float* rotations, cudaStream_t st);
 int dist2_impl(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t dist2_bytes(int P);
 int profile_begin(int max_frames);
@@ -60,6 +63,13 @@ int gsr_normal_maps(int32_t W, int32_t H, const float* normal_img, const float* 
 int gsr_pack_frame(int32_t W, int32_t H, const float* rgb, const float* alpha, const float* depth, const float* normal_hwc,
                    float depth_scale, uint8_t* rgba8, uint8_t* normal8, uint8_t* depth8, void* stream) {
     return gsr::pack_frame_impl(W, H, rgb, alpha, depth, normal_hwc, depth_scale, rgba8, normal8, depth8, (cudaStream_t)stream);
+}
+
+int gsr_activate_gaussians(int32_t N, int32_t M, const float* xyz, const float* f_dc, const float* f_rest, const float* opacity_raw,
+                           const float* scaling_raw, const float* rotation_raw, const gsr_object_xform* xform, float* means3D, float* shs,
+                           float* opacities, float* scales, float* rotations, void* stream) {
+    return gsr::compose_impl(N, M, xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, xform, means3D, shs, opacities, scales, rotations,
+                             (cudaStream_t)stream);
 }
 
 int gsr_backward(const gsr_frame* frame, const gsr_workspace* ws, const int32_t* radii, const float* out_alpha,

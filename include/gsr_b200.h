@@ -17,6 +17,9 @@
  *   gsr_axis_normals  replaces  pc.get_normal(dir_pp_normalized) * 0.5 + 0.5      GR/:131-132,146-147; scene/gaussian_model.py:120-128
  *   gsr_normal_maps   replaces  normal normalisation + depth pseudo normal        GR/:168-191 (depth_pcd2normal GR/:23-38)
  *   gsr_pack_frame    replaces  the per-frame 8-bit conversions before encoding   scene_representation.py:424-438, sugar/render.py:18-22
+ *   gsr_activate_gaussians replaces the activations of every render call and the per-frame object edit
+ *                               get_scaling/get_rotation/get_opacity/get_features   sugar/gaussian_splatting/scene/gaussian_model.py:95-115
+ *                               transform_gaussians + merge_two_gaussians            gaussians_utils.py:71-125, scene_representation.py:357-371
  *
  * Conventions (same as the reference's C++ layer):
  *   - every pointer is a DEVICE pointer to contiguous fp32 / int32 data unless it says "host";
@@ -143,6 +146,27 @@ int gsr_normal_maps(int32_t W, int32_t H, const float* normal_img, const float* 
  *   depth8  [H,W]   = trunc(clip(depth/depth_scale, 0, 1)*255), the colormap index */
 int gsr_pack_frame(int32_t W, int32_t H, const float* rgb, const float* alpha, const float* depth, const float* normal_hwc,
                    float depth_scale, uint8_t* rgba8, uint8_t* normal8, uint8_t* depth8, void* stream);
+
+/* Rigid edit of one inserted object for one frame = the arguments of the reference's transform_gaussians(gaussians, center,
+ * rotation, scaling, initial_center) (gaussians_utils.py:88-125), plus the two values its host code derives from them. */
+typedef struct gsr_object_xform {
+    float rotation[9];       /* R, row-major 3x3                                                       */
+    float quat[4];           /* matrix_to_quaternion(R), (w,x,y,z) (rotation_utils.py:24-84)           */
+    float center[3];         /* target position of the pivot                                          */
+    float initial_center[3]; /* the pivot: centre of the object's mesh                                 */
+    float scaling;           /* uniform scale                                                          */
+    float log_scaling;       /* (float)log(scaling), added to the log-scales                           */
+} gsr_object_xform;
+
+/* RAW parameters (the reference's GaussianModel fields: _xyz [N,3], _features_dc [N,1,3], _features_rest [N,M-1,3],
+ * _opacity [N], _scaling [N,3], _rotation [N,4]) -> the ACTIVATED tensors the rasterizer takes: means3D [N,3],
+ * shs [N,M,3] = cat(dc, rest), opacities [N] = sigmoid, scales [N,3] = exp, rotations [N,4] = normalize.
+ * xform (HOST pointer, may be NULL) applies transform_gaussians first: scale about the pivot, rotate, translate,
+ * compose the quaternions, shift the log-scales.  The output pointers may address a sub-range of larger arrays
+ * (the tail of a resident scene): this replaces merge_two_gaussians' concatenation.  M >= 1. */
+int gsr_activate_gaussians(int32_t N, int32_t M, const float* xyz, const float* f_dc, const float* f_rest, const float* opacity_raw,
+                           const float* scaling_raw, const float* rotation_raw, const gsr_object_xform* xform, float* means3D,
+                           float* shs, float* opacities, float* scales, float* rotations, void* stream);
 
 /* Gradient buffers, all caller-allocated; the library zero-fills what it accumulates into (the
  * reference's torch::zeros, rasterize_points.cu:158-168).  dL_dsh may be NULL when shs is NULL,

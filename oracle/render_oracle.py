@@ -121,3 +121,60 @@ def depth8(depth_hw: np.ndarray, scale: float = 3.0) -> np.ndarray:
     """depth2img (sugar/render.py:18-22) up to the colormap: (clip(depth/scale, 0, 1) * 255).astype(uint8)."""
     d = np.clip(depth_hw.astype(f32) / f32(scale), f32(0), f32(1))
     return (d * f32(255)).astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------- per-frame edit path
+def matrix_to_quaternion(R: np.ndarray) -> np.ndarray:
+    """rotation_utils.py:24-84 for one 3x3 matrix: (w,x,y,z) of the best-conditioned candidate."""
+    m = R.astype(f32).reshape(9)
+    m00, m01, m02, m10, m11, m12, m20, m21, m22 = m
+    sq = np.array([f32(1) + m00 + m11 + m22, f32(1) + m00 - m11 - m22, f32(1) - m00 + m11 - m22, f32(1) - m00 - m11 + m22], dtype=f32)
+    q_abs = np.where(sq > 0, np.sqrt(np.maximum(sq, f32(0))), f32(0)).astype(f32)
+    cand = np.array([[q_abs[0] ** 2, m21 - m12, m02 - m20, m10 - m01], [m21 - m12, q_abs[1] ** 2, m10 + m01, m02 + m20],
+                     [m02 - m20, m10 + m01, q_abs[2] ** 2, m12 + m21], [m10 - m01, m20 + m02, m21 + m12, q_abs[3] ** 2]], dtype=f32)
+    cand = cand / (f32(2) * np.maximum(q_abs, f32(0.1)))[:, None]
+    return cand[int(np.argmax(q_abs))].astype(f32)
+
+
+def quaternion_multiply(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """rotation_utils.py:113-150 (product, then real part made non-negative); a [4], b [N,4]."""
+    aw, ax, ay, az = (f32(v) for v in a)
+    bw, bx, by, bz = (b[:, i].astype(f32) for i in range(4))
+    ow = aw * bw - ax * bx - ay * by - az * bz
+    ox = aw * bx + ax * bw + ay * bz - az * by
+    oy = aw * by - ax * bz + ay * bw + az * bx
+    oz = aw * bz + ax * by - ay * bx + az * bw
+    q = np.stack([ow, ox, oy, oz], -1).astype(f32)
+    return np.where(q[:, 0:1] < 0, -q, q).astype(f32)
+
+
+def transform_gaussians(raw: dict, center, rotation, scaling: float, initial_center) -> dict:
+    """gaussians_utils.py:88-125 on a dict of raw float32 arrays (xyz, scaling (log), rotation; the rest passes through)."""
+    c = np.asarray(initial_center, dtype=f32)[None, :]
+    R = np.asarray(rotation, dtype=f32).reshape(3, 3)
+    s = f32(scaling)
+    xyz = raw["xyz"].astype(f32) - c
+    xyz = xyz * s
+    xyz = xyz + c
+    scales = raw["scaling"].astype(f32) + f32(np.log(scaling))
+    xyz = xyz - c
+    A = R.T  # xyz @ R.T, accumulated left to right with fused multiply-adds like a K=3 GEMM
+    acc = (xyz[:, 0:1] * A[0][None, :]).astype(f32)
+    for j in (1, 2):
+        acc = (xyz[:, j:j + 1].astype(np.float64) * A[j][None, :].astype(np.float64) + acc.astype(np.float64)).astype(f32)
+    xyz = acc + c
+    rot = quaternion_multiply(matrix_to_quaternion(R), raw["rotation"].astype(f32))
+    xyz = xyz + (np.asarray(center, dtype=f32)[None, :] - c)
+    out = dict(raw)
+    out["xyz"], out["rotation"], out["scaling"] = xyz.astype(f32), rot, scales.astype(f32)
+    return out
+
+
+def activate(raw: dict) -> dict:
+    """scene/gaussian_model.py:95-115: exp, normalize, sigmoid, cat(dc, rest)."""
+    q = raw["rotation"].astype(f32)
+    n = np.sqrt(q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1] + q[:, 2] * q[:, 2] + q[:, 3] * q[:, 3])
+    op = raw["opacity"].astype(f32)
+    return {"means3D": raw["xyz"].astype(f32), "shs": np.concatenate([raw["f_dc"], raw["f_rest"]], 1).astype(f32),
+            "opacities": (f32(1) / (f32(1) + np.exp(-op))).astype(f32), "scales": np.exp(raw["scaling"].astype(f32)),
+            "rotations": (q / np.maximum(n, f32(1e-12))[:, None]).astype(f32)}

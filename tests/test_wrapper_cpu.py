@@ -92,3 +92,43 @@ def test_turbo_table_shape():
     lut = np.frombuffer(raw, dtype=np.uint8).reshape(256, 3)
     assert tuple(lut[0]) == (59, 18, 48) and tuple(lut[255]) == (3, 4, 122)  # cv2.COLORMAP_TURBO end points (B,G,R)
     del importlib
+
+
+def _raw(N, M, seed):
+    g = torch.Generator().manual_seed(seed)
+    return {"xyz": torch.randn(N, 3, generator=g), "f_dc": torch.randn(N, 1, 3, generator=g), "f_rest": torch.randn(N, M - 1, 3, generator=g) * 0.1,
+            "opacity": torch.randn(N, 1, generator=g) * 2, "scaling": torch.randn(N, 3, generator=g) * 0.5 - 3, "rotation": torch.randn(N, 4, generator=g)}
+
+
+def _rot(seed):
+    from scipy.spatial.transform import Rotation
+    return torch.tensor(Rotation.random(random_state=seed).as_matrix(), dtype=torch.float32)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_matrix_to_quaternion_oracle_vs_scipy(seed):
+    R = _rot(seed)
+    q = RO.matrix_to_quaternion(R.numpy())
+    ref = WR.matrix_to_quaternion(R).numpy()
+    if q[0] < 0:
+        q = -q
+    assert np.abs(q - ref).max() < 1e-6
+    assert abs(np.linalg.norm(q) - 1) < 1e-6
+
+
+def test_transform_and_activate_oracle_vs_torch():
+    raw = _raw(3000, 16, 4)
+    R = _rot(5)
+    center, pivot, s = torch.tensor([0.4, -1.2, 0.3]), torch.tensor([0.1, 0.2, -0.5]), 1.7
+    quat = torch.from_numpy(RO.matrix_to_quaternion(R.numpy()))
+    ref = WR.activate(WR.transform_gaussians(raw, center, R, s, pivot, quat=quat))
+    rn = {k: v.numpy() for k, v in raw.items()}
+    got = RO.activate(RO.transform_gaussians(rn, center.numpy(), R.numpy(), s, pivot.numpy()))
+    assert np.abs(got["means3D"] - ref["means3D"].numpy()).max() < 2e-6
+    assert np.abs(got["scales"] / ref["scales"].numpy() - 1).max() < 1e-6
+    assert np.abs(got["rotations"] - ref["rotations"].numpy()).max() < 3e-7
+    assert np.abs(got["opacities"] - ref["opacities"].numpy()).max() < 2e-7
+    assert (got["shs"] == ref["shs"].numpy()).all() and got["shs"].shape == (3000, 16, 3)
+    # identity transform = plain activation
+    ident = RO.transform_gaussians(rn, pivot.numpy(), np.eye(3, dtype=np.float32), 1.0, pivot.numpy())
+    assert np.abs(ident["xyz"] - rn["xyz"]).max() < 1e-6 and np.abs(ident["scaling"] - rn["scaling"]).max() == 0

@@ -109,3 +109,55 @@ def render_two_pass(rasterize, xyz, shs, opacity, scales, rotations, sh_degree, 
     return {"render": rendered_image, "depth": depth_image, "normal": normal_image(nimg),
             "pseudo_normal": pseudo_normal(depth_image, cam["viewmatrix"], cam["FoVx"], cam["FoVy"]),
             "normal_normed": normal_normed, "normal_raw_image": nimg, "radii": radii}
+
+
+# ----------------------------------------------------------------------------- per-frame edit path (gaussians_utils.py, rotation_utils.py)
+def matrix_to_quaternion(matrix):
+    """(w,x,y,z) with w >= 0 of a rotation matrix via scipy (an independent implementation; rotation_utils.py:24-84 returns the
+    same quaternion up to the sign convention and float32 round-off)."""
+    from scipy.spatial.transform import Rotation
+    x, y, z, w = Rotation.from_matrix(matrix.detach().cpu().double().numpy()).as_quat()
+    q = torch.tensor([w, x, y, z], dtype=torch.float64)
+    return (q if w >= 0 else -q).to(dtype=matrix.dtype, device=matrix.device)
+
+
+def quaternion_multiply(a, b):
+    """Hamilton product a*b (real part first), result flipped to a non-negative real part — the semantics of
+    rotation_utils.py:113-150, with the same left-to-right evaluation of each component."""
+    a0, a1, a2, a3 = a.unbind(-1)
+    b0, b1, b2, b3 = b.unbind(-1)
+    prod = torch.stack((a0 * b0 - a1 * b1 - a2 * b2 - a3 * b3,
+                        a0 * b1 + a1 * b0 + a2 * b3 - a3 * b2,
+                        a0 * b2 - a1 * b3 + a2 * b0 + a3 * b1,
+                        a0 * b3 + a1 * b2 - a2 * b1 + a3 * b0), -1)
+    return torch.where(prod[..., :1] < 0, -prod, prod)
+
+
+def transform_gaussians(raw, center, rotation, scaling, initial_center, quat=None):
+    """The op sequence of gaussians_utils.py:88-125 on a dict of raw tensors: scale about the pivot (and shift the log-scales),
+    rotate about the pivot (matmul with R^T, quaternion product), translate by (center - pivot)."""
+    import numpy as np
+    pivot = initial_center.unsqueeze(0)
+    p = raw["xyz"].clone()
+    p -= pivot
+    p *= scaling
+    p += pivot
+    log_s = raw["scaling"].clone()
+    log_s += np.log(scaling)
+    p -= pivot
+    p = torch.matmul(p, rotation.T)
+    p += pivot
+    q = quaternion_multiply(matrix_to_quaternion(rotation) if quat is None else quat, raw["rotation"].clone())
+    p += (center - initial_center).unsqueeze(0)
+    out = dict(raw)
+    out["xyz"], out["rotation"], out["scaling"] = p, q, log_s
+    return out
+
+
+def merge_two_gaussians(r1, r2):  # gaussians_utils.py:71-84
+    return {k: torch.cat([r1[k], r2[k]], dim=0) for k in ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")}
+
+
+def activate(raw):  # scene/gaussian_model.py:95-115: get_xyz, get_features, get_opacity, get_scaling, get_rotation
+    return {"means3D": raw["xyz"], "shs": torch.cat((raw["f_dc"], raw["f_rest"]), dim=1), "opacities": torch.sigmoid(raw["opacity"]),
+            "scales": torch.exp(raw["scaling"]), "rotations": torch.nn.functional.normalize(raw["rotation"])}
