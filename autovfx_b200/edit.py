@@ -149,6 +149,10 @@ class ResidentScene:
         self.P_scene = scene["xyz"].shape[0]
         self.M = scene["f_rest"].numel() // max(self.P_scene * 3, 1) + 1
         self.objects = {k: _raw_on(v, self.device) for k, v in (objects or {}).items()}
+        for k, o in self.objects.items():
+            n = o["xyz"].shape[0]
+            if n and o["f_rest"].numel() // (n * 3) + 1 != self.M:
+                raise ValueError("object %r stores %d SH coefficients, the scene %d" % (k, o["f_rest"].numel() // (n * 3) + 1, self.M))
         cap = self.P_scene + sum(o["xyz"].shape[0] for o in self.objects.values())
         self.arrays = _alloc(cap, self.M, self.device)
         activate_into(scene, self.arrays, 0, None)  # once; the raw scene tensors are not kept
