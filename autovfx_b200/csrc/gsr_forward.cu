@@ -710,13 +710,13 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __rest
 // =====================================================================================================
 constexpr int BLEND_THREADS = 256;
 // NX = number of extra colour channels blended with the same weights (0, or 3 for the product frame's second image)
-template <int NX, bool OCC4 = false>
+template <int NX>
 struct BlendCfg {
     static constexpr int REC = 48;               // staged record bytes per splat (stride 48 B: conflict-free 128-bit accesses)
     static constexpr int XREC = NX ? 16 : 0;     // staged extra-colour bytes per splat, kept in a separate array (a 64-byte
                                                  // combined stride costs 4-way bank conflicts on every staged load/store)
     static constexpr int PAIR = NX ? 112 : 96;   // queue bytes per splat pair
-    static constexpr int QCAP = OCC4 ? 46 : 62;  // queue entries per warp, an even number (flushed when fewer than 32 slots remain)
+    static constexpr int QCAP = 62;              // queue entries per warp, an even number (flushed when fewer than 32 slots remain)
     static constexpr int REC_BYTES = 2 * BLEND_THREADS * REC;                  // two staged batches
     static constexpr int XREC_BYTES = 2 * BLEND_THREADS * XREC;
     static constexpr int Q_BYTES = (BLEND_THREADS / 32) * (QCAP / 2) * PAIR;   // per-warp survivor queues
@@ -767,15 +767,15 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
 //       (+ T_final * bg like the colour image) — what a second rasterizer pass with colors_precomp = extra would
 //       return (gaussian_renderer/__init__.py:151-185), without re-running projection, binning, sort and the alpha math.
 // NC  : also record n_contrib (the 1-based list position of the last blended splat) for the backward pass.
-template <int NX, bool NC, bool OCC4 = false>
-__global__ void __launch_bounds__(BLEND_THREADS, OCC4 ? 4 : 0) k_blend(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+template <int NX, bool NC>
+__global__ void __launch_bounds__(BLEND_THREADS) k_blend(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                                                          const float4* __restrict__ records, const float* __restrict__ extra,
                                                          int W, int H, int gx, const float* __restrict__ bg,
                                                          float* __restrict__ out_color, float* __restrict__ out_depth,
                                                          float* __restrict__ out_alpha, float* __restrict__ out_extra,
                                                          uint32_t* __restrict__ n_contrib,
                                                          const gsr_counters* __restrict__ counters) {
-    typedef BlendCfg<NX, OCC4> Cfg;
+    typedef BlendCfg<NX> Cfg;
     constexpr int REC = Cfg::REC, PAIR = Cfg::PAIR, BLEND_QCAP = Cfg::QCAP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* sRec = reinterpret_cast<float4*>(smem_raw);
@@ -1057,38 +1057,26 @@ struct BlendArgs {
     int W, H, gx, gy; const float* bg; float *out_color, *out_depth, *out_alpha, *out_extra; uint32_t* n_contrib;
     const gsr_counters* counters;
 };
-template <int NX, bool NC, bool OCC4 = false>
+template <int NX, bool NC>
 static void launch_blend_t(const BlendArgs& a, cudaStream_t st) {
-    typedef BlendCfg<NX, OCC4> Cfg;
+    typedef BlendCfg<NX> Cfg;
     if (NX) {  // > 48 KB of dynamic shared memory: opt in once per device
         static bool configured[64] = {};
         int dev = 0;
         cudaGetDevice(&dev);
         if (dev >= 0 && dev < 64 && !configured[dev]) {
-            cudaFuncSetAttribute(k_blend<NX, NC, OCC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+            cudaFuncSetAttribute(k_blend<NX, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
             configured[dev] = true;
         }
     }
-    k_blend<NX, NC, OCC4><<<dim3(a.gx, a.gy), BLEND_THREADS, Cfg::SMEM, st>>>(a.ranges, a.point_list, a.records, a.extra, a.W, a.H, a.gx, a.bg,
-                                                                             a.out_color, a.out_depth, a.out_alpha, a.out_extra, a.n_contrib,
-                                                                             a.counters);
+    k_blend<NX, NC><<<dim3(a.gx, a.gy), BLEND_THREADS, Cfg::SMEM, st>>>(a.ranges, a.point_list, a.records, a.extra, a.W, a.H, a.gx, a.bg,
+                                                                       a.out_color, a.out_depth, a.out_alpha, a.out_extra, a.n_contrib, a.counters);
 }
-static int multi_occ4_mode() {  // experiment: GSR_MULTI_OCC=4 holds the 6-channel blend to 64 registers / 4 CTAs per SM
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("GSR_MULTI_OCC");
-        mode = (e && strcmp(e, "4") == 0) ? 1 : 0;
-    }
-    return mode;
-}
+// The 6-channel variant runs at 70 registers / 3 CTAs per SM; holding it to 64 registers / 4 CTAs (shorter queues, 92 B of
+// spills) was measured slower: 780 vs 862 product frames/s (profiles/r01_experiments.md).
 static void launch_blend(const BlendArgs& a, cudaStream_t st) {
-    if (a.extra) {
-        if (a.n_contrib) launch_blend_t<3, true>(a, st);
-        else if (multi_occ4_mode()) launch_blend_t<3, false, true>(a, st);
-        else launch_blend_t<3, false>(a, st);
-    } else {
-        if (a.n_contrib) launch_blend_t<0, true>(a, st); else launch_blend_t<0, false>(a, st);
-    }
+    if (a.extra) { if (a.n_contrib) launch_blend_t<3, true>(a, st); else launch_blend_t<3, false>(a, st); }
+    else         { if (a.n_contrib) launch_blend_t<0, true>(a, st); else launch_blend_t<0, false>(a, st); }
 }
 
 int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,
