@@ -25,7 +25,7 @@ struct GeomLayout {
     __host__ __device__ explicit GeomLayout(size_t P) {
         size_t o = 0;
         records = o; o = align_up(o + 48 * P, 256);
-        ranks = o;   o = align_up(o + 32 * P, 256);  // 8 x u32 in-tile ranks for Gaussians touching <= 8 tiles
+        ranks = o;   o = align_up(o + 48 * P, 256);  // compact list of VISIBLE Gaussians for k_emit: {id, depth bits, rect | 8 in-tile ranks}
         cov3D = o;   o = align_up(o + 24 * P, 256);
         clamped = o; o = align_up(o + P, 256);
         total = o + 256;

@@ -189,7 +189,7 @@ __device__ __forceinline__ void cov3d_ref_rounding(float sx, float sy, float sz,
 // DEG = -1: colours are precomputed.  VEC: SH rows are 16-byte aligned (M % 4 == 0) -> 16-byte staging, either one TMA
 // bulk copy per visible Gaussian issued by its own lane (BULK) or coalesced cp.async by the whole warp.
 template <int DEG, bool VEC, bool BULK>
-__global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
+__global__ void __launch_bounds__(PRE_THREADS, 8) k_preprocess(const PreParams p) {
     constexpr int DG = DEG < 0 ? 0 : DEG;
     constexpr int NF = sh_nf(DG);
     constexpr int STRIDE = sh_stride(DG, VEC);
@@ -364,11 +364,6 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
             rec[0] = make_float4(px, py, con_a, con_b);
             rec[1] = make_float4(con_c, opacity, depth, tau);
             rec[2] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
-            if (rect_n <= 8) {
-                uint4* rr = reinterpret_cast<uint4*>(p.ranks + 8 * (size_t)idx);
-                rr[0] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
-                if (rect_n > 4) rr[1] = make_uint4(rk[4], rk[5], rk[6], rk[7]);
-            }
             if (p.for_backward) {
                 if (p.cov3D_precomp == nullptr) {
 #pragma unroll
@@ -378,8 +373,27 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
             }
         }
     }
+    // Compact list of the visible Gaussians for k_emit (48 contiguous bytes each instead of three sparse rows): the block
+    // reserves its slots with one atomic, every visible thread appends {id, depth bits, tile rect | its 8 ranked tickets}.
+    // The list order varies from run to run; what k_emit writes from it does not (positions come from the ranks).
+    __shared__ uint32_t s_wcnt[PRE_THREADS / 32], s_base;
+    const unsigned vm = __ballot_sync(GSR_FULL, vis);
+    if (lane == 0) s_wcnt[warp] = (uint32_t)__popc(vm);
     const int nvis = __syncthreads_count(vis);
-    if (tid == 0 && nvis) atomicAdd(&p.counters->num_visible, (uint32_t)nvis);
+    if (nvis == 0) return;
+    if (tid == 0) s_base = atomicAdd(&p.counters->num_visible, (uint32_t)nvis);
+    __syncthreads();
+    if (vis) {
+        uint32_t slot = s_base + (uint32_t)__popc(vm & ((1u << lane) - 1u));
+#pragma unroll
+        for (int w = 0; w < PRE_THREADS / 32; w++) slot += (w < warp) ? s_wcnt[w] : 0u;
+        uint4* e = reinterpret_cast<uint4*>(p.ranks) + 3 * (size_t)slot;
+        e[0] = make_uint4((uint32_t)idx, __float_as_uint(depth), (uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
+        if (rect_n <= 8) {
+            e[1] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
+            if (rect_n > 4) e[2] = make_uint4(rk[4], rk[5], rk[6], rk[7]);
+        }
+    }
 }
 
 // =====================================================================================================
@@ -390,48 +404,54 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
                                                     gsr_counters* counters, int tiles, uint32_t capacity) {
     __shared__ uint32_t warp_sum[32];
     __shared__ uint32_t warp_max[32];
+    __shared__ uint32_t chunk_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (tiles + 1023) / 1024;
-    const int b = tid * per, e = min(tiles, b + per);
-    uint32_t local = 0, lmax = 0;
-    for (int t = b; t < e; t++) {
-        uint32_t c = tile_count[t] + tile_big[t];
-        local += c;
+    uint32_t carry = 0, lmax = 0;
+    for (int base = 0; base < tiles; base += 1024) {  // chunks of 1024 consecutive tiles: coalesced loads and stores
+        const int t = base + tid;
+        const uint32_t cs = t < tiles ? tile_count[t] : 0u, c = cs + (t < tiles ? tile_big[t] : 0u);
         lmax = max(lmax, c);
-    }
-    uint32_t incl = local;
+        uint32_t incl = c;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(GSR_FULL, incl, o);
-        if (lane >= o) incl += v;
-        lmax = max(lmax, __shfl_xor_sync(GSR_FULL, lmax, o));
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(GSR_FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t s = warp_sum[lane];
+            uint32_t si = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(GSR_FULL, si, o);
+                if (lane >= o) si += v;
+            }
+            warp_sum[lane] = si - s;  // exclusive
+            if (lane == 31) chunk_total = si;
+        }
+        __syncthreads();
+        const uint32_t start = carry + warp_sum[warp] + (incl - c);
+        if (t < tiles) {
+            ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
+            tile_fill[t] = start + cs;  // absolute cursor of the tile's un-ranked (large-rectangle) instances
+        }
+        carry += chunk_total;
+        __syncthreads();
     }
-    if (lane == 31) warp_sum[warp] = incl;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = max(lmax, __shfl_xor_sync(GSR_FULL, lmax, o));
     if (lane == 0) warp_max[warp] = lmax;
     __syncthreads();
     if (warp == 0) {
-        uint32_t s = warp_sum[lane], m = warp_max[lane];
-        uint32_t si = s;
+        uint32_t m = warp_max[lane];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t v = __shfl_up_sync(GSR_FULL, si, o);
-            if (lane >= o) si += v;
-            m = max(m, __shfl_xor_sync(GSR_FULL, m, o));
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(GSR_FULL, m, o));
+        if (lane == 0) {
+            counters->num_rendered = carry;
+            counters->overflow = carry > capacity ? 1u : 0u;
+            counters->max_tile = m;
         }
-        warp_sum[lane] = si - s;  // exclusive
-        if (lane == 31) {
-            counters->num_rendered = si;
-            counters->overflow = si > capacity ? 1u : 0u;
-        }
-        if (lane == 0) counters->max_tile = m;
-    }
-    __syncthreads();
-    uint32_t start = warp_sum[warp] + (incl - local);
-    for (int t = b; t < e; t++) {
-        const uint32_t cs = tile_count[t], c = cs + tile_big[t];
-        ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
-        tile_fill[t] = start + cs;  // absolute cursor of the tile's un-ranked (large-rectangle) instances
-        start += c;
     }
 }
 
@@ -440,38 +460,29 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
 // (the work of duplicateWithKeys, rasterizer_impl.cu:70-111; the tile id is implicit in the bucket)
 // =====================================================================================================
 template <bool TIGHT>
-__global__ void __launch_bounds__(256) k_emit(int P, int gx, int gy, const int* __restrict__ radii,
-                                              const float4* __restrict__ records, const uint32_t* __restrict__ ranks,
+__global__ void __launch_bounds__(256) k_emit(int gx, const float4* __restrict__ records, const uint4* __restrict__ vislist,
                                               const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_fill,
                                               uint2* __restrict__ pairs, const gsr_counters* __restrict__ counters) {
     if (counters->overflow) return;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nvis = counters->num_visible;
+    if ((uint32_t)blockIdx.x * blockDim.x >= nvis) return;  // the grid covers P, the list holds P_vis entries
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    uint32_t dbits = 0;
-    float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
-    if (idx < P) {
-        const int r = radii[idx];
-        if (r > 0) {
-            r0 = records[3 * (size_t)idx];
-            if (TIGHT) {
-                r1 = records[3 * (size_t)idx + 1];
-                dbits = __float_as_uint(r1.z);
-            } else {
-                dbits = __float_as_uint(records[3 * (size_t)idx + 1].z);
-            }
-            tile_rect(r0.x, r0.y, r, gx, gy, x0, y0, x1, y1);
-        }
+    uint32_t id = 0, dbits = 0;
+    if (i < nvis) {
+        const uint4 e0 = vislist[3 * (size_t)i];
+        id = e0.x; dbits = e0.y;
+        x0 = (int)(e0.z & 0xffffu); y0 = (int)(e0.z >> 16); x1 = (int)(e0.w & 0xffffu); y1 = (int)(e0.w >> 16);
     }
     // <= 8 tiles: the in-tile rank of every instance was drawn by k_preprocess -> plain scatter, no atomics
     // (rank 0xffffffff = tile culled by the tight-tile test)
     const int w = x1 - x0, cnt = w * (y1 - y0);
     if (cnt > 0 && cnt <= 8) {
-        const uint4* rr = reinterpret_cast<const uint4*>(ranks + 8 * (size_t)idx);
-        const uint4 ra = rr[0];
+        const uint4 ra = vislist[3 * (size_t)i + 1];
         uint4 rb = make_uint4(0, 0, 0, 0);
-        if (cnt > 4) rb = rr[1];
+        if (cnt > 4) rb = vislist[3 * (size_t)i + 2];
         const uint32_t rk[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-        const uint2 pr = make_uint2((uint32_t)idx, dbits);  // little endian: u64 = (depth bits << 32) | id
+        const uint2 pr = make_uint2(id, dbits);  // little endian: u64 = (depth bits << 32) | id
         int tx = x0, ty = y0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -485,7 +496,9 @@ __global__ void __launch_bounds__(256) k_emit(int P, int gx, int gy, const int* 
     // tight-tile test is re-evaluated on the same stored values k_preprocess used (bitwise same decision)
     const bool big = cnt > 8;
     if (TIGHT) {
-        const uint32_t pay[8] = {(uint32_t)idx, dbits, __float_as_uint(r0.x), __float_as_uint(r0.y), __float_as_uint(r0.z),
+        float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
+        if (big) { r0 = records[3 * (size_t)id]; r1 = records[3 * (size_t)id + 1]; }
+        const uint32_t pay[8] = {id, dbits, __float_as_uint(r0.x), __float_as_uint(r0.y), __float_as_uint(r0.z),
                                  __float_as_uint(r0.w), __float_as_uint(r1.x), __float_as_uint(r1.w)};
         for_each_tile<0, 8>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, pay, [&](int tile, int tx, int ty, const uint32_t(&o)[8]) {
             if (tile_may_touch(__uint_as_float(o[2]), __uint_as_float(o[3]), __uint_as_float(o[4]), __uint_as_float(o[5]),
@@ -493,7 +506,7 @@ __global__ void __launch_bounds__(256) k_emit(int P, int gx, int gy, const int* 
                 pairs[atomicAdd(&tile_fill[tile], 1u)] = make_uint2(o[0], o[1]);
         });
     } else {
-        const uint32_t pay[2] = {(uint32_t)idx, dbits};
+        const uint32_t pay[2] = {id, dbits};
         for_each_tile<0, 2>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, pay, [&](int tile, int, int, const uint32_t(&o)[2]) {
             pairs[atomicAdd(&tile_fill[tile], 1u)] = make_uint2(o[0], o[1]);
         });
@@ -1171,10 +1184,10 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     if ((rc = check_launch("gsr_forward/tile_scan", debug, st))) return rc;
 
     if (pp.tight)
-        k_emit<true><<<(f->P + 255) / 256, 256, 0, st>>>(f->P, il.gx, il.gy, radii, pp.records, pp.ranks, ranges, (uint32_t*)(img + il.tile_fill),
+        k_emit<true><<<(f->P + 255) / 256, 256, 0, st>>>(il.gx, pp.records, (const uint4*)pp.ranks, ranges, (uint32_t*)(img + il.tile_fill),
                                                          (uint2*)(bin + bl.pairs), counters);
     else
-        k_emit<false><<<(f->P + 255) / 256, 256, 0, st>>>(f->P, il.gx, il.gy, radii, pp.records, pp.ranks, ranges, (uint32_t*)(img + il.tile_fill),
+        k_emit<false><<<(f->P + 255) / 256, 256, 0, st>>>(il.gx, pp.records, (const uint4*)pp.ranks, ranges, (uint32_t*)(img + il.tile_fill),
                                                           (uint2*)(bin + bl.pairs), counters);
     prof_mark(3, st);
     if ((rc = check_launch("gsr_forward/emit", debug, st))) return rc;
