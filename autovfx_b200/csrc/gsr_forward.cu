@@ -57,6 +57,7 @@ struct PreParams {
     uint32_t* tile_count;
     uint32_t* tile_big;
     uint32_t* ranks;
+    uint32_t* block_vis;
     gsr_counters* counters;
 };
 
@@ -373,21 +374,23 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_preprocess(const PreParams p
             }
         }
     }
-    // Compact list of the visible Gaussians for k_emit (48 contiguous bytes each instead of three sparse rows): the block
-    // reserves its slots with one atomic, every visible thread appends {id, depth bits, tile rect | its 8 ranked tickets}.
-    // The list order varies from run to run; what k_emit writes from it does not (positions come from the ranks).
-    __shared__ uint32_t s_wcnt[PRE_THREADS / 32], s_base;
+    // List of the visible Gaussians for k_emit: the block packs {id, depth bits, tile rect | 8 ranked tickets} (48 contiguous
+    // bytes each) of its visible Gaussians to the front of its own 128 slots and records how many there are — k_emit then
+    // reads dense rows instead of three sparse ones, and no global allocation (atomic with return) is needed.
+    static_assert(PRE_THREADS == 128, "GeomLayout::block_vis assumes 128 Gaussians per preprocess block");
+    __shared__ uint32_t s_wcnt[PRE_THREADS / 32];
     const unsigned vm = __ballot_sync(GSR_FULL, vis);
     if (lane == 0) s_wcnt[warp] = (uint32_t)__popc(vm);
     const int nvis = __syncthreads_count(vis);
-    if (nvis == 0) return;
-    if (tid == 0) s_base = atomicAdd(&p.counters->num_visible, (uint32_t)nvis);
-    __syncthreads();
+    if (tid == 0) {
+        p.block_vis[blockIdx.x] = (uint32_t)nvis;
+        if (nvis) atomicAdd(&p.counters->num_visible, (uint32_t)nvis);
+    }
     if (vis) {
-        uint32_t slot = s_base + (uint32_t)__popc(vm & ((1u << lane) - 1u));
+        uint32_t slot = (uint32_t)__popc(vm & ((1u << lane) - 1u));
 #pragma unroll
         for (int w = 0; w < PRE_THREADS / 32; w++) slot += (w < warp) ? s_wcnt[w] : 0u;
-        uint4* e = reinterpret_cast<uint4*>(p.ranks) + 3 * (size_t)slot;
+        uint4* e = reinterpret_cast<uint4*>(p.ranks) + 3 * ((size_t)blockIdx.x * PRE_THREADS + slot);
         e[0] = make_uint4((uint32_t)idx, __float_as_uint(depth), (uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
         if (rect_n <= 8) {
             e[1] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
@@ -459,58 +462,100 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
 // Kernel 3: scatter one (depth bits, Gaussian id) pair per (Gaussian, tile) instance into the tile's bucket
 // (the work of duplicateWithKeys, rasterizer_impl.cu:70-111; the tile id is implicit in the bucket)
 // =====================================================================================================
-template <bool TIGHT>
-__global__ void __launch_bounds__(256) k_emit(int gx, const float4* __restrict__ records, const uint4* __restrict__ vislist,
-                                              const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_fill,
-                                              uint2* __restrict__ pairs, const gsr_counters* __restrict__ counters) {
+// Persistent CTAs walk the preprocess blocks' visible lists.  The kernel is bound by L1 wavefronts — every instance is one
+// scattered 8-byte store plus one scattered look-up of its tile's start offset — so the look-up table (4 B per tile) is
+// staged in shared memory when it fits (SMEM_TABLE; 8,160 tiles at 1080p = 32 KB), which halves the wavefronts.
+constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_MAX_TABLE_TILES = 16384;  // 64 KB of dynamic shared memory
+template <bool TIGHT, bool SMEM_TABLE>
+__global__ void __launch_bounds__(EMIT_THREADS, 5) k_emit(int nblocks /*preprocess blocks*/, int tiles, int gx, const float4* __restrict__ records,
+                                                       const uint4* __restrict__ vislist, const uint32_t* __restrict__ block_vis,
+                                                       const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_fill,
+                                                       uint2* __restrict__ pairs, const gsr_counters* __restrict__ counters) {
+    extern __shared__ uint32_t s_start[];
     if (counters->overflow) return;
-    const uint32_t nvis = counters->num_visible;
-    if ((uint32_t)blockIdx.x * blockDim.x >= nvis) return;  // the grid covers P, the list holds P_vis entries
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    uint32_t id = 0, dbits = 0;
-    if (i < nvis) {
-        const uint4 e0 = vislist[3 * (size_t)i];
-        id = e0.x; dbits = e0.y;
-        x0 = (int)(e0.z & 0xffffu); y0 = (int)(e0.z >> 16); x1 = (int)(e0.w & 0xffffu); y1 = (int)(e0.w >> 16);
+    if (SMEM_TABLE) {
+        for (int t = threadIdx.x; t < tiles; t += EMIT_THREADS) s_start[t] = ranges[t].x;
+        __syncthreads();
     }
-    // <= 8 tiles: the in-tile rank of every instance was drawn by k_preprocess -> plain scatter, no atomics
-    // (rank 0xffffffff = tile culled by the tight-tile test)
-    const int w = x1 - x0, cnt = w * (y1 - y0);
-    if (cnt > 0 && cnt <= 8) {
-        const uint4 ra = vislist[3 * (size_t)i + 1];
-        uint4 rb = make_uint4(0, 0, 0, 0);
-        if (cnt > 4) rb = vislist[3 * (size_t)i + 2];
-        const uint32_t rk[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-        const uint2 pr = make_uint2(id, dbits);  // little endian: u64 = (depth bits << 32) | id
-        int tx = x0, ty = y0;
+    constexpr int PER = EMIT_THREADS / PRE_THREADS;  // preprocess blocks per pass of this CTA
+    const int sub = threadIdx.x / PRE_THREADS, j = threadIdx.x % PRE_THREADS;
+    for (int pb0 = blockIdx.x * PER; pb0 < nblocks; pb0 += gridDim.x * PER) {
+        const int pb = pb0 + sub;
+        const bool have = pb < nblocks && (uint32_t)j < block_vis[pb];
+        int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+        uint32_t id = 0, dbits = 0;
+        const uint4* e = vislist + 3 * ((size_t)pb * PRE_THREADS + j);
+        if (have) {
+            const uint4 e0 = e[0];
+            id = e0.x; dbits = e0.y;
+            x0 = (int)(e0.z & 0xffffu); y0 = (int)(e0.z >> 16); x1 = (int)(e0.w & 0xffffu); y1 = (int)(e0.w >> 16);
+        }
+        // <= 8 tiles: the in-tile rank of every instance was drawn by k_preprocess -> plain scatter, no atomics
+        // (rank 0xffffffff = tile culled by the tight-tile test)
+        const int w = x1 - x0, cnt = w * (y1 - y0);
+        if (cnt > 0 && cnt <= 8) {
+            const uint4 ra = e[1];
+            uint4 rb = make_uint4(0, 0, 0, 0);
+            if (cnt > 4) rb = e[2];
+            const uint32_t rk[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+            const uint2 pr = make_uint2(id, dbits);  // little endian: u64 = (depth bits << 32) | id
+            int tx = x0, ty = y0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (k < cnt) {
-                if (!TIGHT || rk[k] != 0xffffffffu) pairs[ranges[ty * gx + tx].x + rk[k]] = pr;
-                if (++tx == x1) { tx = x0; ty++; }
+            for (int k = 0; k < 8; k++) {
+                if (k < cnt) {
+                    const int tile = ty * gx + tx;
+                    if (!TIGHT || rk[k] != 0xffffffffu) pairs[(SMEM_TABLE ? s_start[tile] : ranges[tile].x) + rk[k]] = pr;
+                    if (++tx == x1) { tx = x0; ty++; }
+                }
             }
         }
-    }
-    // > 8 tiles: walked by the whole warp, positions from the per-tile cursor initialised by k_tile_scan; the
-    // tight-tile test is re-evaluated on the same stored values k_preprocess used (bitwise same decision)
-    const bool big = cnt > 8;
-    if (TIGHT) {
-        float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
-        if (big) { r0 = records[3 * (size_t)id]; r1 = records[3 * (size_t)id + 1]; }
-        const uint32_t pay[8] = {id, dbits, __float_as_uint(r0.x), __float_as_uint(r0.y), __float_as_uint(r0.z),
-                                 __float_as_uint(r0.w), __float_as_uint(r1.x), __float_as_uint(r1.w)};
-        for_each_tile<0, 8>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, pay, [&](int tile, int tx, int ty, const uint32_t(&o)[8]) {
-            if (tile_may_touch(__uint_as_float(o[2]), __uint_as_float(o[3]), __uint_as_float(o[4]), __uint_as_float(o[5]),
-                               __uint_as_float(o[6]), __uint_as_float(o[7]), tx, ty))
+        // > 8 tiles: walked by the whole warp, positions from the per-tile cursor initialised by k_tile_scan; the
+        // tight-tile test is re-evaluated on the same stored values k_preprocess used (bitwise same decision)
+        const bool big = cnt > 8;
+        if (TIGHT) {
+            float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
+            if (big) { r0 = records[3 * (size_t)id]; r1 = records[3 * (size_t)id + 1]; }
+            const uint32_t pay[8] = {id, dbits, __float_as_uint(r0.x), __float_as_uint(r0.y), __float_as_uint(r0.z),
+                                     __float_as_uint(r0.w), __float_as_uint(r1.x), __float_as_uint(r1.w)};
+            for_each_tile<0, 8>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, pay, [&](int tile, int tx, int ty, const uint32_t(&o)[8]) {
+                if (tile_may_touch(__uint_as_float(o[2]), __uint_as_float(o[3]), __uint_as_float(o[4]), __uint_as_float(o[5]),
+                                   __uint_as_float(o[6]), __uint_as_float(o[7]), tx, ty))
+                    pairs[atomicAdd(&tile_fill[tile], 1u)] = make_uint2(o[0], o[1]);
+            });
+        } else {
+            const uint32_t pay[2] = {id, dbits};
+            for_each_tile<0, 2>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, pay, [&](int tile, int, int, const uint32_t(&o)[2]) {
                 pairs[atomicAdd(&tile_fill[tile], 1u)] = make_uint2(o[0], o[1]);
-        });
-    } else {
-        const uint32_t pay[2] = {id, dbits};
-        for_each_tile<0, 2>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, pay, [&](int tile, int, int, const uint32_t(&o)[2]) {
-            pairs[atomicAdd(&tile_fill[tile], 1u)] = make_uint2(o[0], o[1]);
-        });
+            });
+        }
     }
+}
+template <bool TIGHT, bool SMEM_TABLE>
+static void launch_emit(int nblocks, int tiles, int gx, const float4* records, const uint4* vislist, const uint32_t* block_vis, const uint2* ranges,
+                        uint32_t* tile_fill, uint2* pairs, const gsr_counters* counters, cudaStream_t st) {
+    const size_t smem = SMEM_TABLE ? (size_t)tiles * 4 : 0;
+    if (SMEM_TABLE) {
+        static bool configured[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !configured[dev]) {
+            cudaFuncSetAttribute(k_emit<TIGHT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_MAX_TABLE_TILES * 4);
+            configured[dev] = true;
+        }
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const int per = EMIT_THREADS / PRE_THREADS;
+    const int want = (nblocks + per - 1) / per;
+    const int resident = sms * (SMEM_TABLE ? (tiles * 4 > 56 * 1024 ? 3 : (tiles * 4 > 36 * 1024 ? 4 : 5)) : 5);
+    const int grid = want < resident ? want : resident;
+    k_emit<TIGHT, SMEM_TABLE><<<grid > 0 ? grid : 1, EMIT_THREADS, smem, st>>>(nblocks, tiles, gx, records, vislist, block_vis, ranges, tile_fill, pairs, counters);
 }
 
 // =====================================================================================================
@@ -1162,7 +1207,7 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     pp.view = f->viewmatrix; pp.proj = f->projmatrix; pp.campos = f->campos;
     pp.records = (float4*)(geo + gl.records); pp.cov3D = (float*)(geo + gl.cov3D); pp.clamped = (uint8_t*)(geo + gl.clamped);
     pp.radii = radii; pp.tile_count = (uint32_t*)(img + il.tile_count); pp.tile_big = (uint32_t*)(img + il.tile_big);
-    pp.ranks = (uint32_t*)(geo + gl.ranks); pp.counters = counters;
+    pp.ranks = (uint32_t*)(geo + gl.ranks); pp.block_vis = (uint32_t*)(geo + gl.block_vis); pp.counters = counters;
 
     if (f->colors_precomp) launch_pre<-1>(false, pp, st);
     else {
@@ -1183,12 +1228,20 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     prof_mark(2, st);
     if ((rc = check_launch("gsr_forward/tile_scan", debug, st))) return rc;
 
-    if (pp.tight)
-        k_emit<true><<<(f->P + 255) / 256, 256, 0, st>>>(il.gx, pp.records, (const uint4*)pp.ranks, ranges, (uint32_t*)(img + il.tile_fill),
-                                                         (uint2*)(bin + bl.pairs), counters);
-    else
-        k_emit<false><<<(f->P + 255) / 256, 256, 0, st>>>(il.gx, pp.records, (const uint4*)pp.ranks, ranges, (uint32_t*)(img + il.tile_fill),
-                                                          (uint2*)(bin + bl.pairs), counters);
+    {
+        const int nblocks = (f->P + PRE_THREADS - 1) / PRE_THREADS;
+        const bool table = il.tiles <= EMIT_MAX_TABLE_TILES;
+        const uint4* vl = (const uint4*)pp.ranks;
+        uint32_t* tf = (uint32_t*)(img + il.tile_fill);
+        uint2* prs = (uint2*)(bin + bl.pairs);
+        if (pp.tight) {
+            if (table) launch_emit<true, true>(nblocks, il.tiles, il.gx, pp.records, vl, pp.block_vis, ranges, tf, prs, counters, st);
+            else launch_emit<true, false>(nblocks, il.tiles, il.gx, pp.records, vl, pp.block_vis, ranges, tf, prs, counters, st);
+        } else {
+            if (table) launch_emit<false, true>(nblocks, il.tiles, il.gx, pp.records, vl, pp.block_vis, ranges, tf, prs, counters, st);
+            else launch_emit<false, false>(nblocks, il.tiles, il.gx, pp.records, vl, pp.block_vis, ranges, tf, prs, counters, st);
+        }
+    }
     prof_mark(3, st);
     if ((rc = check_launch("gsr_forward/emit", debug, st))) return rc;
 
