@@ -462,100 +462,87 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
 // Kernel 3: scatter one (depth bits, Gaussian id) pair per (Gaussian, tile) instance into the tile's bucket
 // (the work of duplicateWithKeys, rasterizer_impl.cu:70-111; the tile id is implicit in the bucket)
 // =====================================================================================================
-// Persistent CTAs walk the preprocess blocks' visible lists.  The kernel is bound by L1 wavefronts — every instance is one
-// scattered 8-byte store plus one scattered look-up of its tile's start offset — so the look-up table (4 B per tile) is
-// staged in shared memory when it fits (SMEM_TABLE; 8,160 tiles at 1080p = 32 KB), which halves the wavefronts.
+// One thread per slot of the preprocess blocks' visible lists (dense 48-byte rows; slots past a block's count idle).
+// Rectangles of more than 8 tiles draw their positions from the per-tile cursor with an atomic whose return value the
+// store needs; walking them one after the other costs one L2 round trip each (ncu: 28 % of the kernel's stall samples,
+// 2.5-5 such rectangles per warp), so up to EMIT_KB of them are in flight together: all atomics first, then all stores.
 constexpr int EMIT_THREADS = 256;
-constexpr int EMIT_MAX_TABLE_TILES = 16384;  // 64 KB of dynamic shared memory
-template <bool TIGHT, bool SMEM_TABLE>
-__global__ void __launch_bounds__(EMIT_THREADS, 5) k_emit(int nblocks /*preprocess blocks*/, int tiles, int gx, const float4* __restrict__ records,
+constexpr int EMIT_KB = 8;
+template <bool TIGHT>
+__global__ void __launch_bounds__(EMIT_THREADS) k_emit(int nblocks /*preprocess blocks*/, int gx, const float4* __restrict__ records,
                                                        const uint4* __restrict__ vislist, const uint32_t* __restrict__ block_vis,
                                                        const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_fill,
                                                        uint2* __restrict__ pairs, const gsr_counters* __restrict__ counters) {
-    extern __shared__ uint32_t s_start[];
     if (counters->overflow) return;
-    if (SMEM_TABLE) {
-        for (int t = threadIdx.x; t < tiles; t += EMIT_THREADS) s_start[t] = ranges[t].x;
-        __syncthreads();
+    constexpr int PER = EMIT_THREADS / PRE_THREADS;  // preprocess blocks per CTA
+    const int pb = blockIdx.x * PER + threadIdx.x / PRE_THREADS, j = threadIdx.x % PRE_THREADS, lane = threadIdx.x & 31;
+    const uint32_t nv = pb < nblocks ? block_vis[pb] : 0u;
+    if ((uint32_t)(j & ~31) >= nv) return;  // whole warp past the end of its block's list
+    const bool have = (uint32_t)j < nv;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    uint32_t id = 0, dbits = 0;
+    const uint4* e = vislist + 3 * ((size_t)pb * PRE_THREADS + j);
+    if (have) {
+        const uint4 e0 = e[0];
+        id = e0.x; dbits = e0.y;
+        x0 = (int)(e0.z & 0xffffu); y0 = (int)(e0.z >> 16); x1 = (int)(e0.w & 0xffffu); y1 = (int)(e0.w >> 16);
     }
-    constexpr int PER = EMIT_THREADS / PRE_THREADS;  // preprocess blocks per pass of this CTA
-    const int sub = threadIdx.x / PRE_THREADS, j = threadIdx.x % PRE_THREADS;
-    for (int pb0 = blockIdx.x * PER; pb0 < nblocks; pb0 += gridDim.x * PER) {
-        const int pb = pb0 + sub;
-        const bool have = pb < nblocks && (uint32_t)j < block_vis[pb];
-        int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-        uint32_t id = 0, dbits = 0;
-        const uint4* e = vislist + 3 * ((size_t)pb * PRE_THREADS + j);
-        if (have) {
-            const uint4 e0 = e[0];
-            id = e0.x; dbits = e0.y;
-            x0 = (int)(e0.z & 0xffffu); y0 = (int)(e0.z >> 16); x1 = (int)(e0.w & 0xffffu); y1 = (int)(e0.w >> 16);
-        }
-        // <= 8 tiles: the in-tile rank of every instance was drawn by k_preprocess -> plain scatter, no atomics
-        // (rank 0xffffffff = tile culled by the tight-tile test)
-        const int w = x1 - x0, cnt = w * (y1 - y0);
-        if (cnt > 0 && cnt <= 8) {
-            const uint4 ra = e[1];
-            uint4 rb = make_uint4(0, 0, 0, 0);
-            if (cnt > 4) rb = e[2];
-            const uint32_t rk[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-            const uint2 pr = make_uint2(id, dbits);  // little endian: u64 = (depth bits << 32) | id
-            int tx = x0, ty = y0;
+    // <= 8 tiles: the in-tile rank of every instance was drawn by k_preprocess -> plain scatter, no atomics
+    // (rank 0xffffffff = tile culled by the tight-tile test)
+    const int w = x1 - x0, cnt = w * (y1 - y0);
+    if (cnt > 0 && cnt <= 8) {
+        const uint4 ra = e[1];
+        uint4 rb = make_uint4(0, 0, 0, 0);
+        if (cnt > 4) rb = e[2];
+        const uint32_t rk[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+        const uint2 pr = make_uint2(id, dbits);  // little endian: u64 = (depth bits << 32) | id
+        int tx = x0, ty = y0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if (k < cnt) {
-                    const int tile = ty * gx + tx;
-                    if (!TIGHT || rk[k] != 0xffffffffu) pairs[(SMEM_TABLE ? s_start[tile] : ranges[tile].x) + rk[k]] = pr;
-                    if (++tx == x1) { tx = x0; ty++; }
+        for (int k = 0; k < 8; k++) {
+            if (k < cnt) {
+                if (!TIGHT || rk[k] != 0xffffffffu) pairs[ranges[ty * gx + tx].x + rk[k]] = pr;
+                if (++tx == x1) { tx = x0; ty++; }
+            }
+        }
+    }
+    // > 8 tiles: lanes = tiles of one rectangle; positions from the per-tile cursor initialised by k_tile_scan; the
+    // tight-tile test is re-evaluated on the same stored values k_preprocess used (bitwise same decision)
+    unsigned big = __ballot_sync(GSR_FULL, cnt > 8);
+    if (!big) return;
+    float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
+    if (TIGHT && cnt > 8) { r0 = records[3 * (size_t)id]; r1 = records[3 * (size_t)id + 1]; }
+    while (big) {
+        uint32_t pos[EMIT_KB];
+        uint2 val[EMIT_KB];
+        bool ok[EMIT_KB];
+#pragma unroll
+        for (int r = 0; r < EMIT_KB; r++) {
+            ok[r] = false;
+            if (big) {  // warp-uniform
+                const int src = __ffs(big) - 1;
+                big &= big - 1;
+                const int bx0 = __shfl_sync(GSR_FULL, x0, src), by0 = __shfl_sync(GSR_FULL, y0, src);
+                const int bw = __shfl_sync(GSR_FULL, w, src), bn = __shfl_sync(GSR_FULL, cnt, src);
+                val[r] = make_uint2(__shfl_sync(GSR_FULL, id, src), __shfl_sync(GSR_FULL, dbits, src));
+                float4 q0 = r0, q1 = r1;
+                if (TIGHT) {
+                    q0.x = __shfl_sync(GSR_FULL, r0.x, src); q0.y = __shfl_sync(GSR_FULL, r0.y, src); q0.z = __shfl_sync(GSR_FULL, r0.z, src);
+                    q0.w = __shfl_sync(GSR_FULL, r0.w, src); q1.x = __shfl_sync(GSR_FULL, r1.x, src); q1.w = __shfl_sync(GSR_FULL, r1.w, src);
+                }
+                for (int t = lane; t < bn; t += 32) {
+                    const int ty = by0 + t / bw, tx = bx0 + t % bw;
+                    if (!TIGHT || tile_may_touch(q0.x, q0.y, q0.z, q0.w, q1.x, q1.w, tx, ty)) {
+                        const uint32_t ps = atomicAdd(&tile_fill[ty * gx + tx], 1u);
+                        if (t < 32) { pos[r] = ps; ok[r] = true; }   // the first 32 tiles stay in flight
+                        else pairs[ps] = val[r];                      // rectangles of more than 32 tiles: rare
+                    }
                 }
             }
         }
-        // > 8 tiles: walked by the whole warp, positions from the per-tile cursor initialised by k_tile_scan; the
-        // tight-tile test is re-evaluated on the same stored values k_preprocess used (bitwise same decision)
-        const bool big = cnt > 8;
-        if (TIGHT) {
-            float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
-            if (big) { r0 = records[3 * (size_t)id]; r1 = records[3 * (size_t)id + 1]; }
-            const uint32_t pay[8] = {id, dbits, __float_as_uint(r0.x), __float_as_uint(r0.y), __float_as_uint(r0.z),
-                                     __float_as_uint(r0.w), __float_as_uint(r1.x), __float_as_uint(r1.w)};
-            for_each_tile<0, 8>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, pay, [&](int tile, int tx, int ty, const uint32_t(&o)[8]) {
-                if (tile_may_touch(__uint_as_float(o[2]), __uint_as_float(o[3]), __uint_as_float(o[4]), __uint_as_float(o[5]),
-                                   __uint_as_float(o[6]), __uint_as_float(o[7]), tx, ty))
-                    pairs[atomicAdd(&tile_fill[tile], 1u)] = make_uint2(o[0], o[1]);
-            });
-        } else {
-            const uint32_t pay[2] = {id, dbits};
-            for_each_tile<0, 2>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, pay, [&](int tile, int, int, const uint32_t(&o)[2]) {
-                pairs[atomicAdd(&tile_fill[tile], 1u)] = make_uint2(o[0], o[1]);
-            });
-        }
+#pragma unroll
+        for (int r = 0; r < EMIT_KB; r++)
+            if (ok[r]) pairs[pos[r]] = val[r];
     }
-}
-template <bool TIGHT, bool SMEM_TABLE>
-static void launch_emit(int nblocks, int tiles, int gx, const float4* records, const uint4* vislist, const uint32_t* block_vis, const uint2* ranges,
-                        uint32_t* tile_fill, uint2* pairs, const gsr_counters* counters, cudaStream_t st) {
-    const size_t smem = SMEM_TABLE ? (size_t)tiles * 4 : 0;
-    if (SMEM_TABLE) {
-        static bool configured[64] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev >= 0 && dev < 64 && !configured[dev]) {
-            cudaFuncSetAttribute(k_emit<TIGHT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_MAX_TABLE_TILES * 4);
-            configured[dev] = true;
-        }
-    }
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    const int per = EMIT_THREADS / PRE_THREADS;
-    const int want = (nblocks + per - 1) / per;
-    const int resident = sms * (SMEM_TABLE ? (tiles * 4 > 56 * 1024 ? 3 : (tiles * 4 > 36 * 1024 ? 4 : 5)) : 5);
-    const int grid = want < resident ? want : resident;
-    k_emit<TIGHT, SMEM_TABLE><<<grid > 0 ? grid : 1, EMIT_THREADS, smem, st>>>(nblocks, tiles, gx, records, vislist, block_vis, ranges, tile_fill, pairs, counters);
 }
 
 // =====================================================================================================
@@ -1230,17 +1217,12 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
 
     {
         const int nblocks = (f->P + PRE_THREADS - 1) / PRE_THREADS;
-        const bool table = il.tiles <= EMIT_MAX_TABLE_TILES;
+        const int grid = (nblocks + EMIT_THREADS / PRE_THREADS - 1) / (EMIT_THREADS / PRE_THREADS);
         const uint4* vl = (const uint4*)pp.ranks;
         uint32_t* tf = (uint32_t*)(img + il.tile_fill);
         uint2* prs = (uint2*)(bin + bl.pairs);
-        if (pp.tight) {
-            if (table) launch_emit<true, true>(nblocks, il.tiles, il.gx, pp.records, vl, pp.block_vis, ranges, tf, prs, counters, st);
-            else launch_emit<true, false>(nblocks, il.tiles, il.gx, pp.records, vl, pp.block_vis, ranges, tf, prs, counters, st);
-        } else {
-            if (table) launch_emit<false, true>(nblocks, il.tiles, il.gx, pp.records, vl, pp.block_vis, ranges, tf, prs, counters, st);
-            else launch_emit<false, false>(nblocks, il.tiles, il.gx, pp.records, vl, pp.block_vis, ranges, tf, prs, counters, st);
-        }
+        if (pp.tight) k_emit<true><<<grid, EMIT_THREADS, 0, st>>>(nblocks, il.gx, pp.records, vl, pp.block_vis, ranges, tf, prs, counters);
+        else k_emit<false><<<grid, EMIT_THREADS, 0, st>>>(nblocks, il.gx, pp.records, vl, pp.block_vis, ranges, tf, prs, counters);
     }
     prof_mark(3, st);
     if ((rc = check_launch("gsr_forward/emit", debug, st))) return rc;
