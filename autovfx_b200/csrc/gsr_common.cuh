@@ -21,13 +21,11 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 
 // ---- workspace layouts (pure functions of P / capacity / W,H) --------------------------------------
 struct GeomLayout {
-    size_t records, ranks, block_vis, cov3D, clamped, total;
+    size_t records, ranks, cov3D, clamped, total;
     __host__ __device__ explicit GeomLayout(size_t P) {
         size_t o = 0;
         records = o; o = align_up(o + 48 * P, 256);
-        ranks = o;   o = align_up(o + 48 * P, 256);  // per preprocess block, packed to the front of its 128 slots: the block's VISIBLE
-                                                     // Gaussians for k_emit, 48 B each: {id, depth bits, tile rect | 8 in-tile ranks}
-        block_vis = o; o = align_up(o + 4 * ((P + 127) / 128), 256);  // visible Gaussians per preprocess block (128 Gaussians)
+        ranks = o;   o = align_up(o + 32 * P, 256);  // 8 x u32 in-tile ranks for Gaussians touching <= 8 tiles
         cov3D = o;   o = align_up(o + 24 * P, 256);
         clamped = o; o = align_up(o + P, 256);
         total = o + 256;

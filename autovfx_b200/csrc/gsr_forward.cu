@@ -57,7 +57,6 @@ struct PreParams {
     uint32_t* tile_count;
     uint32_t* tile_big;
     uint32_t* ranks;
-    uint32_t* block_vis;
     gsr_counters* counters;
 };
 
@@ -190,7 +189,7 @@ __device__ __forceinline__ void cov3d_ref_rounding(float sx, float sy, float sz,
 // DEG = -1: colours are precomputed.  VEC: SH rows are 16-byte aligned (M % 4 == 0) -> 16-byte staging, either one TMA
 // bulk copy per visible Gaussian issued by its own lane (BULK) or coalesced cp.async by the whole warp.
 template <int DEG, bool VEC, bool BULK>
-__global__ void __launch_bounds__(PRE_THREADS, 8) k_preprocess(const PreParams p) {
+__global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
     constexpr int DG = DEG < 0 ? 0 : DEG;
     constexpr int NF = sh_nf(DG);
     constexpr int STRIDE = sh_stride(DG, VEC);
@@ -365,6 +364,11 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_preprocess(const PreParams p
             rec[0] = make_float4(px, py, con_a, con_b);
             rec[1] = make_float4(con_c, opacity, depth, tau);
             rec[2] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+            if (rect_n <= 8) {
+                uint4* rr = reinterpret_cast<uint4*>(p.ranks + 8 * (size_t)idx);
+                rr[0] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
+                if (rect_n > 4) rr[1] = make_uint4(rk[4], rk[5], rk[6], rk[7]);
+            }
             if (p.for_backward) {
                 if (p.cov3D_precomp == nullptr) {
 #pragma unroll
@@ -374,29 +378,8 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_preprocess(const PreParams p
             }
         }
     }
-    // List of the visible Gaussians for k_emit: the block packs {id, depth bits, tile rect | 8 ranked tickets} (48 contiguous
-    // bytes each) of its visible Gaussians to the front of its own 128 slots and records how many there are — k_emit then
-    // reads dense rows instead of three sparse ones, and no global allocation (atomic with return) is needed.
-    static_assert(PRE_THREADS == 128, "GeomLayout::block_vis assumes 128 Gaussians per preprocess block");
-    __shared__ uint32_t s_wcnt[PRE_THREADS / 32];
-    const unsigned vm = __ballot_sync(GSR_FULL, vis);
-    if (lane == 0) s_wcnt[warp] = (uint32_t)__popc(vm);
     const int nvis = __syncthreads_count(vis);
-    if (tid == 0) {
-        p.block_vis[blockIdx.x] = (uint32_t)nvis;
-        if (nvis) atomicAdd(&p.counters->num_visible, (uint32_t)nvis);
-    }
-    if (vis) {
-        uint32_t slot = (uint32_t)__popc(vm & ((1u << lane) - 1u));
-#pragma unroll
-        for (int w = 0; w < PRE_THREADS / 32; w++) slot += (w < warp) ? s_wcnt[w] : 0u;
-        uint4* e = reinterpret_cast<uint4*>(p.ranks) + 3 * ((size_t)blockIdx.x * PRE_THREADS + slot);
-        e[0] = make_uint4((uint32_t)idx, __float_as_uint(depth), (uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
-        if (rect_n <= 8) {
-            e[1] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
-            if (rect_n > 4) e[2] = make_uint4(rk[4], rk[5], rk[6], rk[7]);
-        }
-    }
+    if (tid == 0 && nvis) atomicAdd(&p.counters->num_visible, (uint32_t)nvis);
 }
 
 // =====================================================================================================
@@ -462,40 +445,39 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
 // Kernel 3: scatter one (depth bits, Gaussian id) pair per (Gaussian, tile) instance into the tile's bucket
 // (the work of duplicateWithKeys, rasterizer_impl.cu:70-111; the tile id is implicit in the bucket)
 // =====================================================================================================
-// One thread per slot of the preprocess blocks' visible lists (dense 48-byte rows; slots past a block's count idle).
-// Rectangles of more than 8 tiles draw their positions from the per-tile cursor with an atomic whose return value the
-// store needs; walking them one after the other costs one L2 round trip each (ncu: 28 % of the kernel's stall samples,
-// 2.5-5 such rectangles per warp), so up to EMIT_KB of them are in flight together: all atomics first, then all stores.
-constexpr int EMIT_THREADS = 256;
-constexpr int EMIT_KB = 8;
 template <bool TIGHT>
-__global__ void __launch_bounds__(EMIT_THREADS) k_emit(int nblocks /*preprocess blocks*/, int gx, const float4* __restrict__ records,
-                                                       const uint4* __restrict__ vislist, const uint32_t* __restrict__ block_vis,
-                                                       const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_fill,
-                                                       uint2* __restrict__ pairs, const gsr_counters* __restrict__ counters) {
+__global__ void __launch_bounds__(256) k_emit(int P, int gx, int gy, const int* __restrict__ radii,
+                                              const float4* __restrict__ records, const uint32_t* __restrict__ ranks,
+                                              const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_fill,
+                                              uint2* __restrict__ pairs, const gsr_counters* __restrict__ counters) {
     if (counters->overflow) return;
-    constexpr int PER = EMIT_THREADS / PRE_THREADS;  // preprocess blocks per CTA
-    const int pb = blockIdx.x * PER + threadIdx.x / PRE_THREADS, j = threadIdx.x % PRE_THREADS, lane = threadIdx.x & 31;
-    const uint32_t nv = pb < nblocks ? block_vis[pb] : 0u;
-    if ((uint32_t)(j & ~31) >= nv) return;  // whole warp past the end of its block's list
-    const bool have = (uint32_t)j < nv;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    uint32_t id = 0, dbits = 0;
-    const uint4* e = vislist + 3 * ((size_t)pb * PRE_THREADS + j);
-    if (have) {
-        const uint4 e0 = e[0];
-        id = e0.x; dbits = e0.y;
-        x0 = (int)(e0.z & 0xffffu); y0 = (int)(e0.z >> 16); x1 = (int)(e0.w & 0xffffu); y1 = (int)(e0.w >> 16);
+    uint32_t dbits = 0;
+    float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
+    if (idx < P) {
+        const int r = radii[idx];
+        if (r > 0) {
+            r0 = records[3 * (size_t)idx];
+            if (TIGHT) {
+                r1 = records[3 * (size_t)idx + 1];
+                dbits = __float_as_uint(r1.z);
+            } else {
+                dbits = __float_as_uint(records[3 * (size_t)idx + 1].z);
+            }
+            tile_rect(r0.x, r0.y, r, gx, gy, x0, y0, x1, y1);
+        }
     }
     // <= 8 tiles: the in-tile rank of every instance was drawn by k_preprocess -> plain scatter, no atomics
     // (rank 0xffffffff = tile culled by the tight-tile test)
     const int w = x1 - x0, cnt = w * (y1 - y0);
     if (cnt > 0 && cnt <= 8) {
-        const uint4 ra = e[1];
+        const uint4* rr = reinterpret_cast<const uint4*>(ranks + 8 * (size_t)idx);
+        const uint4 ra = rr[0];
         uint4 rb = make_uint4(0, 0, 0, 0);
-        if (cnt > 4) rb = e[2];
+        if (cnt > 4) rb = rr[1];
         const uint32_t rk[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-        const uint2 pr = make_uint2(id, dbits);  // little endian: u64 = (depth bits << 32) | id
+        const uint2 pr = make_uint2((uint32_t)idx, dbits);  // little endian: u64 = (depth bits << 32) | id
         int tx = x0, ty = y0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -505,43 +487,22 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(int nblocks /*preprocess 
             }
         }
     }
-    // > 8 tiles: lanes = tiles of one rectangle; positions from the per-tile cursor initialised by k_tile_scan; the
+    // > 8 tiles: walked by the whole warp, positions from the per-tile cursor initialised by k_tile_scan; the
     // tight-tile test is re-evaluated on the same stored values k_preprocess used (bitwise same decision)
-    unsigned big = __ballot_sync(GSR_FULL, cnt > 8);
-    if (!big) return;
-    float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
-    if (TIGHT && cnt > 8) { r0 = records[3 * (size_t)id]; r1 = records[3 * (size_t)id + 1]; }
-    while (big) {
-        uint32_t pos[EMIT_KB];
-        uint2 val[EMIT_KB];
-        bool ok[EMIT_KB];
-#pragma unroll
-        for (int r = 0; r < EMIT_KB; r++) {
-            ok[r] = false;
-            if (big) {  // warp-uniform
-                const int src = __ffs(big) - 1;
-                big &= big - 1;
-                const int bx0 = __shfl_sync(GSR_FULL, x0, src), by0 = __shfl_sync(GSR_FULL, y0, src);
-                const int bw = __shfl_sync(GSR_FULL, w, src), bn = __shfl_sync(GSR_FULL, cnt, src);
-                val[r] = make_uint2(__shfl_sync(GSR_FULL, id, src), __shfl_sync(GSR_FULL, dbits, src));
-                float4 q0 = r0, q1 = r1;
-                if (TIGHT) {
-                    q0.x = __shfl_sync(GSR_FULL, r0.x, src); q0.y = __shfl_sync(GSR_FULL, r0.y, src); q0.z = __shfl_sync(GSR_FULL, r0.z, src);
-                    q0.w = __shfl_sync(GSR_FULL, r0.w, src); q1.x = __shfl_sync(GSR_FULL, r1.x, src); q1.w = __shfl_sync(GSR_FULL, r1.w, src);
-                }
-                for (int t = lane; t < bn; t += 32) {
-                    const int ty = by0 + t / bw, tx = bx0 + t % bw;
-                    if (!TIGHT || tile_may_touch(q0.x, q0.y, q0.z, q0.w, q1.x, q1.w, tx, ty)) {
-                        const uint32_t ps = atomicAdd(&tile_fill[ty * gx + tx], 1u);
-                        if (t < 32) { pos[r] = ps; ok[r] = true; }   // the first 32 tiles stay in flight
-                        else pairs[ps] = val[r];                      // rectangles of more than 32 tiles: rare
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < EMIT_KB; r++)
-            if (ok[r]) pairs[pos[r]] = val[r];
+    const bool big = cnt > 8;
+    if (TIGHT) {
+        const uint32_t pay[8] = {(uint32_t)idx, dbits, __float_as_uint(r0.x), __float_as_uint(r0.y), __float_as_uint(r0.z),
+                                 __float_as_uint(r0.w), __float_as_uint(r1.x), __float_as_uint(r1.w)};
+        for_each_tile<0, 8>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, pay, [&](int tile, int tx, int ty, const uint32_t(&o)[8]) {
+            if (tile_may_touch(__uint_as_float(o[2]), __uint_as_float(o[3]), __uint_as_float(o[4]), __uint_as_float(o[5]),
+                               __uint_as_float(o[6]), __uint_as_float(o[7]), tx, ty))
+                pairs[atomicAdd(&tile_fill[tile], 1u)] = make_uint2(o[0], o[1]);
+        });
+    } else {
+        const uint32_t pay[2] = {(uint32_t)idx, dbits};
+        for_each_tile<0, 2>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, pay, [&](int tile, int, int, const uint32_t(&o)[2]) {
+            pairs[atomicAdd(&tile_fill[tile], 1u)] = make_uint2(o[0], o[1]);
+        });
     }
 }
 
@@ -1194,7 +1155,7 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     pp.view = f->viewmatrix; pp.proj = f->projmatrix; pp.campos = f->campos;
     pp.records = (float4*)(geo + gl.records); pp.cov3D = (float*)(geo + gl.cov3D); pp.clamped = (uint8_t*)(geo + gl.clamped);
     pp.radii = radii; pp.tile_count = (uint32_t*)(img + il.tile_count); pp.tile_big = (uint32_t*)(img + il.tile_big);
-    pp.ranks = (uint32_t*)(geo + gl.ranks); pp.block_vis = (uint32_t*)(geo + gl.block_vis); pp.counters = counters;
+    pp.ranks = (uint32_t*)(geo + gl.ranks); pp.counters = counters;
 
     if (f->colors_precomp) launch_pre<-1>(false, pp, st);
     else {
@@ -1215,15 +1176,12 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     prof_mark(2, st);
     if ((rc = check_launch("gsr_forward/tile_scan", debug, st))) return rc;
 
-    {
-        const int nblocks = (f->P + PRE_THREADS - 1) / PRE_THREADS;
-        const int grid = (nblocks + EMIT_THREADS / PRE_THREADS - 1) / (EMIT_THREADS / PRE_THREADS);
-        const uint4* vl = (const uint4*)pp.ranks;
-        uint32_t* tf = (uint32_t*)(img + il.tile_fill);
-        uint2* prs = (uint2*)(bin + bl.pairs);
-        if (pp.tight) k_emit<true><<<grid, EMIT_THREADS, 0, st>>>(nblocks, il.gx, pp.records, vl, pp.block_vis, ranges, tf, prs, counters);
-        else k_emit<false><<<grid, EMIT_THREADS, 0, st>>>(nblocks, il.gx, pp.records, vl, pp.block_vis, ranges, tf, prs, counters);
-    }
+    if (pp.tight)
+        k_emit<true><<<(f->P + 255) / 256, 256, 0, st>>>(f->P, il.gx, il.gy, radii, pp.records, pp.ranks, ranges, (uint32_t*)(img + il.tile_fill),
+                                                         (uint2*)(bin + bl.pairs), counters);
+    else
+        k_emit<false><<<(f->P + 255) / 256, 256, 0, st>>>(f->P, il.gx, il.gy, radii, pp.records, pp.ranks, ranges, (uint32_t*)(img + il.tile_fill),
+                                                          (uint2*)(bin + bl.pairs), counters);
     prof_mark(3, st);
     if ((rc = check_launch("gsr_forward/emit", debug, st))) return rc;
 

@@ -35,7 +35,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_workspace_size_queries():
     from autovfx_b200._lib import lib
     assert lib.gsr_geom_bytes(0) > 0
-    assert 3_000_000 * (48 + 48 + 24 + 1) <= lib.gsr_geom_bytes(3_000_000) < 3_000_000 * 122
+    assert 3_000_000 * (48 + 32 + 24 + 1) <= lib.gsr_geom_bytes(3_000_000) < 3_000_000 * 106
     assert lib.gsr_binning_bytes(1000) == 12 * 1000  # 12 B/instance (reference: 24 B + sort temp)
     assert lib.gsr_binning_capacity(lib.gsr_binning_bytes(12345)) == 12345
     a, b = lib.gsr_image_bytes(1920, 1080), lib.gsr_image_bytes(256, 256)
