@@ -63,27 +63,18 @@ __device__ __forceinline__ float reduce10(const float (&v)[10], int lane, int& v
 }
 
 constexpr int BWD_QCAP = 48;
-constexpr int BWD_ACC = 11;  // 10 gradients per staged splat (+1 pad: conflict-free flush)
-// dynamic shared memory of k_blend_backward: two staged batches (records + ids), two accumulator sets, the per-warp queues
-constexpr int BWD_REC_BYTES = 2 * BWD_THREADS * 48;
-constexpr int BWD_ID_BYTES = 2 * BWD_THREADS * 4;
-constexpr int BWD_ACC_BYTES = 2 * BWD_THREADS * BWD_ACC * 4;
-constexpr int BWD_Q_BYTES = (BWD_THREADS / 32) * BWD_QCAP * 48;
-constexpr int BWD_SMEM = BWD_REC_BYTES + BWD_ID_BYTES + BWD_ACC_BYTES + BWD_Q_BYTES;
 
-// One CTA per tile; batches of 256 entries of the tile's list are walked from the back, double-buffered: while batch b is
-// culled / replayed out of buffer b&1 (gradients accumulating in accumulator set b&1), the records of batch b-1 (gathered
-// into registers during batch b+1) are stored into the other buffer and the gather of batch b-2 is issued.  ONE barrier per
-// batch; the finished accumulator set is flushed to global memory after it, overlapping the next batch.
-__global__ void __launch_bounds__(BWD_THREADS, 3) k_blend_backward(
+// One CTA per tile; batches of the tile's list are walked from the back.
+__global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const float4* __restrict__ records, int W, int H, int gx,
     const float* __restrict__ bg, const float* __restrict__ accum_alphas, const uint32_t* __restrict__ n_contrib,
     const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dpixel_alphas,
     float* __restrict__ dL_dmean2D /*[P,3]*/, float* __restrict__ dL_dconic /*[P,4]*/, float* __restrict__ dL_dopacity,
     float* __restrict__ dL_dcolors /*[P,3]*/, float* __restrict__ dL_ddepths) {
-    extern __shared__ __align__(16) unsigned char bsm[];
-    uint32_t* sId = reinterpret_cast<uint32_t*>(bsm + BWD_REC_BYTES);                     // [2][256]
-    float* acc = reinterpret_cast<float*>(bsm + BWD_REC_BYTES + BWD_ID_BYTES);            // [2][256][11]
+    __shared__ __align__(16) float4 sRec[BWD_THREADS * 3];                    // staged batch, 48 B per splat
+    __shared__ __align__(16) float4 sQ[(BWD_THREADS / 32) * BWD_QCAP * 3];    // per-warp survivor queues (back to front)
+    __shared__ uint32_t sId[BWD_THREADS];
+    __shared__ float acc[BWD_THREADS][11];  // 10 gradients per staged splat (+1 pad: conflict-free flush)
     __shared__ uint32_t s_wl[BWD_THREADS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -94,8 +85,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 3) k_blend_backward(
     const float pixx = (float)pxi, pixy = (float)pyi;
     const float fcx = (float)X0 + FOOT_HX, fcy = (float)Y0 + FOOT_HY;
     const size_t pid = (size_t)W * pyi + pxi, HW = (size_t)H * W;
-    const uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(bsm);
-    const uint32_t q_base = rec_base + BWD_REC_BYTES + BWD_ID_BYTES + BWD_ACC_BYTES + (uint32_t)warp * (BWD_QCAP * 48);
+    const uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(sRec);
+    const uint32_t q_base = (uint32_t)__cvta_generic_to_shared(sQ) + (uint32_t)warp * (BWD_QCAP * 48);
     const unsigned gt_mask = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
 
     const uint2 range = ranges[tile];
@@ -115,16 +106,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 3) k_blend_backward(
     float last_alpha = 0, last_c0 = 0, last_c1 = 0, last_c2 = 0, last_depth = 0;
     const float ddelx_dx = 0.5 * W, ddely_dy = 0.5 * H;  // backward.cu:488-489
     const float bg_dot_dpixel = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
-    const bool has_bg = bg[0] != 0.0f || bg[1] != 0.0f || bg[2] != 0.0f;  // CTA-uniform: the background term (backward.cu:571-574) is
-                                                                          // exactly -0 for a black background and its division is skipped
 
     // entries with 1-based position > the warp's furthest contributor are skipped by every lane
     uint32_t warp_last = last_contributor;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(GSR_FULL, warp_last, o));
     if (lane == 0) s_wl[warp] = warp_last;
-#pragma unroll
-    for (int k = 0; k < 2 * BWD_ACC; k++) acc[k * BWD_THREADS + tid] = 0.f;  // both accumulator sets
     __syncthreads();
     uint32_t tile_last = 0;
 #pragma unroll
@@ -135,7 +122,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 3) k_blend_backward(
     // replay the queued splats (back to front) for this lane's pixel: backward.cu:494-597
     auto drain = [&](int batch) {
         __syncwarp();
-        float* accb = acc + (batch & 1) * (BWD_THREADS * BWD_ACC);
         uint32_t qa = q_base;
         for (int k = 0; k < qn; k++, qa += 48) {
             const float4 A = lds128b(qa), B = lds128b(qa + 16), Cc = lds128b(qa + 32);
@@ -150,33 +136,31 @@ __global__ void __launch_bounds__(BWD_THREADS, 3) k_blend_backward(
                     const float alpha = min(0.99f, B.y * G);
                     if (!(alpha < 1.0f / 255.0f)) {
                         contrib = true;
-                        const float om = 1.f - alpha;
-                        T = T / om;
+                        T = T / (1.f - alpha);
                         const float dchannel_dcolor = alpha * T;
-                        const float la = last_alpha, ola = 1.f - last_alpha;
                         float dL_dalpha = 0.0f;
-                        accum_rec0 = la * last_c0 + ola * accum_rec0;
+                        accum_rec0 = last_alpha * last_c0 + (1.f - last_alpha) * accum_rec0;
                         last_c0 = Cc.x;
                         dL_dalpha += (Cc.x - accum_rec0) * dLp0;
                         g[0] = dchannel_dcolor * dLp0;
-                        accum_rec1 = la * last_c1 + ola * accum_rec1;
+                        accum_rec1 = last_alpha * last_c1 + (1.f - last_alpha) * accum_rec1;
                         last_c1 = Cc.y;
                         dL_dalpha += (Cc.y - accum_rec1) * dLp1;
                         g[1] = dchannel_dcolor * dLp1;
-                        accum_rec2 = la * last_c2 + ola * accum_rec2;
+                        accum_rec2 = last_alpha * last_c2 + (1.f - last_alpha) * accum_rec2;
                         last_c2 = Cc.z;
                         dL_dalpha += (Cc.z - accum_rec2) * dLp2;
                         g[2] = dchannel_dcolor * dLp2;
                         const float dep = B.z;
-                        accum_red = la * last_depth + ola * accum_red;
+                        accum_red = last_alpha * last_depth + (1.f - last_alpha) * accum_red;
                         last_depth = dep;
                         dL_dalpha += (dep - accum_red) * dLd;
                         g[3] = dchannel_dcolor * dLd;
-                        accum_rea = la + ola * accum_rea;
+                        accum_rea = last_alpha + (1.f - last_alpha) * accum_rea;
                         dL_dalpha += (1 - accum_rea) * dLa;
                         dL_dalpha *= T;
                         last_alpha = alpha;
-                        if (has_bg) dL_dalpha += (-T_final / om) * bg_dot_dpixel;
+                        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
                         const float dL_dG = B.y * dL_dalpha;
                         const float gdx = G * d.x, gdy = G * d.y;
                         const float dG_ddelx = -gdx * A.z - gdy * A.w;
@@ -194,43 +178,33 @@ __global__ void __launch_bounds__(BWD_THREADS, 3) k_blend_backward(
                 int vid;
                 bool valid;
                 const float z = reduce10(g, lane, vid, valid);
-                if (valid) atomicAdd(&accb[((int)pos - 1 - batch * BWD_THREADS) * BWD_ACC + vid], z);
+                if (valid) atomicAdd(&acc[(int)pos - 1 - batch * BWD_THREADS][vid], z);
             }
         }
         qn = 0;
         __syncwarp();
     };
 
-    float4 ra = make_float4(0, 0, 0, 0), rb = ra, rc = ra;
-    uint32_t rid = 0;
-    auto gather = [&](int batch) {  // list entry (batch, tid) -> registers
-        if (batch >= 0 && batch * BWD_THREADS + tid < n) {
-            rid = point_list[range.x + batch * BWD_THREADS + tid];
-            const float4* r = records + 3 * (size_t)rid;
-            ra = r[0]; rb = r[1]; rc = r[2];
-            rc.w = __uint_as_float((uint32_t)(batch * BWD_THREADS + tid + 1));
-        }
-    };
-    auto stage = [&](int batch) {  // registers -> buffer batch&1
-        if (batch >= 0 && batch * BWD_THREADS + tid < n) {
-            const uint32_t sa = rec_base + (uint32_t)((batch & 1) * BWD_THREADS + tid) * 48;
-            sts128b(sa, ra); sts128b(sa + 16, rb); sts128b(sa + 32, rc);
-            sId[(batch & 1) * BWD_THREADS + tid] = rid;
-        }
-    };
-    const int b_hi = (int)((tile_last - 1) / BWD_THREADS);
-    gather(b_hi);
-    stage(b_hi);
-    gather(b_hi - 1);
-    __syncthreads();
-
-    for (int b = b_hi; b >= 0; b--) {
+    for (int b = (int)((tile_last - 1) / BWD_THREADS); b >= 0; b--) {
         const int cnt = min(BWD_THREADS, n - b * BWD_THREADS);
-        const uint32_t buf = rec_base + (uint32_t)((b & 1) * BWD_THREADS) * 48;
+        __syncthreads();  // previous batch fully flushed
+        if (tid < cnt) {
+            const uint32_t id = point_list[range.x + b * BWD_THREADS + tid];
+            const float4* r = records + 3 * (size_t)id;
+            float4 rc = r[2];
+            rc.w = __uint_as_float((uint32_t)(b * BWD_THREADS + tid + 1));
+            const uint32_t sa = rec_base + (uint32_t)tid * 48;
+            sts128b(sa, r[0]); sts128b(sa + 16, r[1]); sts128b(sa + 32, rc);
+            sId[tid] = id;
+        }
+#pragma unroll
+        for (int k = 0; k < 11; k++) acc[tid][k] = 0.f;
+        __syncthreads();
+
         if ((uint32_t)(b * BWD_THREADS) < warp_last) {
             for (int base = ((cnt - 1) / 32) * 32; base >= 0; base -= 32) {
                 const int s = base + lane;
-                const uint32_t sa = buf + (uint32_t)s * 48;
+                const uint32_t sa = rec_base + (uint32_t)s * 48;
                 bool keep = false;
                 float4 A, B;
                 if (s < cnt && (uint32_t)(b * BWD_THREADS + s + 1) <= warp_last) {
@@ -249,12 +223,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 3) k_blend_backward(
             }
             if (qn) drain(b);
         }
-        stage(b - 1);
-        gather(b - 2);
-        __syncthreads();  // accumulator set b&1 is complete; buffer (b-1)&1 is staged; buffer b&1 may be overwritten
-        if (tid < cnt) {  // flush this batch's sums (one global atomic per (tile, Gaussian, component)) and re-arm the set
-            float* a = acc + (b & 1) * (BWD_THREADS * BWD_ACC) + tid * BWD_ACC;
-            const uint32_t id = sId[(b & 1) * BWD_THREADS + tid];
+        __syncthreads();
+        if (tid < cnt) {
+            const float* a = acc[tid];
+            const uint32_t id = sId[tid];
             if (a[0] != 0.f) atomicAdd(&dL_dcolors[3 * (size_t)id + 0], a[0]);
             if (a[1] != 0.f) atomicAdd(&dL_dcolors[3 * (size_t)id + 1], a[1]);
             if (a[2] != 0.f) atomicAdd(&dL_dcolors[3 * (size_t)id + 2], a[2]);
@@ -265,8 +237,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 3) k_blend_backward(
             if (a[7] != 0.f) atomicAdd(&dL_dconic[4 * (size_t)id + 1], a[7]);
             if (a[8] != 0.f) atomicAdd(&dL_dconic[4 * (size_t)id + 3], a[8]);
             if (a[9] != 0.f) atomicAdd(&dL_dopacity[id], a[9]);
-#pragma unroll
-            for (int k = 0; k < 10; k++) a[k] = 0.f;
         }
     }
 }
@@ -571,16 +541,7 @@ int backward_impl(const gsr_frame* f, const gsr_workspace* ws, const int32_t* ra
     char* img = (char*)ws->image; char* geo = (char*)ws->geom; char* bin = (char*)ws->binning;
     const int D = f->D < 0 ? 0 : (f->D > 3 ? 3 : f->D);
 
-    {
-        static bool configured[64] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev >= 0 && dev < 64 && !configured[dev]) {
-            cudaFuncSetAttribute(k_blend_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-            configured[dev] = true;
-        }
-    }
-    k_blend_backward<<<dim3(il.gx, il.gy), BWD_THREADS, BWD_SMEM, st>>>(
+    k_blend_backward<<<dim3(il.gx, il.gy), BWD_THREADS, 0, st>>>(
         (const uint2*)(img + il.ranges), (const uint32_t*)(bin + bl.point_list), (const float4*)(geo + gl.records), f->W, f->H, il.gx, f->bg,
         out_alpha, (const uint32_t*)(img + il.n_contrib), dL_dc, dL_dd, dL_da, g->dL_dmeans2D, g->dL_dconic, g->dL_dopacity, g->dL_dcolors,
         g->dL_ddepths);
