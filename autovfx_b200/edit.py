@@ -67,8 +67,9 @@ def make_xform(center, rotation, scaling: float, initial_center) -> _lib.gsr_obj
 
 def _raw_on(raw: Mapping[str, torch.Tensor], device) -> Dict[str, torch.Tensor]:
     out = {}
+    alias = {"scaling": "scale", "rotation": "rot"}  # scene.load_ply's names
     for k in RAW_KEYS:
-        t = torch.as_tensor(raw[k])
+        t = torch.as_tensor(raw[k] if k in raw else raw[alias[k]])
         out[k] = t.to(device=device, dtype=torch.float32).contiguous()
     N = out["xyz"].shape[0]
     if out["f_dc"].numel() != N * 3 or out["opacity"].numel() != N or out["scaling"].shape != (N, 3) or out["rotation"].shape != (N, 4):
@@ -111,6 +112,8 @@ def activate_into(raw: Mapping[str, torch.Tensor], dst: Mapping[str, torch.Tenso
                                        at(dst["opacities"], 1), at(dst["scales"], 3), at(dst["rotations"], 4),
                                        C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
         _lib.check(rc, "gsr_activate_gaussians")
+    from . import rasterizer as _R  # the arrays changed behind the version counters the geometry-reuse cache watches
+    _R.invalidate_geometry_cache(device)
     return N
 
 

@@ -32,7 +32,8 @@ from ._lib import lib as _L
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "set_sync_mode", "get_sync_mode",
            "set_tight_tiles", "get_tight_tiles", "set_geometry_reuse",
-           "last_frame_stats", "FrameTicket", "forward_raw", "forward_multi", "debug_views"]
+           "last_frame_stats", "FrameTicket", "forward_raw", "forward_multi", "debug_views",
+           "invalidate_geometry_cache"]
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -172,6 +173,20 @@ def _state(device: torch.device) -> _DeviceState:
         st = _DeviceState(torch.device("cuda", idx))
         _STATES[idx] = st
     return st
+
+
+def invalidate_geometry_cache(device=None) -> None:
+    """Forget which geometry the cached workspaces hold.  Called by code that rewrites parameter tensors in place through
+    raw pointers (``edit.activate_into``): such writes do not bump the tensors' version counters, which the automatic
+    second-pass reuse (``set_geometry_reuse``) relies on."""
+    if device is None:
+        for st in _STATES.values():
+            st.geom_cache.clear()
+        return
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx in _STATES:
+        _STATES[idx].geom_cache.clear()
 
 
 def last_ticket(device=None) -> Optional[FrameTicket]:

@@ -167,7 +167,8 @@ class FrameLoop:
         self.cam_dev[slot].copy_(self.cam_pinned[slot], non_blocking=True)
         f = self.frames[slot]
         g = self.g
-        out = (f[0:3], f[3:4], f[4:5], self.radii[slot])
+        P = g["means3D"].shape[0]
+        out = (f[0:3], f[3:4], f[4:5], self.radii[slot][:P])
         tfx, tfy = float(cam_row[35]), float(cam_row[36])
         st = self._settings(slot, tfx, tfy)
         if not self.product:
@@ -176,8 +177,9 @@ class FrameLoop:
             return res[5]  # ticket
         RD = self._RD
         cam = self.cam_dev[slot]
-        RD.axis_normals(g["means3D"], g["scales"], g["rotations"], cam[32:35], remap01=True, out=self.normals)
-        res = self._R.forward_multi(g["means3D"], g["shs"], None, self.normals, g["opacities"], g["scales"], g["rotations"], None, st, sync=sync,
+        normals = self.normals[:P]
+        RD.axis_normals(g["means3D"], g["scales"], g["rotations"], cam[32:35], remap01=True, out=normals)
+        res = self._R.forward_multi(g["means3D"], g["shs"], None, normals, g["opacities"], g["scales"], g["rotations"], None, st, sync=sync,
                                     out=out, extra_out=self.extra[slot], tight=self.tight_tiles)
         c2w = torch.linalg.inv_ex(cam[0:16].view(4, 4))[0]  # the reference's world_view_transform.inverse(), no host sync
         n_out, p_out = self.nmaps[slot]
@@ -195,10 +197,26 @@ class FrameLoop:
         src = self.host[slot] if self.to_host else self.outputs[slot]
         return src["frame"] if not self.product else src
 
-    def render(self, packed_cams: torch.Tensor, consume: Optional[Callable] = None) -> List[Dict[str, int]]:
+    def set_gaussians(self, gaussians: Dict[str, torch.Tensor]) -> None:
+        """Swap the (activated) parameter tensors the next frames read — e.g. the views ``edit.ResidentScene.compose`` returns
+        for this frame.  The tensors must live on this loop's device; kernels run in stream order, so frames already issued
+        are not affected as long as the caller's edits are issued on the same stream (``compose`` is)."""
+        P_old = self.g["means3D"].shape[0]
+        self.g = {k: v for k, v in gaussians.items()}
+        P = self.g["means3D"].shape[0]
+        if P > self.radii[0].shape[0]:
+            self.radii = [torch.empty((P,), dtype=torch.int32, device=self.device) for _ in range(self.ring)]
+            if self.product:
+                self.normals = torch.empty((P, 3), dtype=torch.float32, device=self.device)
+        del P_old
+
+    def render(self, packed_cams: torch.Tensor, consume: Optional[Callable] = None,
+               before_frame: Optional[Callable[[int], Optional[Dict[str, torch.Tensor]]]] = None) -> List[Dict[str, int]]:
         """Render every row of ``packed_cams`` ([N,37] host tensor).  ``consume(i, frame, stats)`` receives the finished
         frame (pinned host memory if ``to_host`` else the device ring slot; a ``[5,H,W]`` tensor, or the dict described in
-        the class docstring when ``product``) — valid until ``ring-1`` further frames have been issued.  Returns the
+        the class docstring when ``product``) — valid until ``ring-1`` further frames have been issued.
+        ``before_frame(i)`` runs before frame ``i`` is issued and may return the Gaussians of that frame (per-frame object
+        edits: ``lambda i: resident_scene.compose(transforms[i])``; reference scene_representation.py:357-371).  Returns the
         per-frame statistics."""
         n = packed_cams.shape[0]
         stats: List[Optional[Dict[str, int]]] = [None] * n
@@ -209,6 +227,10 @@ class FrameLoop:
             i, slot, ticket, ev = entry
             if not ticket.ok():  # binning overflow: re-render this frame synchronously with the grown capacity
                 self.rerendered += 1
+                if before_frame is not None:  # later frames may have edited the resident arrays: restore frame i's scene first
+                    g_i = before_frame(i)
+                    if g_i is not None:
+                        self.set_gaussians(g_i)
                 ticket = self._issue(slot, packed_cams[i], sync=True)
                 if self.to_host:
                     self._copy_out(slot)
@@ -223,6 +245,10 @@ class FrameLoop:
             slot = i % self.ring
             if len(inflight) == self.ring:
                 retire(inflight.pop(0))  # frees this slot (device frame + pinned frame)
+            if before_frame is not None:
+                g_i = before_frame(i)
+                if g_i is not None:
+                    self.set_gaussians(g_i)
             ticket = self._issue(slot, packed_cams[i], sync=False)
             ev = None
             if self.to_host:

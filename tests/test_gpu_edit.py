@@ -107,3 +107,30 @@ def test_edit_errors():
         edit.ResidentScene(raw, {"A": _to(_raw(10, 9, 7))}, DEV)  # SH storage mismatch
     with pytest.raises(RuntimeError):
         edit.activate_into({k: v.cpu() for k, v in raw.items()}, {k: v.cpu() for k, v in rs.arrays.items()})
+
+
+def test_frame_loop_with_per_frame_edits():
+    """FrameLoop.render(before_frame=compose): every frame shows the scene with that frame's object transform; equals rendering
+    the composed tensors directly."""
+    from autovfx_b200 import edit, scene
+    from autovfx_b200 import rasterizer as R
+    from autovfx_b200.render_loop import FrameLoop, pack_cameras
+    from tests.helpers import settings_from
+    scene_raw, obj = _to(_raw(8_000, 16, 11)), _to(_raw(2_000, 16, 12))
+    for r in (scene_raw, obj):
+        r["scaling"] = r["scaling"] - 1.0
+    rs = edit.ResidentScene(scene_raw, {"A": obj}, DEV)
+    cams = scene.cameras_from_trajectory(scene.trajectory_dict(radius=4.5, num_views=4, theta=25.0, w=128, h=96))
+    tfs = [{"A": (torch.tensor([0.3 * i, 0.0, 0.1]), _rot(i), 1.0 + 0.2 * i, torch.zeros(3))} if i != 2 else {} for i in range(4)]
+    loop = FrameLoop(rs.compose({}), 0, 128, 96, device=DEV, ring=2, to_host=True)
+    got = {}
+    loop.render(pack_cameras(cams), lambda i, fr, st: got.__setitem__(i, fr.clone()), before_frame=lambda i: rs.compose(tfs[i]))
+    for i, cam in enumerate(cams):
+        g = rs.compose(tfs[i])
+        a = dict(view=cam.world_view_transform.to(DEV), proj=cam.full_proj_transform.to(DEV), campos=cam.camera_center.to(DEV), W=128, H=96,
+                 tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, sh_degree=0, scale_modifier=1.0, bg=torch.zeros(3, device=DEV))
+        color, depth, alpha, radii, _w, _t, _k = R.forward_raw(g["means3D"], g["shs"], None, g["opacities"], g["scales"], g["rotations"], None,
+                                                               settings_from(a), sync=True)
+        assert g["means3D"].shape[0] == (8_000 if i == 2 else 10_000)
+        fr = got[i].to(DEV)
+        assert torch.equal(fr[0:3], color) and torch.equal(fr[3:4], depth) and torch.equal(fr[4:5], alpha), i
