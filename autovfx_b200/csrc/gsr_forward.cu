@@ -63,11 +63,11 @@ struct PreParams {
 constexpr int PRE_THREADS = 128;
 
 __host__ __device__ constexpr int sh_nf(int deg) { return 3 * (deg + 1) * (deg + 1); }
-__host__ __device__ constexpr int sh_stride(int deg, bool vec) {
+__host__ __device__ constexpr int sh_nv(int deg, bool win) { return (sh_nf(deg) + 3) / 4 + (win ? 1 : 0); }  // float4 per staged row
+__host__ __device__ constexpr int sh_stride(int deg, bool vec, bool win = false) {
     // vec: rows of nv float4, padded so that (stride/4) is odd -> conflict-free LDS.128 across 8 lanes
     // scalar: odd number of words -> conflict-free LDS.32
-    return vec ? (((sh_nf(deg) + 3) / 4) % 2 == 0 ? ((sh_nf(deg) + 3) / 4 + 1) * 4 : ((sh_nf(deg) + 3) / 4) * 4)
-               : (sh_nf(deg) | 1);
+    return vec ? (sh_nv(deg, win) % 2 == 0 ? (sh_nv(deg, win) + 1) * 4 : sh_nv(deg, win) * 4) : (sh_nf(deg) | 1);
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -187,12 +187,14 @@ __device__ __forceinline__ void cov3d_ref_rounding(float sx, float sy, float sz,
 }
 
 // DEG = -1: colours are precomputed.  VEC: SH rows are 16-byte aligned (M % 4 == 0) -> 16-byte staging, either one TMA
-// bulk copy per visible Gaussian issued by its own lane (BULK) or coalesced cp.async by the whole warp.
-template <int DEG, bool VEC, bool BULK>
+// bulk copy per visible Gaussian issued by its own lane (BULK) or coalesced cp.async by the whole warp.  WIN (with VEC and
+// BULK): rows are only 4-byte aligned (M = 25, the SuGaR storage: 300-byte rows) — each lane bulk-copies the 16-byte aligned
+// window that contains its coefficients (one extra float4) and evaluates from its row's offset inside the window.
+template <int DEG, bool VEC, bool BULK, bool WIN = false>
 __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
     constexpr int DG = DEG < 0 ? 0 : DEG;
     constexpr int NF = sh_nf(DG);
-    constexpr int STRIDE = sh_stride(DG, VEC);
+    constexpr int STRIDE = sh_stride(DG, VEC, WIN);
     __shared__ CamConsts cam;
     __shared__ __align__(16) float stage[DEG < 0 ? 4 : PRE_THREADS * STRIDE];
     __shared__ __align__(8) unsigned long long stage_bar[PRE_THREADS / 32];
@@ -328,12 +330,20 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
         float* wstage = stage + warp * 32 * STRIDE;
         const size_t gbase = (size_t)(blockIdx.x * PRE_THREADS + warp * 32);
         const size_t row_floats = (size_t)p.M * 3;
+        int win_off = 0;  // floats between the start of the staged window and the row's first coefficient (WIN only)
         if (VEC && BULK) {
-            constexpr int NV = (NF + 3) / 4;
+            constexpr int NV = sh_nv(DG, WIN);
             const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar[warp]);
             if (vismask) {
                 if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)__popc(vismask) * NV * 16u);
-                if (vis) bulk_g2s((uint32_t)__cvta_generic_to_shared(wstage + lane * STRIDE), p.shs + (gbase + lane) * row_floats, NV * 16u, bar);
+                if (vis) {
+                    const float* src = p.shs + (gbase + lane) * row_floats;
+                    if (WIN) {
+                        win_off = (int)(((uintptr_t)src & 15u) >> 2);
+                        src -= win_off;
+                    }
+                    bulk_g2s((uint32_t)__cvta_generic_to_shared(wstage + lane * STRIDE), src, NV * 16u, bar);
+                }
                 mbar_wait(bar, 0u);
             }
         } else if (VEC) {
@@ -354,7 +364,7 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
             }
         }
         __syncwarp();
-        if (vis) sh_eval<DG>(wstage + lane * STRIDE, mean, cam.campos, rgb, clamp_bits);
+        if (vis) sh_eval<DG>(wstage + lane * STRIDE + win_off, mean, cam.campos, rgb, clamp_bits);
     }
 
     if (valid) {
@@ -1051,9 +1061,10 @@ static int sh_bulk_mode() {  // GSR_SH_STAGING=cpasync selects the LDGSTS path, 
     return mode;
 }
 template <int DEG>
-static void launch_pre(bool vec, const PreParams& pp, cudaStream_t st) {
+static void launch_pre(bool vec, bool win, const PreParams& pp, cudaStream_t st) {
     const int grid = (pp.P + PRE_THREADS - 1) / PRE_THREADS;
-    if (vec && sh_bulk_mode()) k_preprocess<DEG, true, true><<<grid, PRE_THREADS, 0, st>>>(pp);
+    if (win && sh_bulk_mode()) k_preprocess<DEG, true, true, true><<<grid, PRE_THREADS, 0, st>>>(pp);
+    else if (vec && sh_bulk_mode()) k_preprocess<DEG, true, true><<<grid, PRE_THREADS, 0, st>>>(pp);
     else if (vec) k_preprocess<DEG, true, false><<<grid, PRE_THREADS, 0, st>>>(pp);
     else k_preprocess<DEG, false, false><<<grid, PRE_THREADS, 0, st>>>(pp);
 }
@@ -1157,14 +1168,16 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     pp.radii = radii; pp.tile_count = (uint32_t*)(img + il.tile_count); pp.tile_big = (uint32_t*)(img + il.tile_big);
     pp.ranks = (uint32_t*)(geo + gl.ranks); pp.counters = counters;
 
-    if (f->colors_precomp) launch_pre<-1>(false, pp, st);
+    if (f->colors_precomp) launch_pre<-1>(false, false, pp, st);
     else {
         const bool vec = (f->M % 4 == 0) && (((uintptr_t)f->shs & 15) == 0);
+        // 4-byte aligned rows (e.g. M = 25): the aligned window of sh_nv(D, true) float4 must fit inside every row
+        const bool win = !vec && (((uintptr_t)f->shs & 15) == 0) && (size_t)f->M * 12 >= (size_t)sh_nv(D, true) * 16;
         switch (D) {
-            case 0: launch_pre<0>(vec, pp, st); break;
-            case 1: launch_pre<1>(vec, pp, st); break;
-            case 2: launch_pre<2>(vec, pp, st); break;
-            default: launch_pre<3>(vec, pp, st); break;
+            case 0: launch_pre<0>(vec, win, pp, st); break;
+            case 1: launch_pre<1>(vec, win, pp, st); break;
+            case 2: launch_pre<2>(vec, win, pp, st); break;
+            default: launch_pre<3>(vec, win, pp, st); break;
         }
     }
     prof_mark(1, st);

@@ -54,7 +54,7 @@ def test_oracle_backward_matches_autograd():
     assert np.all(og["dL_dmeans2D"][:, 2] == 0)
 
 
-@pytest.mark.parametrize("name", ["config1", "small_sh", "small_deg1_m25", "small_precomp", "big_splats", "dense_tile", "coplanar"])
+@pytest.mark.parametrize("name", ["config1", "small_sh", "small_deg1_m25", "deg3_m25", "deg2_m25", "small_precomp", "big_splats", "dense_tile", "coplanar"])
 def test_oracle_binning_invariants(name):
     a = Hh.resolve(Hh.case_inputs(name))
     fw = Hh.run_oracle(a, stop_after="binning")
