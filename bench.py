@@ -118,6 +118,18 @@ def algorithmic_bytes(P, P_vis, R, M_used=16):
     return {"preprocess": pre, "binning": binning, "blend": blend, "frame": pre + binning + blend}
 
 
+_RESULT_FD = None
+
+
+def emit_result(line) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -127,6 +139,12 @@ def main():
     ap.add_argument("--gaussians", type=int, default=3_000_000, help="override only for debugging; the metric is quoted at 3M")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: everything else that writes to file descriptor 1 (NCCL's version
+    # banner, library chatter) is sent to stderr for the duration of the run
+    sys.stdout.flush()
+    global _RESULT_FD
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     K, Wm = args.steps, max(args.warmup, 3)
     rank, world, local = dist_setup()
 
@@ -197,7 +215,7 @@ def main():
                     "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload},
                     "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": "1 frame (camera 0), CPU oracle"},
                     "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-            print(json.dumps(line))
+            emit_result(line)
             return 0
 
         def ref_frame(s):
@@ -228,7 +246,7 @@ def main():
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference",
                                  "sample": "%d frames; the reference path is CUDA, driven by 1 host thread incl. its per-frame blocking D2H" % K},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit_result(line)
         return 0
 
     # =================================================================================== our arm
@@ -431,7 +449,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * K * world, "roofline": roofline, "tight_tiles": tight_info, "product_frame": product_info}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line))
+        emit_result(line)
     if use_dist:
         import torch.distributed as dist
         dist.destroy_process_group()
