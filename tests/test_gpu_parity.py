@@ -396,3 +396,84 @@ def test_geometry_reuse_second_pass_is_bit_identical_to_a_full_forward(dev):
         R.set_geometry_reuse(True)
         for x, y in zip(third, want):
             assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("W,H", [(1, 1), (16, 16), (17, 1), (33, 47)])
+def test_degenerate_image_sizes_match_reference(dev, W, H):
+    """Tile grids of 1x1, exact multiples and ragged edges; the same inputs through the compiled reference."""
+    case = Hh.case_inputs("small_sh")
+    case["cam"] = scene.lookat_camera((0.3, -3.0, 0.4), (0, 0, 0), W, H, 55.0)
+    a = Hh.resolve(case, dev)
+    ours = Hh.run_ours(a, for_backward=True)
+    ref = Hh.run_ref(a)
+    for k in ("color", "depth", "alpha", "radii"):
+        assert torch.equal(ours[k], ref[k]), k
+    dc, dd, da = Hh.image_grads(a, device=dev)
+    _, g = Hh.ours_backward(a, dc, dd, da)
+    assert all(torch.isfinite(v).all() for v in g.values() if v is not None)
+
+
+def test_everything_behind_the_camera(dev):
+    """No Gaussian survives the near cull: zero instances, background-only image, zero gradients, no kernel misbehaves."""
+    case = Hh.case_inputs("small_sh")
+    case["cam"] = scene.lookat_camera((0.0, -3.0, 0.0), (0.0, -6.0, 0.0), 64, 48, 55.0)  # looking away from the cloud
+    a = Hh.resolve(case, dev)
+    ours = Hh.run_ours(a, for_backward=True)
+    assert ours["stats"]["num_rendered"] == 0 and ours["stats"]["num_visible"] == 0
+    assert int(ours["radii"].abs().max()) == 0 and float(ours["alpha"].abs().max()) == 0.0
+    bg = a["bg"].view(3, 1, 1).expand(3, 48, 64)
+    assert torch.equal(ours["color"], bg.contiguous())
+    ref = Hh.run_ref(a)
+    assert torch.equal(ours["color"], ref["color"])
+    dc, dd, da = Hh.image_grads(a, device=dev)
+    _, g = Hh.ours_backward(a, dc, dd, da)
+    for k, v in g.items():
+        if v is not None:
+            assert float(v.abs().max()) == 0.0, k
+    from autovfx_b200 import rasterizer as R
+    extra = torch.rand(a["means3D"].shape[0], 3, device=dev)
+    res = R.forward_multi(a["means3D"], a["shs"], None, extra, a["opacities"], a["scales"], a["rotations"], None, Hh.settings_from(a), sync=True)
+    assert torch.equal(res[3], bg.contiguous())
+
+
+def test_c_abi_rejects_bad_arguments(dev):
+    """Status codes + gsr_last_error for the argument errors the reference raises from C++ (rasterize_points.cu:57-59,
+    rasterizer_impl.cu:243-246) and for undersized workspaces."""
+    import ctypes as C
+    from autovfx_b200 import _lib
+    L = _lib.lib
+    a = Hh.resolve(Hh.case_inputs("small_sh"), dev)
+    P, W, H = a["means3D"].shape[0], a["W"], a["H"]
+    buf = lambda n: torch.empty(int(n), dtype=torch.uint8, device=dev)  # noqa: E731
+    geom, binning, image = buf(L.gsr_geom_bytes(P)), buf(L.gsr_binning_bytes(1 << 16)), buf(L.gsr_image_bytes(W, H))
+    color, depth, alpha = (torch.empty((c, H, W), device=dev) for c in (3, 1, 1))
+    radii = torch.empty(P, dtype=torch.int32, device=dev)
+    p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+
+    def frame(**over):
+        fr = _lib.gsr_frame(P, 3, 16, W, H, 1.0, a["tanfovx"], a["tanfovy"], 0, 0, p(a["bg"]), p(a["means3D"]), p(a["shs"]), None, p(a["opacities"]),
+                            p(a["scales"]), p(a["rotations"]), None, p(a["view"]), p(a["proj"]), p(a["campos"]))
+        for k, v in over.items():
+            setattr(fr, k, v)
+        return fr
+
+    def call(fr, ws, out_color=color):
+        return L.gsr_forward(C.byref(fr), C.byref(ws), p(out_color), p(depth), p(alpha), p(radii), 0, None)
+    ws = _lib.gsr_workspace(p(geom), geom.numel(), p(binning), binning.numel(), p(image), image.numel())
+    assert call(frame(), ws) == 0
+    torch.cuda.synchronize()
+    assert call(frame(colors_precomp=p(a["means3D"])), ws) == -1 and b"exactly one" in L.gsr_last_error()          # both shs and colors
+    assert call(frame(shs=None), ws) == -1                                                                          # neither
+    assert call(frame(scales=None), ws) == -1                                                                       # rotations without scales
+    assert call(frame(D=3, M=4), ws) == -1 and b"coefficients" in L.gsr_last_error()                                # degree needs 16 coefficients
+    assert call(frame(W=0), ws) == -1
+    small = _lib.gsr_workspace(p(geom), 16, p(binning), binning.numel(), p(image), image.numel())
+    assert call(frame(), small) == -2 and b"geometry workspace" in L.gsr_last_error()
+    small = _lib.gsr_workspace(p(geom), geom.numel(), p(binning), binning.numel(), p(image), 64)
+    assert call(frame(), small) == -2
+    assert call(frame(), ws, out_color=None) == -1
+    assert L.gsr_forward_multi(C.byref(frame()), C.byref(ws), p(color), p(depth), p(alpha), p(radii), p(a["means3D"]), None, 0, None) == -1
+    assert L.gsr_axis_normals(P, None, None, None, None, 0, None, None) == -1
+    assert L.gsr_normal_maps(0, 4, None, None, None, 1.0, 1.0, 0.0, 0.0, None, None, None) == -1
+    assert L.gsr_pack_frame(4, 4, None, None, None, None, 3.0, p(color), None, None, None) == -1
+    assert L.gsr_activate_gaussians(4, 0, None, None, None, None, None, None, None, None, None, None, None, None, None) == -1
