@@ -395,13 +395,13 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
 // =====================================================================================================
 // Kernel 2: exclusive scan over the per-tile counts -> ranges, R, overflow flag (single CTA)
 // =====================================================================================================
-// Also orders the tiles by descending list length (a counting sort over 1024 length classes, longest first): k_sort_tiles
-// and k_blend take their tile from that order, so the longest lists start first and the tail of the grid is short work
-// (the per-tile outputs do not depend on the order).
+// Also orders the tiles by descending list length (a counting sort over 1024 length classes, longest first): k_blend takes
+// its tile from that order, so the longest lists start first and the tail of the grid is short work (the per-tile outputs do
+// not depend on the order; k_sort_tiles measured slower in that order and keeps the natural one).
 constexpr int ORDER_CLASSES = 1024;
 __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_big,
                                                     uint32_t* __restrict__ tile_fill, uint2* __restrict__ ranges, uint32_t* __restrict__ tile_order,
-                                                    gsr_counters* counters, int tiles, uint32_t capacity) {
+                                                    gsr_counters* counters, int tiles, uint32_t capacity, int longest_first) {
     __shared__ uint32_t warp_sum[32];
     __shared__ uint32_t warp_max[32];
     __shared__ uint32_t chunk_total;
@@ -436,6 +436,7 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
         if (t < tiles) {
             ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
             tile_fill[t] = start + cs;  // absolute cursor of the tile's un-ranked (large-rectangle) instances
+            if (!longest_first) tile_order[t] = (uint32_t)t;
         }
         carry += chunk_total;
         __syncthreads();
@@ -455,6 +456,7 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
             chunk_total = m;
         }
     }
+    if (!longest_first) return;
     // ---- launch order: class = ORDER_CLASSES-1 for the longest lists ... 0 for empty tiles; positions by descending class
     cls[tid] = 0;  // blockDim.x == ORDER_CLASSES
     __syncthreads();
@@ -751,13 +753,13 @@ __device__ void sort_tile(const uint2 rg, unsigned long long* __restrict__ pairs
 }
 
 // stand-alone per-tile sort kernel (fusing it into the blend prologue was measured and dropped, profiles/r01_experiments.md)
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __restrict__ ranges,
                                                              unsigned long long* __restrict__ pairs, uint32_t* __restrict__ point_list,
                                                              const gsr_counters* __restrict__ counters, int keep_pairs) {
     if (counters->overflow) return;
     __shared__ unsigned long long s[SORT_CAP];
     __shared__ uint32_t hist[SORT_BUCKETS + 1];
-    sort_tile(ranges[tile_order[blockIdx.x]], pairs, point_list, keep_pairs, s, hist);
+    sort_tile(ranges[blockIdx.x], pairs, point_list, keep_pairs, s, hist);
 }
 
 // =====================================================================================================
@@ -1097,6 +1099,14 @@ int profile_end(float* ms, int* frames) {
 // =====================================================================================================
 // host side
 // =====================================================================================================
+static int tile_order_mode() {  // GSR_TILE_ORDER=natural: blend tiles in row-major order instead of longest list first
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("GSR_TILE_ORDER");
+        mode = (e && strcmp(e, "natural") == 0) ? 0 : 1;
+    }
+    return mode;
+}
 static int sh_bulk_mode() {  // GSR_SH_STAGING=cpasync selects the LDGSTS path, default is the TMA bulk copy
     static int mode = -1;
     if (mode < 0) {
@@ -1231,7 +1241,7 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     if (rc) return rc;
 
     uint2* ranges = (uint2*)(img + il.ranges);
-    k_tile_scan<<<1, 1024, 0, st>>>(pp.tile_count, pp.tile_big, (uint32_t*)(img + il.tile_fill), ranges, (uint32_t*)(img + il.tile_order), counters, il.tiles, (uint32_t)(cap > 0xffffffffull ? 0xffffffffull : cap));
+    k_tile_scan<<<1, 1024, 0, st>>>(pp.tile_count, pp.tile_big, (uint32_t*)(img + il.tile_fill), ranges, (uint32_t*)(img + il.tile_order), counters, il.tiles, (uint32_t)(cap > 0xffffffffull ? 0xffffffffull : cap), tile_order_mode());
     prof_mark(2, st);
     if ((rc = check_launch("gsr_forward/tile_scan", debug, st))) return rc;
 
@@ -1246,7 +1256,7 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
 
     const int keep_pairs = (flags & GSR_FLAG_SORTED_KEYS) ? 1 : 0;
     uint32_t* n_contrib = (flags & GSR_FLAG_FOR_BACKWARD) ? (uint32_t*)(img + il.n_contrib) : nullptr;
-    k_sort_tiles<<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (const uint32_t*)(img + il.tile_order), (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters, keep_pairs);
+    k_sort_tiles<<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters, keep_pairs);
     prof_mark(4, st);
     if ((rc = check_launch("gsr_forward/sort", debug, st))) return rc;
     BlendArgs ba{ranges, (const uint32_t*)(bin + bl.point_list), (const uint32_t*)(img + il.tile_order), pp.records, extra_colors, f->W, f->H, il.gx, il.gy, f->bg,
