@@ -32,7 +32,7 @@ struct GeomLayout {
     }
 };
 struct ImageLayout {
-    size_t counters, tile_count, tile_big, tile_fill, ranges, tile_order, n_contrib, total;
+    size_t counters, tile_count, tile_big, tile_fill, ranges, n_contrib, total;
     int gx, gy, tiles;
     __host__ __device__ ImageLayout(int W, int H) {
         gx = (W + GSR_TILE - 1) / GSR_TILE;
@@ -44,7 +44,6 @@ struct ImageLayout {
         tile_big = o;   o = align_up(o + 4 * (size_t)tiles, 256);  // instances of Gaussians touching > 8 tiles
         tile_fill = o;  o = align_up(o + 4 * (size_t)tiles, 256);  // cursor for the latter, written by the scan
         ranges = o;     o = align_up(o + 8 * (size_t)tiles, 256);
-        tile_order = o; o = align_up(o + 4 * (size_t)tiles, 256);  // tiles by descending list length (launch order of sort / blend)
         n_contrib = o;  o = align_up(o + 4 * (size_t)W * H, 256);
         total = o + 256;
     }

@@ -395,17 +395,12 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
 // =====================================================================================================
 // Kernel 2: exclusive scan over the per-tile counts -> ranges, R, overflow flag (single CTA)
 // =====================================================================================================
-// Also orders the tiles by descending list length (a counting sort over 1024 length classes, longest first): k_blend takes
-// its tile from that order, so the longest lists start first and the tail of the grid is short work (the per-tile outputs do
-// not depend on the order; k_sort_tiles measured slower in that order and keeps the natural one).
-constexpr int ORDER_CLASSES = 1024;
 __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_big,
-                                                    uint32_t* __restrict__ tile_fill, uint2* __restrict__ ranges, uint32_t* __restrict__ tile_order,
-                                                    gsr_counters* counters, int tiles, uint32_t capacity, int longest_first) {
+                                                    uint32_t* __restrict__ tile_fill, uint2* __restrict__ ranges,
+                                                    gsr_counters* counters, int tiles, uint32_t capacity) {
     __shared__ uint32_t warp_sum[32];
     __shared__ uint32_t warp_max[32];
     __shared__ uint32_t chunk_total;
-    __shared__ uint32_t cls[ORDER_CLASSES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t carry = 0, lmax = 0;
     for (int base = 0; base < tiles; base += 1024) {  // chunks of 1024 consecutive tiles: coalesced loads and stores
@@ -436,7 +431,6 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
         if (t < tiles) {
             ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
             tile_fill[t] = start + cs;  // absolute cursor of the tile's un-ranked (large-rectangle) instances
-            if (!longest_first) tile_order[t] = (uint32_t)t;
         }
         carry += chunk_total;
         __syncthreads();
@@ -453,47 +447,7 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
             counters->num_rendered = carry;
             counters->overflow = carry > capacity ? 1u : 0u;
             counters->max_tile = m;
-            chunk_total = m;
         }
-    }
-    if (!longest_first) return;
-    // ---- launch order: class = ORDER_CLASSES-1 for the longest lists ... 0 for empty tiles; positions by descending class
-    cls[tid] = 0;  // blockDim.x == ORDER_CLASSES
-    __syncthreads();
-    const uint32_t mx = chunk_total;
-    const float scale = mx ? (float)(ORDER_CLASSES - 1) / (float)mx : 0.f;
-    for (int t = tid; t < tiles; t += 1024) {
-        const uint32_t c = tile_count[t] + tile_big[t];
-        atomicAdd(&cls[min((uint32_t)ORDER_CLASSES - 1, (uint32_t)((float)c * scale))], 1u);
-    }
-    __syncthreads();
-    {   // exclusive scan over the classes in DESCENDING class order: thread tid owns class ORDER_CLASSES-1-tid
-        const uint32_t mine = cls[ORDER_CLASSES - 1 - tid];
-        uint32_t incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(GSR_FULL, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) warp_sum[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t s = warp_sum[lane];
-            uint32_t si = s;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(GSR_FULL, si, o);
-                if (lane >= o) si += v;
-            }
-            warp_sum[lane] = si - s;
-        }
-        __syncthreads();
-        cls[ORDER_CLASSES - 1 - tid] = warp_sum[warp] + incl - mine;  // first slot of this class
-    }
-    __syncthreads();
-    for (int t = tid; t < tiles; t += 1024) {
-        const uint32_t c = tile_count[t] + tile_big[t];
-        tile_order[atomicAdd(&cls[min((uint32_t)ORDER_CLASSES - 1, (uint32_t)((float)c * scale))], 1u)] = (uint32_t)t;
     }
 }
 
@@ -753,8 +707,8 @@ __device__ void sort_tile(const uint2 rg, unsigned long long* __restrict__ pairs
 }
 
 // stand-alone per-tile sort kernel (fusing it into the blend prologue was measured and dropped, profiles/r01_experiments.md)
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __restrict__ ranges,
-                                                             unsigned long long* __restrict__ pairs, uint32_t* __restrict__ point_list,
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __restrict__ ranges, unsigned long long* __restrict__ pairs,
+                                                             uint32_t* __restrict__ point_list,
                                                              const gsr_counters* __restrict__ counters, int keep_pairs) {
     if (counters->overflow) return;
     __shared__ unsigned long long s[SORT_CAP];
@@ -831,8 +785,8 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
 // NC  : also record n_contrib (the 1-based list position of the last blended splat) for the backward pass.
 template <int NX, bool NC>
 __global__ void __launch_bounds__(BLEND_THREADS, NX ? 0 : 4) k_blend(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                                                         const uint32_t* __restrict__ tile_order, const float4* __restrict__ records,
-                                                         const float* __restrict__ extra, int W, int H, int gx, const float* __restrict__ bg,
+                                                         const float4* __restrict__ records, const float* __restrict__ extra,
+                                                         int W, int H, int gx, const float* __restrict__ bg,
                                                          float* __restrict__ out_color, float* __restrict__ out_depth,
                                                          float* __restrict__ out_alpha, float* __restrict__ out_extra,
                                                          uint32_t* __restrict__ n_contrib,
@@ -843,9 +797,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, NX ? 0 : 4) k_blend(const uint2
     float4* sRec = reinterpret_cast<float4*>(smem_raw);
     float4* sQ = reinterpret_cast<float4*>(smem_raw + Cfg::REC_BYTES + Cfg::XREC_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = (int)tile_order[blockIdx.x];
-    const int tile_x = tile % gx, tile_y = tile / gx;
-    const int X0 = tile_x * GSR_TILE + (warp & 1) * 8, Y0 = tile_y * GSR_TILE + (warp >> 1) * 4;
+    const int tile = blockIdx.y * gx + blockIdx.x;
+    const int X0 = blockIdx.x * GSR_TILE + (warp & 1) * 8, Y0 = blockIdx.y * GSR_TILE + (warp >> 1) * 4;
     const int pxi = X0 + (lane & 7), pyi = Y0 + (lane >> 3);
     const bool inside = pxi < W && pyi < H;
     const float pixx = (float)pxi, pixy = (float)pyi;
@@ -1099,14 +1052,6 @@ int profile_end(float* ms, int* frames) {
 // =====================================================================================================
 // host side
 // =====================================================================================================
-static int tile_order_mode() {  // GSR_TILE_ORDER=natural: blend tiles in row-major order instead of longest list first
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("GSR_TILE_ORDER");
-        mode = (e && strcmp(e, "natural") == 0) ? 0 : 1;
-    }
-    return mode;
-}
 static int sh_bulk_mode() {  // GSR_SH_STAGING=cpasync selects the LDGSTS path, default is the TMA bulk copy
     static int mode = -1;
     if (mode < 0) {
@@ -1125,7 +1070,7 @@ static void launch_pre(bool vec, bool win, const PreParams& pp, cudaStream_t st)
 }
 
 struct BlendArgs {
-    const uint2* ranges; const uint32_t* point_list; const uint32_t* tile_order; const float4* records; const float* extra;
+    const uint2* ranges; const uint32_t* point_list; const float4* records; const float* extra;
     int W, H, gx, gy; const float* bg; float *out_color, *out_depth, *out_alpha, *out_extra; uint32_t* n_contrib;
     const gsr_counters* counters;
 };
@@ -1141,7 +1086,7 @@ static void launch_blend_t(const BlendArgs& a, cudaStream_t st) {
             configured[dev] = true;
         }
     }
-    k_blend<NX, NC><<<a.gx * a.gy, BLEND_THREADS, Cfg::SMEM, st>>>(a.ranges, a.point_list, a.tile_order, a.records, a.extra, a.W, a.H, a.gx, a.bg,
+    k_blend<NX, NC><<<dim3(a.gx, a.gy), BLEND_THREADS, Cfg::SMEM, st>>>(a.ranges, a.point_list, a.records, a.extra, a.W, a.H, a.gx, a.bg,
                                                                        a.out_color, a.out_depth, a.out_alpha, a.out_extra, a.n_contrib, a.counters);
 }
 // The 6-channel variant runs at 70 registers / 3 CTAs per SM; holding it to 64 registers / 4 CTAs (shorter queues, 92 B of
@@ -1199,8 +1144,7 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
         k_recolor<<<(f->P + 255) / 256, 256, 0, st>>>(f->P, radii, f->colors_precomp, (float4*)(geo + gl.records));
         int rc0 = check_launch("gsr_forward/recolor", debug, st);
         if (rc0) return rc0;
-        BlendArgs ba{(const uint2*)(img + il.ranges), (const uint32_t*)(bin + bl.point_list), (const uint32_t*)(img + il.tile_order),
-                     (const float4*)(geo + gl.records), extra_colors,
+        BlendArgs ba{(const uint2*)(img + il.ranges), (const uint32_t*)(bin + bl.point_list), (const float4*)(geo + gl.records), extra_colors,
                      f->W, f->H, il.gx, il.gy, f->bg, out_color, out_depth, out_alpha, out_extra, nullptr, counters};
         launch_blend(ba, st);
         return check_launch("gsr_forward/blend(reuse)", debug, st);
@@ -1241,7 +1185,7 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     if (rc) return rc;
 
     uint2* ranges = (uint2*)(img + il.ranges);
-    k_tile_scan<<<1, 1024, 0, st>>>(pp.tile_count, pp.tile_big, (uint32_t*)(img + il.tile_fill), ranges, (uint32_t*)(img + il.tile_order), counters, il.tiles, (uint32_t)(cap > 0xffffffffull ? 0xffffffffull : cap), tile_order_mode());
+    k_tile_scan<<<1, 1024, 0, st>>>(pp.tile_count, pp.tile_big, (uint32_t*)(img + il.tile_fill), ranges, counters, il.tiles, (uint32_t)(cap > 0xffffffffull ? 0xffffffffull : cap));
     prof_mark(2, st);
     if ((rc = check_launch("gsr_forward/tile_scan", debug, st))) return rc;
 
@@ -1259,7 +1203,7 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     k_sort_tiles<<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters, keep_pairs);
     prof_mark(4, st);
     if ((rc = check_launch("gsr_forward/sort", debug, st))) return rc;
-    BlendArgs ba{ranges, (const uint32_t*)(bin + bl.point_list), (const uint32_t*)(img + il.tile_order), pp.records, extra_colors, f->W, f->H, il.gx, il.gy, f->bg,
+    BlendArgs ba{ranges, (const uint32_t*)(bin + bl.point_list), pp.records, extra_colors, f->W, f->H, il.gx, il.gy, f->bg,
                  out_color, out_depth, out_alpha, out_extra, n_contrib, counters};
     launch_blend(ba, st);
     prof_mark(5, st);
