@@ -83,10 +83,11 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
     const int pxi = X0 + (lane & 7), pyi = Y0 + (lane >> 3);
     const bool inside = pxi < W && pyi < H;
     const float pixx = (float)pxi, pixy = (float)pyi;
-    const float fcx = (float)X0 + FOOT_HX, fcy = (float)Y0 + FOOT_HY;
+    // warp-uniform values go through a broadcast so the compiler keeps them instead of re-deriving them from the ids in the loops
+    const float fcx = __shfl_sync(GSR_FULL, (float)X0 + FOOT_HX, 0), fcy = __shfl_sync(GSR_FULL, (float)Y0 + FOOT_HY, 0);
     const size_t pid = (size_t)W * pyi + pxi, HW = (size_t)H * W;
-    const uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(sRec);
-    const uint32_t q_base = (uint32_t)__cvta_generic_to_shared(sQ) + (uint32_t)warp * (BWD_QCAP * 48);
+    const uint32_t rec_base = __shfl_sync(GSR_FULL, (uint32_t)__cvta_generic_to_shared(sRec), 0);
+    const uint32_t q_base = __shfl_sync(GSR_FULL, (uint32_t)__cvta_generic_to_shared(sQ) + (uint32_t)warp * (BWD_QCAP * 48), 0);
     const unsigned gt_mask = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
 
     const uint2 range = ranges[tile];

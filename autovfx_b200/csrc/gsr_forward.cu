@@ -802,9 +802,11 @@ __global__ void __launch_bounds__(BLEND_THREADS, NX ? 0 : 4) k_blend(const uint2
     const int pxi = X0 + (lane & 7), pyi = Y0 + (lane >> 3);
     const bool inside = pxi < W && pyi < H;
     const float pixx = (float)pxi, pixy = (float)pyi;
-    const float cx = (float)X0 + FOOT_HX, cy = (float)Y0 + FOOT_HY;  // footprint centre
-    const uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(sRec);
-    const uint32_t q_base = (uint32_t)__cvta_generic_to_shared(sQ) + (uint32_t)warp * ((BLEND_QCAP / 2) * PAIR);
+    // warp-uniform values are routed through a broadcast so that the compiler keeps them in uniform registers instead of
+    // re-deriving them from the thread / CTA ids inside the cull loop (it rematerialises them there to stay at 64 registers)
+    const float cx = __shfl_sync(GSR_FULL, (float)X0 + FOOT_HX, 0), cy = __shfl_sync(GSR_FULL, (float)Y0 + FOOT_HY, 0);  // footprint centre
+    const uint32_t rec_base = __shfl_sync(GSR_FULL, (uint32_t)__cvta_generic_to_shared(sRec), 0);
+    const uint32_t q_base = __shfl_sync(GSR_FULL, (uint32_t)__cvta_generic_to_shared(sQ) + (uint32_t)warp * ((BLEND_QCAP / 2) * PAIR), 0);
     const unsigned lt_mask = (1u << lane) - 1u;
 
     uint2 range = ranges[tile];
