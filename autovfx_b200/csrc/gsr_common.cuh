@@ -142,8 +142,10 @@ __device__ __forceinline__ void for_each_tile(int x0, int y0, int x1, int y1, in
         uint32_t bp[NW];
 #pragma unroll
         for (int k = 0; k < NW; k++) bp[k] = __shfl_sync(GSR_FULL, pay[k], src);
-        for (int t = lane; t < bn; t += 32) {
-            const int ty = by0 + t / bw, tx = bx0 + t % bw;
+        const float inv_w = 1.0f / (float)bw;  // row of tile t without an integer division: (t + 0.5) / bw is at least 0.5/bw away from
+        for (int t = lane; t < bn; t += 32) {  // an integer and the float product is off by < t * 2^-22 / bw, so it truncates exactly for t < 2^21
+            const int row = (int)(((float)t + 0.5f) * inv_w);
+            const int ty = by0 + row, tx = bx0 + (t - row * bw);
             op(ty * gx + tx, tx, ty, bp);
         }
         __syncwarp();
