@@ -191,17 +191,15 @@ __device__ __forceinline__ void cov3d_ref_rounding(float sx, float sy, float sz,
 // BULK): rows are only 4-byte aligned (M = 25, the SuGaR storage: 300-byte rows) — each lane bulk-copies the 16-byte aligned
 // window that contains its coefficients (one extra float4) and evaluates from its row's offset inside the window.
 template <int DEG, bool VEC, bool BULK, bool WIN = false>
-__global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
+__global__ void __launch_bounds__(PRE_THREADS, 8) k_preprocess(const PreParams p) {
     constexpr int DG = DEG < 0 ? 0 : DEG;
     constexpr int NF = sh_nf(DG);
     constexpr int STRIDE = sh_stride(DG, VEC, WIN);
     __shared__ CamConsts cam;
     __shared__ __align__(16) float stage[DEG < 0 ? 4 : PRE_THREADS * STRIDE];
     __shared__ __align__(8) unsigned long long stage_bar[PRE_THREADS / 32];
-    __shared__ uint32_t s_vis[2];  // visible Gaussians of the block, warps that have reported
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 2) s_vis[tid] = 0;
     if (BULK && lane == 0) {
         mbar_init((uint32_t)__cvta_generic_to_shared(&stage_bar[warp]), 1u);
         mbar_fence_init();
@@ -390,18 +388,8 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreParams p) {
             }
         }
     }
-    // P_vis: every warp reports its count; the last one to arrive adds the block's total (no barrier: a block-wide
-    // __syncthreads_count here made every warp wait for the slowest one, 10 % of the kernel's stall samples)
-    const unsigned vm = __ballot_sync(GSR_FULL, vis);
-    if (lane == 0) {
-        const uint32_t before = atomicAdd(&s_vis[0], (uint32_t)__popc(vm));
-        __threadfence_block();
-        if (atomicAdd(&s_vis[1], 1u) == PRE_THREADS / 32 - 1) {
-            const uint32_t total = atomicAdd(&s_vis[0], 0u);
-            if (total) atomicAdd(&p.counters->num_visible, total);
-        }
-        (void)before;
-    }
+    const int nvis = __syncthreads_count(vis);
+    if (tid == 0 && nvis) atomicAdd(&p.counters->num_visible, (uint32_t)nvis);
 }
 
 // =====================================================================================================
