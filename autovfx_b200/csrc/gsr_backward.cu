@@ -74,7 +74,6 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
     __shared__ __align__(16) float4 sRec[BWD_THREADS * 3];                    // staged batch, 48 B per splat
     __shared__ __align__(16) float4 sQ[(BWD_THREADS / 32) * BWD_QCAP * 3];    // per-warp survivor queues (back to front)
     __shared__ uint32_t sId[BWD_THREADS];
-    __shared__ float acc[BWD_THREADS][11];  // 10 gradients per staged splat (+1 pad: conflict-free flush)
     __shared__ uint32_t s_wl[BWD_THREADS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -93,6 +92,26 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
     const uint2 range = ranges[tile];
     const int n = (int)(range.y - range.x);
     if (n == 0) return;
+
+    // After reduce10 the warp total of gradient component `vid` sits in one fixed lane (vid depends on the lane only), so
+    // each of those ten lanes keeps the array and stride its component goes to and adds the total straight to global memory
+    // with a fire-and-forget reduction (RED.ADD.F32): one per (warp, splat, component).  (Combining the 8 warps of a tile in
+    // shared memory first costs a compare-and-swap loop per add — shared memory has no native float add — plus two extra
+    // barriers and a flush pass per batch.)
+    float* my_dst;
+    uint32_t my_stride;
+    {
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+        const int vid = (b4 ? 5 : 0) + (b3 ? (b1 ? 4 : 3) : (b2 ? 2 : (b1 ? 1 : 0)));  // as in reduce10
+        float* const dst[10] = {dL_dcolors, dL_dcolors + 1, dL_dcolors + 2, dL_ddepths, dL_dmean2D, dL_dmean2D + 1,
+                                dL_dconic, dL_dconic + 1, dL_dconic + 3, dL_dopacity};
+        const uint32_t strd[10] = {3, 3, 3, 1, 3, 3, 4, 4, 4, 1};
+        my_dst = dst[0];
+        my_stride = strd[0];
+#pragma unroll
+        for (int k = 1; k < 10; k++)
+            if (vid == k) { my_dst = dst[k]; my_stride = strd[k]; }
+    }
 
     const float T_final = inside ? (1 - accum_alphas[pid]) : 0;
     float T = T_final;
@@ -179,7 +198,8 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
                 int vid;
                 bool valid;
                 const float z = reduce10(g, lane, vid, valid);
-                if (valid) atomicAdd(&acc[(int)pos - 1 - batch * BWD_THREADS][vid], z);
+                (void)vid;
+                if (valid && z != 0.0f) atomicAdd(my_dst + (size_t)sId[(int)pos - 1 - batch * BWD_THREADS] * my_stride, z);
             }
         }
         qn = 0;
@@ -188,7 +208,7 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
 
     for (int b = (int)((tile_last - 1) / BWD_THREADS); b >= 0; b--) {
         const int cnt = min(BWD_THREADS, n - b * BWD_THREADS);
-        __syncthreads();  // previous batch fully flushed
+        __syncthreads();  // every warp is done with the previous batch's records
         if (tid < cnt) {
             const uint32_t id = point_list[range.x + b * BWD_THREADS + tid];
             const float4* r = records + 3 * (size_t)id;
@@ -198,8 +218,6 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
             sts128b(sa, r[0]); sts128b(sa + 16, r[1]); sts128b(sa + 32, rc);
             sId[tid] = id;
         }
-#pragma unroll
-        for (int k = 0; k < 11; k++) acc[tid][k] = 0.f;
         __syncthreads();
 
         if ((uint32_t)(b * BWD_THREADS) < warp_last) {
@@ -223,21 +241,6 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
                 }
             }
             if (qn) drain(b);
-        }
-        __syncthreads();
-        if (tid < cnt) {
-            const float* a = acc[tid];
-            const uint32_t id = sId[tid];
-            if (a[0] != 0.f) atomicAdd(&dL_dcolors[3 * (size_t)id + 0], a[0]);
-            if (a[1] != 0.f) atomicAdd(&dL_dcolors[3 * (size_t)id + 1], a[1]);
-            if (a[2] != 0.f) atomicAdd(&dL_dcolors[3 * (size_t)id + 2], a[2]);
-            if (a[3] != 0.f) atomicAdd(&dL_ddepths[id], a[3]);
-            if (a[4] != 0.f) atomicAdd(&dL_dmean2D[3 * (size_t)id + 0], a[4]);
-            if (a[5] != 0.f) atomicAdd(&dL_dmean2D[3 * (size_t)id + 1], a[5]);
-            if (a[6] != 0.f) atomicAdd(&dL_dconic[4 * (size_t)id + 0], a[6]);
-            if (a[7] != 0.f) atomicAdd(&dL_dconic[4 * (size_t)id + 1], a[7]);
-            if (a[8] != 0.f) atomicAdd(&dL_dconic[4 * (size_t)id + 3], a[8]);
-            if (a[9] != 0.f) atomicAdd(&dL_dopacity[id], a[9]);
         }
     }
 }
