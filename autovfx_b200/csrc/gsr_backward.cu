@@ -7,8 +7,8 @@
 //
 // Differences in mechanism (the mathematics and the per-pixel recursion are the reference's):
 //   * the reference issues 10 global atomicAdds per contributing (pixel, Gaussian) pair; here each warp
-//     (an 8x4 pixel footprint) reduces the 10 partial gradients with shuffles, the 8 warps of a tile
-//     combine them in shared memory, and one flush per (tile, Gaussian) goes to global memory;
+//     (an 8x4 pixel footprint) reduces the 10 partial gradients with shuffles and issues one global
+//     reduction per (warp, Gaussian, component);
 //   * splats that cannot touch a warp's footprint are culled exactly as in the forward blend;
 //   * the two per-Gaussian backward kernels are fused; SH rows are staged through shared memory with
 //     coalesced accesses in both directions, and the kernel writes every output row itself (zeros for
