@@ -54,7 +54,10 @@ def measured_hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons, one sample every 50 ms, each stamped with the host time it was read.  The sampler is
+    started before the untimed pre-pass (nvidia-smi needs a few hundred ms to come up, longer with 8 ranks starting one each);
+    ``stop(t0, t1)`` reports the samples that fall inside the timed region and, if fewer than two do, the samples of the whole
+    loaded window (pre-pass + warm-up + timed region run the same kernels back to back) — ``window`` says which."""
 
     def __init__(self, index: int):
         self.index = index
@@ -65,7 +68,7 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -74,9 +77,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         self.proc.terminate()
@@ -84,9 +87,14 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:  # noqa: BLE001
             self.proc.kill()
+        window = "timed region"
+        lines = [ln for (ts, ln) in self.lines if t0 is None or (t0 <= ts <= t1 + 0.06)]
+        if len(lines) < 2:
+            window = "pre-pass + warm-up + timed region (same kernels, back to back)"
+            lines = [ln for (_ts, ln) in self.lines]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in lines:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -100,7 +108,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def dist_setup():
@@ -271,28 +279,34 @@ def main():
                              tight=tight)
 
     # pre-pass (untimed, synchronous): sizes the binning capacity for every camera of the run and warms everything up
+    sampler = ClockSampler(local)
+    sampler.start()
     for s in range(Wm + K):
         frame(s, True)
     attempts = 0
     while True:
         attempts += 1
-        sampler = ClockSampler(local)
-        sampler.start()
+        if sampler is None:
+            sampler = ClockSampler(local)
+            sampler.start()
         for s in range(Wm):
             frame(s, False)
         barrier()
         _lib.check(_lib.lib.gsr_profile_begin(K), "gsr_profile_begin")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tickets = []
+        t_w0 = time.time()
         e0.record()
         for s in range(K):
             tickets.append(frame(Wm + s, False)[5])
         e1.record()
         barrier()
+        t_w1 = time.time()
         ms_k = (C.c_float * 5)()
         nfr = C.c_int(0)
         _lib.check(_lib.lib.gsr_profile_end(ms_k, C.byref(nfr)), "gsr_profile_end")
-        clocks = sampler.stop()
+        clocks = sampler.stop(t_w0, t_w1)
+        sampler = None
         ms_local = e0.elapsed_time(e1)
         st = [t.stats() for t in tickets]
         bad = [x for x in st if x["overflow"]]
