@@ -23,6 +23,22 @@ from .scene import Camera
 CAM_FLOATS = 37  # view(16) | proj(16) | campos(3) | tanfovx | tanfovy
 
 
+# ----------------------------------------------------------------------------- host placement
+def bind_to_gpu_numa_node(index: int) -> str:
+    """Pin the calling process to the CPUs NVML reports as closest to GPU ``index`` so that pinned host buffers (the D2H ring
+    of ``FrameLoop``) are first-touched on that NUMA node.  With one process per GPU on an 8-GPU node this decides whether the
+    eight frame streams share one socket's memory controllers: measured 6,080 -> 7,572 end-to-end frames/s at N=8
+    (profiles/r01_bench_n8_final.json).  Call it before creating the loop; returns a short description, never raises."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return "cpus=%d" % len(os.sched_getaffinity(0))
+    except Exception as ex:  # noqa: BLE001
+        return "unchanged (%s)" % type(ex).__name__
+
+
 # ----------------------------------------------------------------------------- sharding (pure host logic)
 def shard_indices(n_frames: int, rank: int, world: int, mode: str = "roundrobin") -> List[int]:
     """Frames owned by ``rank``.  Round-robin balances the slowly varying per-frame cost (R changes smoothly along a

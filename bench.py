@@ -111,19 +111,6 @@ class ClockSampler:
                 "samples": len(sm), "window": window}
 
 
-def bind_to_gpu_numa_node(index: int) -> str:
-    """Pin this rank's threads to the CPUs NVML reports as closest to its GPU, so that the pinned host buffers of the e2e loop
-    are allocated (first touch) on that NUMA node and eight ranks do not all stream their frames into one socket."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        pynvml.nvmlDeviceSetCpuAffinity(h)
-        return "cpus=%d" % len(os.sched_getaffinity(0))
-    except Exception as ex:  # noqa: BLE001
-        return "unchanged (%s)" % type(ex).__name__
-
-
 def dist_setup():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -175,6 +162,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     use_dist = world > 1 and args.impl == "ours"
+    from autovfx_b200.render_loop import bind_to_gpu_numa_node
     affinity = bind_to_gpu_numa_node(local) if world > 1 else "unchanged (single rank)"
     log("[bench] rank %d: cpu affinity %s" % (rank, affinity))
     if use_dist:

@@ -45,6 +45,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+        RL.bind_to_gpu_numa_node(local)
     W, H = 1920, 1080
     g_scene = scene.synthetic_gaussians(args.scene, seed=1234, extent=(4, 4, 1), log_scale_mean=math.log(0.006), log_scale_std=0.5,
                                         opacity_mean=0.0, opacity_std=2.0, sh_degree=4)
