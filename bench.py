@@ -163,7 +163,7 @@ def main():
     dev = torch.device("cuda", local)
     use_dist = world > 1 and args.impl == "ours"
     from autovfx_b200.render_loop import bind_to_gpu_numa_node
-    affinity = bind_to_gpu_numa_node(local) if world > 1 else "unchanged (single rank)"
+    affinity = bind_to_gpu_numa_node(local)
     log("[bench] rank %d: cpu affinity %s" % (rank, affinity))
     if use_dist:
         import torch.distributed as dist
