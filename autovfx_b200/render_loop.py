@@ -165,9 +165,12 @@ class FrameLoop:
                                      "normal8": torch.empty((H, W, 3), dtype=torch.uint8, device=dev)})
         self.host = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in self.outputs[s].items()} for s in range(ring)] if to_host else None
         self.copy_stream = torch.cuda.Stream(self.device) if to_host else None
-        self.cam_pinned = torch.empty((ring, CAM_FLOATS), dtype=torch.float32).pin_memory()
-        self.cam_dev = torch.empty((ring, CAM_FLOATS), dtype=torch.float32, device=self.device)
-        self.h2d_bytes_per_frame = CAM_FLOATS * 4
+        # per-frame host->device payload: the 37 camera floats, plus (product mode) the 4x4 inverse of the view matrix that the
+        # pseudo-normal needs — inverted on the host in float64 (the reference calls torch.inverse on the GPU every frame)
+        self._cam_floats = CAM_FLOATS + (16 if product else 0)
+        self.cam_pinned = torch.empty((ring, self._cam_floats), dtype=torch.float32).pin_memory()
+        self.cam_dev = torch.empty((ring, self._cam_floats), dtype=torch.float32, device=self.device)
+        self.h2d_bytes_per_frame = self._cam_floats * 4
         self.d2h_bytes_per_frame = sum(v.numel() * v.element_size() for v in self.outputs[0].values()) if to_host else 0
         self.rerendered = 0
 
@@ -179,7 +182,9 @@ class FrameLoop:
 
     def _issue(self, slot: int, cam_row: torch.Tensor, sync: bool):
         """host camera row -> pinned -> device (H2D inside the frame), then the frame's kernels into ring slot ``slot``."""
-        self.cam_pinned[slot].copy_(cam_row)
+        self.cam_pinned[slot, :CAM_FLOATS].copy_(cam_row)
+        if self.product:
+            self.cam_pinned[slot, CAM_FLOATS:] = torch.linalg.inv(cam_row[0:16].view(4, 4).double()).float().reshape(16)
         self.cam_dev[slot].copy_(self.cam_pinned[slot], non_blocking=True)
         f = self.frames[slot]
         g = self.g
@@ -197,7 +202,7 @@ class FrameLoop:
         RD.axis_normals(g["means3D"], g["scales"], g["rotations"], cam[32:35], remap01=True, out=normals)
         res = self._R.forward_multi(g["means3D"], g["shs"], None, normals, g["opacities"], g["scales"], g["rotations"], None, st, sync=sync,
                                     out=out, extra_out=self.extra[slot], tight=self.tight_tiles)
-        c2w = torch.linalg.inv_ex(cam[0:16].view(4, 4))[0]  # the reference's world_view_transform.inverse(), no host sync
+        c2w = cam[CAM_FLOATS:CAM_FLOATS + 16]  # the reference's world_view_transform.inverse(), shipped with the camera
         n_out, p_out = self.nmaps[slot]
         RD.normal_maps(self.extra[slot], f[3], c2w, self.W / (2 * tfx), self.H / (2 * tfy), self.W / 2, self.H / 2, out=(n_out, p_out))
         if self.pack8:
