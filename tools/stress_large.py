@@ -1,5 +1,11 @@
-import sys, os, torch
-sys.path.insert(0, '/root/repo')
+"""Large-scene check: P Gaussians (default 12M, R ~ 28M, tiles with > 4096 entries) through ours and the compiled reference;
+prints whether radii and images are bit-identical."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from autovfx_b200 import scene
 from tests import helpers as Hh
 dev = torch.device('cuda:0')
