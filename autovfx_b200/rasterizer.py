@@ -69,7 +69,7 @@ def get_sync_mode() -> str:
     return _SYNC_MODE
 
 
-_TIGHT_TILES: Optional[bool] = None  # None = automatic
+_TIGHT_TILES = False
 _REUSE_GEOMETRY = True
 
 
@@ -83,29 +83,16 @@ def set_geometry_reuse(on: bool) -> None:
     _REUSE_GEOMETRY = bool(on)
 
 
-def set_tight_tiles(on: Optional[bool]) -> None:
-    """Tile-list policy (GSR_FLAG_TIGHT_TILES).  A (Gaussian, tile) instance is *tight* if the splat can reach alpha >= 1/255 at
-    a pixel of the tile; the reference also lists the instances of the 3-sigma rectangle that cannot, and then skips them at
-    every pixel.  color / depth / alpha / radii and all gradients are bit-for-bit the same either way; only the opaque
-    per-tile lists (and the instance count) differ, tight lists being sub-sequences of the reference's.
-
-    ``None`` (default): automatic — forward-only calls use tight lists (nothing a caller of the reference API can observe
-    changes, fewer instances are sorted and staged), calls that keep buffers for a backward pass or expose the sorted keys
-    reproduce the reference's lists exactly.  ``True`` / ``False`` force one policy everywhere."""
+def set_tight_tiles(on: bool) -> None:
+    """Opt-in (default off): only emit a (Gaussian, tile) instance if the splat can reach alpha >= 1/255 at a pixel of the
+    tile (GSR_FLAG_TIGHT_TILES).  color / depth / alpha / radii and all gradients are bit-for-bit unchanged; the opaque
+    per-tile lists become sub-sequences of the reference's, so fewer instances are sorted and staged."""
     global _TIGHT_TILES
-    _TIGHT_TILES = None if on is None else bool(on)
+    _TIGHT_TILES = bool(on)
 
 
-def get_tight_tiles() -> Optional[bool]:
+def get_tight_tiles() -> bool:
     return _TIGHT_TILES
-
-
-def _use_tight(tight: Optional[bool], for_backward: bool, sorted_keys: bool) -> bool:
-    if tight is None:
-        tight = _TIGHT_TILES
-    if tight is None:
-        return not for_backward and not sorted_keys
-    return bool(tight)
 
 
 class FrameTicket:
@@ -286,8 +273,7 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
         else:
             color, depth, alpha, radii = out
         flags = (_lib.GSR_FLAG_FOR_BACKWARD if for_backward else 0) | (_lib.GSR_FLAG_SORTED_KEYS if sorted_keys else 0)
-        use_tight = _use_tight(tight, for_backward, sorted_keys)
-        if use_tight:
+        if _TIGHT_TILES if tight is None else tight:
             flags |= _lib.GSR_FLAG_TIGHT_TILES
         fr = _lib.gsr_frame()
         _fill_frame(fr, P, int(settings.sh_degree), M, W, H, settings, bg, means3D, shs, colors_precomp, opacities, scales, rotations,
@@ -298,6 +284,7 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
         st.ensure_capacity(P)
         do_sync = (_SYNC_MODE == "safe") if sync is None else sync
         stream = torch.cuda.current_stream(device)
+        use_tight = _TIGHT_TILES if tight is None else tight
 
         def tk(t):
             return None if t is None else (t.data_ptr(), t._version, tuple(t.shape))

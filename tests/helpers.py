@@ -95,9 +95,7 @@ def settings_from(a: Dict, debug=False, prefiltered=False):
                                          sh_degree=a["sh_degree"], campos=a["campos"], prefiltered=prefiltered, debug=debug)
 
 
-def run_ours(a: Dict, for_backward=False, sorted_keys=False, debug=True, tight=False):
-    """One forward through the C ABI.  ``tight=False`` (default here): the reference's per-tile lists, so that the internal
-    buffers can be compared with the reference's; the library's own default for forward-only calls is tight lists."""
+def run_ours(a: Dict, for_backward=False, sorted_keys=False, debug=True, tight=None):
     from autovfx_b200 import rasterizer as R
     s = settings_from(a, debug=debug)
     color, depth, alpha, radii, ws, ticket, keep = R.forward_raw(a["means3D"], a["shs"], a["colors_precomp"], a["opacities"], a["scales"],
