@@ -57,7 +57,7 @@ ABI_VERSION = 2
 
 EXPORTS = ("gsr_abi_version", "gsr_last_error", "gsr_geom_bytes", "gsr_binning_bytes", "gsr_binning_capacity", "gsr_image_bytes",
            "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_dist2_bytes", "gsr_dist2", "gsr_get_views",
-           "gsr_profile_begin", "gsr_profile_end", "gsr_forward_multi", "gsr_axis_normals", "gsr_normal_maps",
+           "gsr_profile_begin", "gsr_profile_begin_strided", "gsr_profile_end", "gsr_forward_multi", "gsr_axis_normals", "gsr_normal_maps",
            "gsr_pack_frame", "gsr_activate_gaussians")
 
 
@@ -113,6 +113,8 @@ def _load() -> C.CDLL:
     lib.gsr_get_views.argtypes = [C.POINTER(gsr_workspace), C.c_int32, C.c_int32, C.c_int32, C.POINTER(gsr_views)]
     lib.gsr_profile_begin.restype = C.c_int
     lib.gsr_profile_begin.argtypes = [C.c_int]
+    lib.gsr_profile_begin_strided.restype = C.c_int
+    lib.gsr_profile_begin_strided.argtypes = [C.c_int, C.c_int]
     lib.gsr_profile_end.restype = C.c_int
     lib.gsr_profile_end.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
     return lib

@@ -17,7 +17,7 @@ int compose_impl(int N, int M, const float* xyz, const float* f_dc, const float*
                  float* rotations, cudaStream_t st);
 int dist2_impl(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t dist2_bytes(int P);
-int profile_begin(int max_frames);
+int profile_begin(int max_frames, int stride);
 int profile_end(float* ms, int* frames);
 
 // checkFrustum (rasterizer_impl.cu:54-66): in_frustum() only tests view-space z (auxiliary.h:154)
@@ -92,7 +92,8 @@ int gsr_dist2(int32_t P, const float* points, float* mean_dists, void* workspace
     return gsr::dist2_impl(P, points, mean_dists, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-int gsr_profile_begin(int max_frames) { return gsr::profile_begin(max_frames); }
+int gsr_profile_begin(int max_frames) { return gsr::profile_begin(max_frames, 1); }
+int gsr_profile_begin_strided(int max_frames, int stride) { return gsr::profile_begin(max_frames, stride); }
 int gsr_profile_end(float* ms_per_kernel, int* frames) { return gsr::profile_end(ms_per_kernel, frames); }
 
 int gsr_get_views(const gsr_workspace* ws, int32_t P, int32_t W, int32_t H, gsr_views* out) {

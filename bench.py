@@ -295,7 +295,7 @@ def main():
         for s in range(Wm):
             frame(s, False)
         barrier()
-        _lib.check(_lib.lib.gsr_profile_begin(K), "gsr_profile_begin")
+        _lib.check(_lib.lib.gsr_profile_begin_strided(K, 4), "gsr_profile_begin")  # per-kernel events on every 4th frame of the timed region
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tickets = []
         t_w0 = time.time()
