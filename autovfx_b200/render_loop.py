@@ -173,42 +173,72 @@ class FrameLoop:
         self.h2d_bytes_per_frame = self._cam_floats * 4
         self.d2h_bytes_per_frame = sum(v.numel() * v.element_size() for v in self.outputs[0].values()) if to_host else 0
         self.rerendered = 0
+        self._prep = [None] * ring
 
-    def _settings(self, slot: int, tanfovx: float, tanfovy: float):
-        c = self.cam_dev[slot]
-        return self._R.GaussianRasterizationSettings(
-            image_height=self.H, image_width=self.W, tanfovx=tanfovx, tanfovy=tanfovy, bg=self.bg, scale_modifier=self.scale_modifier,
-            viewmatrix=c[0:16], projmatrix=c[16:32], sh_degree=self.sh_degree, campos=c[32:35], prefiltered=False, debug=False)
+    def _prepared(self, slot: int):
+        """Per-slot resolved forward (and, in product mode, the resolved argument lists of the surrounding kernels): built on
+        first use and whenever the parameter tensors change (``set_gaussians``)."""
+        g = self.g
+        key = tuple((g[k].data_ptr(), tuple(g[k].shape)) for k in ("means3D", "shs", "opacities", "scales", "rotations"))
+        ent = self._prep[slot]
+        if ent is not None and ent["key"] == key:
+            return ent
+        import ctypes as C
+        from . import _lib
+        R, f, P, cam = self._R, self.frames[slot], g["means3D"].shape[0], self.cam_dev[slot]
+        out = (f[0:3], f[3:4], f[4:5], self.radii[slot][:P])
+        ent = {"key": key}
+        if not self.product:
+            ent["fwd"] = R.PreparedForward(g["means3D"], g["shs"], g["opacities"], g["scales"], g["rotations"], cam, self.W, self.H, self.bg,
+                                           self.sh_degree, self.scale_modifier, out, tight=self.tight_tiles)
+        else:
+            normals = self.normals[:P]
+            ent["fwd"] = R.PreparedForward(g["means3D"], g["shs"], g["opacities"], g["scales"], g["rotations"], cam, self.W, self.H, self.bg,
+                                           self.sh_degree, self.scale_modifier, out, extra=normals, extra_out=self.extra[slot], tight=self.tight_tiles)
+            L = _lib.lib
+            camp = cam.data_ptr()
+            n_out, p_out = self.nmaps[slot]
+            ptr = lambda t: t.data_ptr() if t.numel() else None  # noqa: E731
+            ent["axis"] = (P, ptr(g["means3D"]), ptr(g["scales"]), ptr(g["rotations"]), camp + 32 * 4, 1, ptr(normals))
+            ent["maps"] = (self.W, self.H, self.extra[slot].data_ptr(), f[3].data_ptr(), camp + CAM_FLOATS * 4)
+            ent["maps_out"] = (n_out.data_ptr(), p_out.data_ptr())
+            if self.pack8:
+                o = self.outputs[slot]
+                ent["pack"] = (self.W, self.H, f[0:3].data_ptr(), f[4].data_ptr(), f[3].data_ptr(), n_out.data_ptr(), float(self.depth_scale),
+                               o["rgba8"].data_ptr(), o["normal8"].data_ptr(), o["depth8"].data_ptr())
+            ent["L"], ent["check"], ent["C"] = L, _lib.check, C
+        self._prep[slot] = ent
+        return ent
 
     def _issue(self, slot: int, cam_row: torch.Tensor, sync: bool):
-        """host camera row -> pinned -> device (H2D inside the frame), then the frame's kernels into ring slot ``slot``."""
+        """host camera row -> pinned -> device (H2D inside the frame), then the frame's kernels into ring slot ``slot``.
+        Everything is launched through per-slot prepared argument lists: per frame the host only copies the camera, updates two
+        scalars and makes the C calls."""
         self.cam_pinned[slot, :CAM_FLOATS].copy_(cam_row)
         if self.product:
             self.cam_pinned[slot, CAM_FLOATS:] = torch.linalg.inv(cam_row[0:16].view(4, 4).double()).float().reshape(16)
         self.cam_dev[slot].copy_(self.cam_pinned[slot], non_blocking=True)
-        f = self.frames[slot]
-        g = self.g
-        P = g["means3D"].shape[0]
-        out = (f[0:3], f[3:4], f[4:5], self.radii[slot][:P])
         tfx, tfy = float(cam_row[35]), float(cam_row[36])
-        st = self._settings(slot, tfx, tfy)
+        ent = self._prepared(slot)
+        fwd = ent["fwd"]
         if not self.product:
-            res = self._R.forward_raw(g["means3D"], g["shs"], None, g["opacities"], g["scales"], g["rotations"], None, st, sync=sync, out=out,
-                                      tight=self.tight_tiles)
-            return res[5]  # ticket
-        RD = self._RD
-        cam = self.cam_dev[slot]
-        normals = self.normals[:P]
-        RD.axis_normals(g["means3D"], g["scales"], g["rotations"], cam[32:35], remap01=True, out=normals)
-        res = self._R.forward_multi(g["means3D"], g["shs"], None, normals, g["opacities"], g["scales"], g["rotations"], None, st, sync=sync,
-                                    out=out, extra_out=self.extra[slot], tight=self.tight_tiles)
-        c2w = cam[CAM_FLOATS:CAM_FLOATS + 16]  # the reference's world_view_transform.inverse(), shipped with the camera
-        n_out, p_out = self.nmaps[slot]
-        RD.normal_maps(self.extra[slot], f[3], c2w, self.W / (2 * tfx), self.H / (2 * tfy), self.W / 2, self.H / 2, out=(n_out, p_out))
-        if self.pack8:
-            o = self.outputs[slot]
-            RD.pack_frame(f[0:3], f[4], f[3], n_out, self.depth_scale, out=o)
-        return res[5]
+            ticket = fwd.launch(tfx, tfy)
+            while sync and not ticket.ok():  # ok() waits for the counters and grows the capacity after an overflow
+                ticket = fwd.launch(tfx, tfy)
+            return ticket
+        L, check, C = ent["L"], ent["check"], ent["C"]
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            check(L.gsr_axis_normals(*ent["axis"], stream), "gsr_axis_normals")
+            ticket = fwd.launch(tfx, tfy)
+            while sync and not ticket.ok():
+                ticket = fwd.launch(tfx, tfy)
+            W, H, extra_p, depth_p, c2w_p = ent["maps"]
+            check(L.gsr_normal_maps(W, H, extra_p, depth_p, c2w_p, self.W / (2 * tfx), self.H / (2 * tfy), self.W / 2, self.H / 2,
+                                    ent["maps_out"][0], ent["maps_out"][1], stream), "gsr_normal_maps")
+            if self.pack8:
+                check(L.gsr_pack_frame(*ent["pack"], stream), "gsr_pack_frame")
+        return ticket
 
     def _copy_out(self, slot: int):
         for k, v in self.outputs[slot].items():
