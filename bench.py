@@ -343,7 +343,9 @@ def main():
                 "kernel_share": {k: (v / sum(kms.values()) if sum(kms.values()) else 0) for k, v in kms.items()},
                 "per_kernel_gbs": {k: (stage_bytes[k] / (v * 1e-3) / 1e9 if v > 0 else 0) for k, v in kms.items()},
                 "frame_algorithmic_bytes": ab["frame"], "frame_achieved": frame_gbs, "frame_frac": frame_gbs / peak,
-                "note": "blend is FP32/MUFU-bound, not HBM-bound (SURVEY §7); its HBM fraction is reported because the metric names the HBM roofline"}
+                "note": "k_blend is bound by FP32 instruction issue, not by HBM (ncu, profiles/r01_ncu_forward_final.md: 76 % of issue slots busy, FMA pipe 53 %, "
+                        "5 % of DRAM throughput, 446 M warp instructions for 304 M pixel-splat evaluations); its HBM fraction is reported because the metric "
+                        "names the HBM roofline. The HBM-bound kernels are k_preprocess (per_kernel_gbs) and, in training, k_gaussian_backward"}
 
     # ---- opt-in tight-tile mode (GSR_FLAG_TIGHT_TILES): identical images, shorter per-tile lists; reported separately ----
     for s in range(Wm):
