@@ -18,7 +18,7 @@ from oracle import ref_cuda  # noqa: E402
 
 CASES = {  # name -> store gradients?
     "config1": ("fw+small_grads",), "small_sh": ("fw+grads",), "small_deg1_m25": ("fw+grads",), "small_precomp": ("fw+grads",),
-    "big_splats": ("fw+grads",), "dense_tile": ("fw",), "coplanar": ("fw",),
+    "big_splats": ("fw+grads",), "dense_tile": ("fw",), "coplanar": ("fw",), "deg3_m25": ("fw+grads",), "deg2_m25": ("fw",),
 }
 
 
@@ -50,5 +50,38 @@ def main(outdir):
         print(name, "->", path, "%.0f KB" % (os.path.getsize(path) / 1024), "R =", fw["num_rendered"])
 
 
+def wrapper_golden(outdir, name="small_sh"):
+    """render()-wrapper row: the reference's two rasterizer passes (compiled reference) around the wrapper's helper functions
+    restated in torch (tests/wrapper_ref.py; the originals cannot be imported) and executed with torch's CUDA kernels."""
+    import math
+    from tests import wrapper_ref as WR
+    dev = torch.device("cuda:0")
+    case = Hh.case_inputs(name)
+    a = Hh.resolve(case, dev)
+    cam = case["cam"]
+
+    def rasterize(shs=None, colors_precomp=None):
+        b = dict(a)
+        b["shs"], b["colors_precomp"] = shs, colors_precomp
+        fw = Hh.run_ref(b)
+        return fw["color"], fw["depth"], fw["alpha"], fw["radii"]
+    FoVx, FoVy = 2 * math.atan(cam.tanfovx), 2 * math.atan(cam.tanfovy)
+    ref = WR.render_two_pass(rasterize, a["means3D"], a["shs"], a["opacities"], a["scales"], a["rotations"], case["sh_degree"],
+                             dict(campos=a["campos"], viewmatrix=a["view"], FoVx=FoVx, FoVy=FoVy), a["bg"])
+    rgba8 = WR.save_image_bytes(ref["render"].clone())
+    nrm = ref["normal"].cpu().numpy()
+    normal8 = (((nrm + 1) / 2) * 255).astype(np.uint8)
+    depth8 = (np.clip(ref["depth"].cpu().numpy() / 3.0, a_min=0., a_max=1.) * 255).astype(np.uint8)
+    out = {"case": np.array(name), "FoVx": np.array(FoVx), "FoVy": np.array(FoVy), "c2w": a["view"].inverse().cpu().numpy(),
+           "normal_normed": ref["normal_normed"].cpu().numpy(), "normal_raw_image": ref["normal_raw_image"].cpu().numpy(),
+           "render": ref["render"].cpu().numpy(), "depth": ref["depth"].cpu().numpy(), "normal": nrm,
+           "pseudo_normal": ref["pseudo_normal"].cpu().numpy(), "rgba8": rgba8.cpu().numpy(), "normal8": normal8, "depth8": depth8}
+    path = os.path.join(outdir, "wrapper_" + name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrapper", name, "->", path, "%.0f KB" % (os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"))
+    out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
+    main(out)
+    wrapper_golden(out)
