@@ -132,3 +132,25 @@ def test_transform_and_activate_oracle_vs_torch():
     # identity transform = plain activation
     ident = RO.transform_gaussians(rn, pivot.numpy(), np.eye(3, dtype=np.float32), 1.0, pivot.numpy())
     assert np.abs(ident["xyz"] - rn["xyz"]).max() < 1e-6 and np.abs(ident["scaling"] - rn["scaling"]).max() == 0
+
+
+def test_wrapper_oracle_against_golden_from_the_gpu():
+    """tests/golden/wrapper_small_sh.npz: the reference's two rasterizer passes (compiled reference, B200) around the wrapper's
+    helper functions executed with torch's CUDA kernels (tests/golden/make_golden.py).  Pins oracle/render_oracle.py."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wrapper_small_sh.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden file missing")
+    z = np.load(path)
+    case = case_inputs(str(z["case"]))
+    g, cam = case["g"], case["cam"]
+    n01 = RO.get_normal(g["means3D"].numpy(), g["scales"].numpy(), g["rotations"].numpy(), cam.camera_center.numpy(), remap01=True)
+    assert np.abs(n01 - z["normal_normed"]).max() <= 5e-7
+    assert np.abs(RO.normal_image(z["normal_raw_image"]) - z["normal"]).max() <= 5e-7
+    H, W = z["depth"].shape
+    fx, fy = WR.fov2focal(float(z["FoVx"]), W), WR.fov2focal(float(z["FoVy"]), H)
+    pn = RO.pseudo_normal(z["depth"], z["c2w"], fx, fy, W / 2, H / 2)
+    assert np.abs(pn - z["pseudo_normal"]).max() < 5e-3
+    assert (RO.rgba8(z["render"][0:3], z["render"][3]) == z["rgba8"]).all()
+    assert (RO.normal8(z["normal"]) == z["normal8"]).all()
+    assert (RO.depth8(z["depth"], 3.0) == z["depth8"]).all()
