@@ -12,34 +12,28 @@ import math
 import torch
 
 
-def build_rotation(r):  # GU/:78-99
-    norm = torch.sqrt(r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1] + r[:, 2] * r[:, 2] + r[:, 3] * r[:, 3])
-    q = r / norm[:, None]
-    R = torch.zeros((q.size(0), 3, 3), device=r.device, dtype=r.dtype)
-    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
-    R[:, 0, 0] = 1 - 2 * (y * y + z * z)
-    R[:, 0, 1] = 2 * (x * y - w * z)
-    R[:, 0, 2] = 2 * (x * z + w * y)
-    R[:, 1, 0] = 2 * (x * y + w * z)
-    R[:, 1, 1] = 1 - 2 * (x * x + z * z)
-    R[:, 1, 2] = 2 * (y * z - w * x)
-    R[:, 2, 0] = 2 * (x * z - w * y)
-    R[:, 2, 1] = 2 * (y * z + w * x)
-    R[:, 2, 2] = 1 - 2 * (x * x + y * y)
-    return R
+def build_rotation(quats):
+    """Rotation matrices [N,3,3] of quaternions (real part first) that are normalised first — the semantics and the per-element
+    operation order of GU/:78-99 (each entry is formed by the same products, sums and the final `1 - 2*(..)` / `2*(..)`)."""
+    n = torch.sqrt(quats[:, 0] * quats[:, 0] + quats[:, 1] * quats[:, 1] + quats[:, 2] * quats[:, 2] + quats[:, 3] * quats[:, 3])
+    w, x, y, z = (quats / n[:, None]).unbind(-1)
+    rows = [torch.stack((1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)), -1),
+            torch.stack((2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)), -1),
+            torch.stack((2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)), -1)]
+    return torch.stack(rows, 1)
 
 
-def get_minimum_axis(scales, rotations):  # GU/:136-141
-    sorted_idx = torch.argsort(scales, descending=False, dim=-1)
-    R = build_rotation(rotations)
-    R_sorted = torch.gather(R, dim=2, index=sorted_idx[:, None, :].repeat(1, 3, 1)).squeeze()
-    return R_sorted[:, :, 0]
+def get_minimum_axis(scales, rotations):
+    """Column of the rotation matrix that belongs to the smallest scale (GU/:136-141: argsort ascending, gather, first column)."""
+    order = torch.argsort(scales, dim=-1, descending=False)
+    cols = torch.gather(build_rotation(rotations), 2, order[:, None, :].expand(-1, 3, -1))
+    return cols[:, :, 0]
 
 
-def flip_align_view(normal, viewdir):  # GU/:151-157
-    dotprod = torch.sum(normal * -viewdir, dim=-1, keepdims=True)
-    non_flip = dotprod >= 0
-    return normal * torch.where(non_flip, 1, -1), non_flip
+def flip_align_view(normal, viewdir):
+    """Flip the normals that point away from the viewer (GU/:151-157): sign of sum(normal * -viewdir)."""
+    facing = (normal * -viewdir).sum(dim=-1, keepdim=True) >= 0
+    return normal * torch.where(facing, 1, -1), facing
 
 
 def get_normal(xyz, scales, rotations, campos):  # scene/gaussian_model.py:120-124 + GR/:131-132
@@ -62,17 +56,17 @@ def get_ray_directions(H, W, K, device):  # GR/:41-80, create_meshgrid(H, W, Fal
     return torch.stack([(u - cx + 0.5) / fx, (v - cy + 0.5) / fy, torch.ones_like(u)], -1)
 
 
-def depth_pcd2normal(xyz):  # GR/:23-38
-    hd, wd, _ = xyz.shape
-    bottom_point = xyz[..., 2:hd, 1:wd - 1, :]
-    top_point = xyz[..., 0:hd - 2, 1:wd - 1, :]
-    right_point = xyz[..., 1:hd - 1, 2:wd, :]
-    left_point = xyz[..., 1:hd - 1, 0:wd - 2, :]
-    left_to_right = right_point - left_point
-    bottom_to_top = top_point - bottom_point
-    xyz_normal = torch.cross(left_to_right, bottom_to_top, dim=-1)
-    xyz_normal = torch.nn.functional.normalize(xyz_normal, p=2, dim=-1)
-    return torch.nn.functional.pad(xyz_normal.permute(2, 0, 1), (1, 1, 1, 1), mode="constant").permute(1, 2, 0)
+def depth_pcd2normal(points):
+    """Pseudo normals of an [H,W,3] point map: normalised cross product of the horizontal and vertical central differences,
+    zero on the one-pixel border (the computation of GR/:23-38)."""
+    H, W, _ = points.shape
+    horiz = points[1:H - 1, 2:W] - points[1:H - 1, 0:W - 2]     # right - left
+    vert = points[0:H - 2, 1:W - 1] - points[2:H, 1:W - 1]      # top - bottom
+    n = torch.nn.functional.normalize(torch.cross(horiz, vert, dim=-1), p=2, dim=-1)
+    out = torch.zeros_like(points)
+    if H > 2 and W > 2:
+        out[1:H - 1, 1:W - 1] = n
+    return out
 
 
 def normal_image(normal_img_chw):  # GR/:168-176
