@@ -446,6 +446,11 @@ class PreparedForward:
         return ticket
 
 
+def _cpu_copy(items):
+    """CPU clones of the tensors in ``items`` (the reference's cpu_deep_copy_tuple, __init__.py:16-18)."""
+    return tuple(x.detach().cpu().clone() if isinstance(x, torch.Tensor) else x for x in items)
+
+
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings)
 
@@ -455,8 +460,22 @@ class _RasterizeGaussians(torch.autograd.Function):
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
         need_bw = any(isinstance(t, torch.Tensor) and t.requires_grad for t in
                       (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
-        color, depth, alpha, radii, (geom, binning, image), ticket, keep = forward_raw(
-            means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings, for_backward=need_bw)
+        if raster_settings.debug:
+            # reference debug behaviour (__init__.py:83-90): keep a CPU copy of the arguments and dump it if the call fails
+            cpu_args = _cpu_copy((raster_settings.bg, means3D, colors_precomp, opacities, scales, rotations, raster_settings.scale_modifier,
+                                  cov3Ds_precomp, raster_settings.viewmatrix, raster_settings.projmatrix, raster_settings.tanfovx,
+                                  raster_settings.tanfovy, raster_settings.image_height, raster_settings.image_width, sh,
+                                  raster_settings.sh_degree, raster_settings.campos, raster_settings.prefiltered, raster_settings.debug))
+            try:
+                res = forward_raw(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings,
+                                  for_backward=need_bw)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        else:
+            res = forward_raw(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings, for_backward=need_bw)
+        color, depth, alpha, radii, (geom, binning, image), ticket, keep = res
         ctx.raster_settings = raster_settings
         ctx.ticket = ticket
         ctx.has = (sh.numel() != 0, colors_precomp.numel() != 0, scales.numel() != 0, cov3Ds_precomp.numel() != 0)
@@ -507,6 +526,10 @@ class _RasterizeGaussians(torch.autograd.Function):
                                 _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations))
             rc = _L.gsr_backward(C.byref(fr), C.byref(ws), _ptr(radii), _ptr(alpha), _ptr(g_color), _ptr(g_depth), _ptr(g_alpha),
                                  C.byref(gr), C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+            if rc != 0 and s.debug:  # reference debug behaviour (__init__.py:135-142)
+                torch.save(_cpu_copy((bg, means3D, radii, colors_precomp, scales, rotations, s.scale_modifier, cov3Ds_precomp, view, proj, s.tanfovx,
+                                      s.tanfovy, g_color, g_depth, g_alpha, sh, s.sh_degree, campos, alpha, s.debug)), "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
             _lib.check(rc, "gsr_backward")
         has_sh, has_col, has_scale, has_cov = ctx.has
         # reference order (__init__.py:146-156): means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, settings

@@ -505,3 +505,20 @@ def test_4k_image_and_sugar_storage_against_reference(dev):
     b = dict(a)
     b["shs"], b["colors_precomp"] = None, extra
     assert torch.equal(res[3], Hh.run_ref(b)["color"]) and torch.equal(res[0], ref["color"])
+
+
+def test_debug_mode_dumps_a_snapshot_on_failure(dev, tmp_path, monkeypatch):
+    """raster_settings.debug: a failing forward leaves snapshot_fw.dump with CPU copies of the arguments (reference __init__.py:83-90)."""
+    from autovfx_b200.rasterizer import GaussianRasterizer
+    monkeypatch.chdir(tmp_path)
+    a = Hh.resolve(Hh.case_inputs("small_sh"), dev)
+    s = Hh.settings_from(a, debug=True)
+    rast = GaussianRasterizer(s)
+    bad_shs = a["shs"][:, :4].contiguous()  # degree 3 needs 16 coefficients
+    with pytest.raises(RuntimeError):
+        rast(a["means3D"], torch.zeros_like(a["means3D"]), a["opacities"], shs=bad_shs, scales=a["scales"], rotations=a["rotations"])
+    dump = torch.load(tmp_path / "snapshot_fw.dump", weights_only=False)
+    assert isinstance(dump, tuple) and len(dump) == 19 and dump[1].shape == a["means3D"].shape and not dump[1].is_cuda
+    # and a correct call in debug mode still works (synchronous error checking after every stage)
+    out = rast(a["means3D"], torch.zeros_like(a["means3D"]), a["opacities"], shs=a["shs"], scales=a["scales"], rotations=a["rotations"])
+    assert torch.equal(out[0], Hh.run_ours(a)["color"])
