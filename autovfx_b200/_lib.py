@@ -31,7 +31,8 @@ class gsr_workspace(C.Structure):
 
 class gsr_counters(C.Structure):
     _fields_ = [("num_rendered", C.c_uint32), ("overflow", C.c_uint32), ("max_tile", C.c_uint32), ("trapped", C.c_uint32),
-                ("num_visible", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("num_visible", C.c_uint32), ("foot_total", C.c_uint32), ("exact_redos", C.c_uint32),
+                ("reserved", C.c_uint32 * 1)]
 
 
 class gsr_grads(C.Structure):
@@ -53,7 +54,8 @@ GSR_FLAG_FOR_BACKWARD = 1
 GSR_FLAG_SORTED_KEYS = 2
 GSR_FLAG_TIGHT_TILES = 4
 GSR_FLAG_REUSE_GEOMETRY = 8
-ABI_VERSION = 2
+GSR_FLAG_EXACT_IMAGES = 16
+ABI_VERSION = 3
 
 EXPORTS = ("gsr_abi_version", "gsr_last_error", "gsr_geom_bytes", "gsr_binning_bytes", "gsr_binning_capacity", "gsr_image_bytes",
            "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_dist2_bytes", "gsr_dist2", "gsr_get_views",

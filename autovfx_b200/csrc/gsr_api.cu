@@ -37,7 +37,7 @@ const char* gsr_last_error(void) { return gsr::last_error(); }
 
 size_t gsr_geom_bytes(int32_t P) { return gsr::GeomLayout((size_t)(P < 0 ? 0 : P)).total; }
 size_t gsr_binning_bytes(size_t capacity) { return gsr::BinLayout(capacity < 1 ? 1 : capacity).total; }
-size_t gsr_binning_capacity(size_t bytes) { return bytes / 12; }
+size_t gsr_binning_capacity(size_t bytes) { return gsr::BinLayout::capacity_of(bytes); }
 size_t gsr_image_bytes(int32_t W, int32_t H) { return gsr::ImageLayout(W < 1 ? 1 : W, H < 1 ? 1 : H).total; }
 
 int gsr_forward(const gsr_frame* frame, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,
@@ -100,7 +100,7 @@ int gsr_get_views(const gsr_workspace* ws, int32_t P, int32_t W, int32_t H, gsr_
     if (!ws || !out) { gsr::set_error("gsr_get_views: null argument"); return GSR_ERR_INVALID; }
     const gsr::GeomLayout gl((size_t)P);
     const gsr::ImageLayout il(W, H);
-    const gsr::BinLayout bl(ws->binning_bytes / 12);
+    const gsr::BinLayout bl(gsr::BinLayout::capacity_of(ws->binning_bytes));
     const char* geo = (const char*)ws->geom; const char* img = (const char*)ws->image; const char* bin = (const char*)ws->binning;
     out->records = (const float*)(geo + gl.records);
     out->cov3D = (const float*)(geo + gl.cov3D);

@@ -541,7 +541,7 @@ int backward_impl(const gsr_frame* f, const gsr_workspace* ws, const int32_t* ra
     const ImageLayout il(f->W, f->H);
     const GeomLayout gl(P);
     if (ws->image_bytes < il.total || ws->geom_bytes < gl.total || !ws->binning) { set_error("gsr_backward: workspace too small"); return GSR_ERR_WORKSPACE; }
-    const BinLayout bl(ws->binning_bytes / 12);
+    const BinLayout bl(BinLayout::capacity_of(ws->binning_bytes));
     char* img = (char*)ws->image; char* geo = (char*)ws->geom; char* bin = (char*)ws->binning;
     const int D = f->D < 0 ? 0 : (f->D > 3 ? 3 : f->D);
 

@@ -13,6 +13,7 @@
 
 #define GSR_TILE 16
 #define GSR_TILE_PIX 256
+#define GSR_FOOTS 8  // warp footprints (8x4 pixels) per tile
 #define GSR_FULL 0xffffffffu
 
 namespace gsr {
@@ -32,7 +33,7 @@ struct GeomLayout {
     }
 };
 struct ImageLayout {
-    size_t counters, tile_count, tile_big, tile_fill, ranges, n_contrib, total;
+    size_t counters, tile_count, tile_big, tile_fill, ranges, foot_ranges, n_contrib, total;
     int gx, gy, tiles;
     __host__ __device__ ImageLayout(int W, int H) {
         gx = (W + GSR_TILE - 1) / GSR_TILE;
@@ -44,20 +45,27 @@ struct ImageLayout {
         tile_big = o;   o = align_up(o + 4 * (size_t)tiles, 256);  // instances of Gaussians touching > 8 tiles
         tile_fill = o;  o = align_up(o + 4 * (size_t)tiles, 256);  // cursor for the latter, written by the scan
         ranges = o;     o = align_up(o + 8 * (size_t)tiles, 256);
+        foot_ranges = o; o = align_up(o + 8 * (size_t)GSR_FOOTS * tiles, 256);  // {start, count} of every warp footprint's list
         n_contrib = o;  o = align_up(o + 4 * (size_t)W * H, 256);
         total = o + 256;
     }
     // bytes [0, zero_bytes) are cleared at the start of every frame (counters + tile_count + tile_big)
     __host__ __device__ size_t zero_bytes() const { return tile_fill; }
 };
+// bytes of binning workspace per instance of capacity: 8 (pair) + 4 (point_list) + 4 * GSR_FOOT_FACTOR (footprint lists)
+#define GSR_FOOT_FACTOR 2
+#define GSR_BIN_BYTES (12 + 4 * GSR_FOOT_FACTOR)
 struct BinLayout {
-    size_t pairs, point_list, total, capacity;
+    size_t pairs, point_list, foot_list, foot_capacity, total, capacity;
     __host__ __device__ explicit BinLayout(size_t cap) {
         capacity = cap;
         pairs = 0;
         point_list = 8 * cap;
-        total = 12 * cap;
+        foot_list = 12 * cap;             // per-footprint survivor lists, allocated by k_sort_tiles from one cursor
+        foot_capacity = GSR_FOOT_FACTOR * cap;
+        total = (size_t)GSR_BIN_BYTES * cap;
     }
+    __host__ __device__ static size_t capacity_of(size_t bytes) { return bytes / GSR_BIN_BYTES; }
 };
 
 // ---- camera block staged in shared memory ------------------------------------------------------------
@@ -191,6 +199,44 @@ __device__ __forceinline__ bool tile_may_touch(float px, float py, float a, floa
     return box_may_touch(px - ((float)(tx * GSR_TILE) + 7.5f), py - ((float)(ty * GSR_TILE) + 7.5f), a, b, c, tau, 7.5f, 7.5f);
 }
 
+// All eight warp footprints of tile (tx, ty) at once, for one splat: bit w of the result is set if footprint w (origin
+// ((w & 1) * 8, (w >> 1) * 4) inside the tile, 8x4 pixels) may be touched — the same exact box minimum as box_may_touch, with
+// the per-column / per-row parts of the two face parabolas shared between the footprints and one (larger, hence still
+// conservative) rounding margin for the whole tile.
+__device__ __forceinline__ uint32_t tile_foot_mask(float px, float py, float a, float b, float c, float tau, int tx, int ty) {
+    const float dxt = px - (float)(tx * GSR_TILE), dyt = py - (float)(ty * GSR_TILE);
+    const bool pd = a > 0.f && c > 0.f;
+    const float um = fabsf(dxt - 7.5f) + 7.5f, vm = fabsf(dyt - 7.5f) + 7.5f;
+    const float mag = a * um * um + c * vm * vm + 2.f * fabsf(b) * um * vm;
+    const float thr = 2.f * (tau + 1.0e-3f + 4.0e-6f * mag);
+    const float nbrc = -b * rcp_approx(c), nbra = -b * rcp_approx(a), b2 = 2.f * b;
+    float dxl[2], dxh[2], Auc[2], Buc[2], vs0[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const float dx = dxt - (FOOT_HX + 8.f * i);
+        const float uc = dx - fminf(fmaxf(dx, -FOOT_HX), FOOT_HX);
+        dxl[i] = dx - FOOT_HX; dxh[i] = dx + FOOT_HX;
+        Auc[i] = a * uc * uc; Buc[i] = b2 * uc; vs0[i] = nbrc * uc;
+    }
+    uint32_t mask = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float dy = dyt - (FOOT_HY + 4.f * j);
+        const float vc = dy - fminf(fmaxf(dy, -FOOT_HY), FOOT_HY);
+        const float dyl = dy - FOOT_HY, dyh = dy + FOOT_HY;
+        const float Cvc = c * vc * vc, Bvc = b2 * vc, us0 = nbra * vc;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const float vs = fminf(fmaxf(vs0[i], dyl), dyh);
+            const float us = fminf(fmaxf(us0, dxl[i]), dxh[i]);
+            const float q1 = Auc[i] + vs * (Buc[i] + c * vs);
+            const float q2 = Cvc + us * (Bvc + a * us);
+            if (!(pd && fminf(q1, q2) > thr)) mask |= 1u << (2 * j + i);
+        }
+    }
+    return mask;
+}
+
 // SH basis constants (auxiliary.h:22-39)
 constexpr float SH_C0 = 0.28209479177387814f;
 constexpr float SH_C1 = 0.4886025119029199f;
@@ -199,6 +245,16 @@ constexpr float SH_C2_0 = 1.0925484305920792f, SH_C2_1 = -1.0925484305920792f, S
 constexpr float SH_C3_0 = -0.5900435899266435f, SH_C3_1 = 2.890611442640554f, SH_C3_2 = -0.4570457994644658f,
                            SH_C3_3 = 0.3731763325901154f, SH_C3_4 = -0.4570457994644658f, SH_C3_5 = 1.445305721320277f,
                            SH_C3_6 = -0.5900435899266435f;
+
+// arguments of the blend kernels (gsr_forward.cu builds them, gsr_blend.cu consumes them)
+struct BlendArgs {
+    const uint2* ranges; const uint32_t* point_list; const float4* records; const float* extra;
+    int W, H, gx, gy; const float* bg; float *out_color, *out_depth, *out_alpha, *out_extra; uint32_t* n_contrib;
+    gsr_counters* counters;
+    const uint2* foot_ranges; const uint32_t* foot_list;
+    int exact;  // GSR_FLAG_EXACT_IMAGES
+};
+void launch_blend_lists(const BlendArgs& a, cudaStream_t st);
 
 void set_error(const char* fmt, ...);
 const char* last_error();

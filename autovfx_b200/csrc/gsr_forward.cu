@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "gsr_common.cuh"
+#include "gsr_packed.cuh"
 
 namespace gsr {
 
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_preprocess(const PreParams p
             float4* rec = p.records + 3 * (size_t)idx;
             rec[0] = make_float4(px, py, con_a, con_b);
             rec[1] = make_float4(con_c, opacity, depth, tau);
-            rec[2] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+            rec[2] = make_float4(rgb[0], rgb[1], rgb[2], log2f(opacity));  // .w: log2(opacity) for the default (fast-alpha) blend
             if (rect_n <= 8) {
                 uint4* rr = reinterpret_cast<uint4*>(p.ranks + 8 * (size_t)idx);
                 rr[0] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
@@ -660,17 +661,100 @@ __device__ void sort_bucket(const unsigned long long* __restrict__ g, uint32_t n
     }
 }
 
+// ---- per-footprint survivor lists ---------------------------------------------------------------------------
+// After the sort, every entry of the tile is tested ONCE against the tile's eight 8x4-pixel warp footprints (one thread
+// per entry, tile_foot_mask) and the survivors of footprint f are written, in list order, to a compact list that the
+// blend warp owning that footprint walks on its own — the blend kernel has no block-level staging, barrier or cull left.
+// Lists are carved from one global cursor (counters->foot_total), one atomic per tile; foot_ranges[tile*8+f] = {start, count}.
+// A list entry is the Gaussian id, or (store_pos, when a backward pass follows) the absolute position in point_list.
+struct FootArgs {
+    const float4* records;
+    uint32_t* foot_list;
+    uint2* foot_ranges;
+    gsr_counters* counters;
+    uint32_t foot_cap;
+    int store_pos;
+    int gx;
+};
+// keys: the n sorted (depth bits << 32 | id) of the tile (shared or global memory); mask8: n bytes of scratch (shared
+// memory), or nullptr to park the masks in park32[] (global, 4 bytes per entry — the large-tile path).
+__device__ void foot_lists(const FootArgs& fa, const unsigned long long* keys, uint32_t n, uint32_t list_base, int tile,
+                           uint8_t* mask8, uint32_t* park32) {
+    __shared__ uint32_t f_cnt[GSR_FOOTS], f_off[GSR_FOOTS];
+    __shared__ int f_ok;
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int ty = tile / fa.gx, tx = tile - ty * fa.gx;
+    if (t < GSR_FOOTS) f_cnt[t] = 0;
+    __syncthreads();
+    uint32_t acc = 0;  // lane f (< 8) of every warp counts footprint f
+    for (uint32_t base = warp * 32; base < n; base += SORT_THREADS) {
+        const uint32_t i = base + lane;
+        uint32_t m = 0;
+        if (i < n) {
+            const uint32_t id = (uint32_t)keys[i];
+            const float4 r0 = fa.records[3 * (size_t)id], r1 = fa.records[3 * (size_t)id + 1];
+            m = tile_foot_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.w, tx, ty);
+            if (mask8) mask8[i] = (uint8_t)m; else park32[i] = m;
+        }
+#pragma unroll
+        for (int f = 0; f < GSR_FOOTS; f++) {
+            const uint32_t c = __popc(__ballot_sync(GSR_FULL, (m >> f) & 1u));
+            if (lane == (uint32_t)f) acc += c;
+        }
+    }
+    if (lane < GSR_FOOTS && acc) atomicAdd(&f_cnt[lane], acc);
+    __syncthreads();
+    if (t == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int f = 0; f < GSR_FOOTS; f++) total += f_cnt[f];
+        uint32_t start = 0;
+        int ok = 1;
+        if (total) {
+            start = atomicAdd(&fa.counters->foot_total, total);
+            if (start + total > fa.foot_cap || start + total < start) { ok = 0; atomicExch(&fa.counters->overflow, 1u); }
+        }
+        f_ok = ok;
+        uint2* fr = fa.foot_ranges + (size_t)tile * GSR_FOOTS;
+#pragma unroll
+        for (int f = 0; f < GSR_FOOTS; f++) {
+            f_off[f] = start;
+            fr[f] = ok ? make_uint2(start, f_cnt[f]) : make_uint2(0u, 0u);
+            start += f_cnt[f];
+        }
+    }
+    __syncthreads();
+    if (f_ok && warp < GSR_FOOTS && f_cnt[warp]) {  // warp f compacts footprint f (SORT_THREADS / 32 == GSR_FOOTS)
+        uint32_t run = f_off[warp];
+        const uint32_t lt = (1u << lane) - 1u;
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t i = base + lane;
+            const uint32_t m = i < n ? (mask8 ? (uint32_t)mask8[i] : park32[i]) : 0u;
+            const bool keep = (m >> warp) & 1u;
+            const uint32_t bal = __ballot_sync(GSR_FULL, keep);
+            if (keep) fa.foot_list[run + __popc(bal & lt)] = fa.store_pos ? list_base + i : (uint32_t)keys[i];
+            run += __popc(bal);
+        }
+    }
+}
+static_assert(SORT_THREADS / 32 == GSR_FOOTS, "one sort warp per footprint");
+
 // Sorts the bucket of one tile (pairs[rg.x..rg.y) by (depth bits, id)) and writes the ids to point_list.
 // s: SORT_CAP u64 of shared memory, hist: SORT_BUCKETS+1 u32.  Block-wide (SORT_THREADS threads), ends without a barrier.
 __device__ void sort_tile(const uint2 rg, unsigned long long* __restrict__ pairs, uint32_t* __restrict__ point_list, int keep_pairs,
-                          unsigned long long* s, uint32_t* hist) {
+                          unsigned long long* s, uint32_t* hist, const FootArgs& fa, int tile) {
     const uint32_t n = rg.y - rg.x;
-    if (n == 0) return;
+    const uint32_t tid = threadIdx.x;
+    if (n == 0) {
+        if (tid < GSR_FOOTS) fa.foot_ranges[(size_t)tile * GSR_FOOTS + tid] = make_uint2(0u, 0u);
+        return;
+    }
     unsigned long long* g = pairs + rg.x;
     uint32_t* out = point_list + rg.x;
-    const uint32_t tid = threadIdx.x;
     if (n <= SORT_CAP) {
         sort_bucket(g, n, out, keep_pairs ? g : nullptr, s, hist);
+        __syncthreads();  // the histogram is dead: its storage holds the footprint masks
+        foot_lists(fa, s, n, rg.x, tile, reinterpret_cast<uint8_t*>(hist), nullptr);
         return;
     }
     // ---- large tile: chunks sorted in shared memory, cross-chunk steps in global (L2) memory ----
@@ -703,17 +787,20 @@ __device__ void sort_tile(const uint2 rg, unsigned long long* __restrict__ pairs
             __syncthreads();
         }
     }
+    __syncthreads();
+    foot_lists(fa, g, n, rg.x, tile, nullptr, out);  // masks parked in point_list until the ids are written
+    __syncthreads();
     for (uint32_t i = tid; i < n; i += SORT_THREADS) out[i] = (uint32_t)g[i];
 }
 
 // stand-alone per-tile sort kernel (fusing it into the blend prologue was measured and dropped, profiles/r01_experiments.md)
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __restrict__ ranges, unsigned long long* __restrict__ pairs,
                                                              uint32_t* __restrict__ point_list,
-                                                             const gsr_counters* __restrict__ counters, int keep_pairs) {
-    if (counters->overflow) return;
+                                                             const gsr_counters* __restrict__ counters, int keep_pairs, const FootArgs fa) {
+    if (counters->overflow) return;  // set by k_tile_scan, before this kernel started
     __shared__ unsigned long long s[SORT_CAP];
     __shared__ uint32_t hist[SORT_BUCKETS + 1];
-    sort_tile(ranges[blockIdx.x], pairs, point_list, keep_pairs, s, hist);
+    sort_tile(ranges[blockIdx.x], pairs, point_list, keep_pairs, s, hist, fa, (int)blockIdx.x);
 }
 
 // =====================================================================================================
@@ -740,45 +827,6 @@ struct BlendCfg {
 };
 static_assert(BlendCfg<0>::SMEM <= 48 * 1024, "k_blend<.,0> must fit the default dynamic shared memory limit");
 
-__device__ __forceinline__ float4 lds128(uint32_t a) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
-__device__ __forceinline__ float2 lds64(uint32_t a) {
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
-    return v;
-}
-
-// Blackwell packed fp32: one FFMA2 / FMUL2 / FADD2 performs two IEEE round-to-nearest operations, one per 32-bit half
-// of a 64-bit register pair.  The blend evaluates TWO queued splats per iteration in the two halves.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
 // NX  : extra colour channels `extra[P,NX]` accumulated with the same per-splat weights into `out_extra[NX,H,W]`
 //       (+ T_final * bg like the colour image) — what a second rasterizer pass with colors_precomp = extra would
 //       return (gaussian_renderer/__init__.py:151-185), without re-running projection, binning, sort and the alpha math.
@@ -1000,8 +1048,10 @@ __global__ void __launch_bounds__(256) k_recolor(int P, const int* __restrict__ 
                                                  float4* __restrict__ records) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P || radii[idx] <= 0) return;
-    records[3 * (size_t)idx + 2] = make_float4(colors_precomp[3 * (size_t)idx], colors_precomp[3 * (size_t)idx + 1],
-                                               colors_precomp[3 * (size_t)idx + 2], 0.0f);
+    float* c = reinterpret_cast<float*>(records + 3 * (size_t)idx + 2);  // .w (log2 opacity) stays
+    c[0] = colors_precomp[3 * (size_t)idx];
+    c[1] = colors_precomp[3 * (size_t)idx + 1];
+    c[2] = colors_precomp[3 * (size_t)idx + 2];
 }
 
 // =====================================================================================================
@@ -1074,11 +1124,6 @@ static void launch_pre(bool vec, bool win, const PreParams& pp, cudaStream_t st)
     else k_preprocess<DEG, false, false><<<grid, PRE_THREADS, 0, st>>>(pp);
 }
 
-struct BlendArgs {
-    const uint2* ranges; const uint32_t* point_list; const float4* records; const float* extra;
-    int W, H, gx, gy; const float* bg; float *out_color, *out_depth, *out_alpha, *out_extra; uint32_t* n_contrib;
-    const gsr_counters* counters;
-};
 template <int NX, bool NC>
 static void launch_blend_t(const BlendArgs& a, cudaStream_t st) {
     typedef BlendCfg<NX> Cfg;
@@ -1096,7 +1141,13 @@ static void launch_blend_t(const BlendArgs& a, cudaStream_t st) {
 }
 // The 6-channel variant runs at 70 registers / 3 CTAs per SM; holding it to 64 registers / 4 CTAs (shorter queues, 92 B of
 // spills) was measured slower: 780 vs 862 product frames/s (profiles/r01_experiments.md).
+static int blend_legacy() {  // GSR_BLEND=legacy: the round-1 tile-staged blend (bit-exact only), kept for A/B measurements
+    static int m = -1;
+    if (m < 0) { const char* e = getenv("GSR_BLEND"); m = (e && strcmp(e, "legacy") == 0) ? 1 : 0; }
+    return m;
+}
 static void launch_blend(const BlendArgs& a, cudaStream_t st) {
+    if (!blend_legacy()) { launch_blend_lists(a, st); return; }
     if (a.extra) { if (a.n_contrib) launch_blend_t<3, true>(a, st); else launch_blend_t<3, false>(a, st); }
     else         { if (a.n_contrib) launch_blend_t<0, true>(a, st); else launch_blend_t<0, false>(a, st); }
 }
@@ -1136,7 +1187,7 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     if (f->shs && (D + 1) * (D + 1) > f->M) { set_error("gsr_forward: sh degree %d needs %d coefficients, shs has M=%d", D, (D + 1) * (D + 1), f->M); return GSR_ERR_INVALID; }
     const GeomLayout gl((size_t)f->P);
     if (!ws->geom || ws->geom_bytes < gl.total) { set_error("gsr_forward: geometry workspace too small (%zu < %zu)", ws->geom_bytes, gl.total); return GSR_ERR_WORKSPACE; }
-    const size_t cap = ws->binning ? ws->binning_bytes / 12 : 0;
+    const size_t cap = ws->binning ? BinLayout::capacity_of(ws->binning_bytes) : 0;
     if (cap < 1) { set_error("gsr_forward: binning workspace too small"); return GSR_ERR_WORKSPACE; }
     const BinLayout bl(cap);
     char* geo = (char*)ws->geom;
@@ -1150,7 +1201,8 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
         int rc0 = check_launch("gsr_forward/recolor", debug, st);
         if (rc0) return rc0;
         BlendArgs ba{(const uint2*)(img + il.ranges), (const uint32_t*)(bin + bl.point_list), (const float4*)(geo + gl.records), extra_colors,
-                     f->W, f->H, il.gx, il.gy, f->bg, out_color, out_depth, out_alpha, out_extra, nullptr, counters};
+                     f->W, f->H, il.gx, il.gy, f->bg, out_color, out_depth, out_alpha, out_extra, nullptr, counters,
+                     (const uint2*)(img + il.foot_ranges), (const uint32_t*)(bin + bl.foot_list), (flags & GSR_FLAG_EXACT_IMAGES) ? 1 : 0};
         launch_blend(ba, st);
         return check_launch("gsr_forward/blend(reuse)", debug, st);
     }
@@ -1205,11 +1257,14 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
 
     const int keep_pairs = (flags & GSR_FLAG_SORTED_KEYS) ? 1 : 0;
     uint32_t* n_contrib = (flags & GSR_FLAG_FOR_BACKWARD) ? (uint32_t*)(img + il.n_contrib) : nullptr;
-    k_sort_tiles<<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters, keep_pairs);
+    FootArgs fa{pp.records, (uint32_t*)(bin + bl.foot_list), (uint2*)(img + il.foot_ranges), counters,
+                (uint32_t)(bl.foot_capacity > 0xffffffffull ? 0xffffffffull : bl.foot_capacity), n_contrib ? 1 : 0, il.gx};
+    k_sort_tiles<<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters, keep_pairs, fa);
     prof_mark(4, st);
     if ((rc = check_launch("gsr_forward/sort", debug, st))) return rc;
     BlendArgs ba{ranges, (const uint32_t*)(bin + bl.point_list), pp.records, extra_colors, f->W, f->H, il.gx, il.gy, f->bg,
-                 out_color, out_depth, out_alpha, out_extra, n_contrib, counters};
+                 out_color, out_depth, out_alpha, out_extra, n_contrib, counters,
+                 (const uint2*)(img + il.foot_ranges), (const uint32_t*)(bin + bl.foot_list), (flags & GSR_FLAG_EXACT_IMAGES) ? 1 : 0};
     launch_blend(ba, st);
     prof_mark(5, st);
     if (g_prof.on) {

@@ -31,7 +31,7 @@ from . import _lib
 from ._lib import lib as _L
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "set_sync_mode", "get_sync_mode",
-           "set_tight_tiles", "get_tight_tiles", "set_geometry_reuse",
+           "set_tight_tiles", "get_tight_tiles", "set_geometry_reuse", "set_exact_images", "get_exact_images",
            "last_frame_stats", "FrameTicket", "forward_raw", "forward_multi", "PreparedForward", "debug_views",
            "invalidate_geometry_cache"]
 
@@ -71,6 +71,22 @@ def get_sync_mode() -> str:
 
 _TIGHT_TILES = False
 _REUSE_GEOMETRY = True
+_EXACT_IMAGES = False
+
+
+def set_exact_images(on: bool) -> None:
+    """Default off.  On: the blend uses the reference's own fp32 instruction sequence (GSR_FLAG_EXACT_IMAGES) and
+    color / depth / alpha are bit-identical to the reference's CUDA rasterizer.  Off: alpha = ex2.approx(power*log2e +
+    log2(opacity)); every skip / termination decision inside the approximation's error band is re-done exactly, so the
+    images differ from the exact ones by ~1e-6 relative (the requirement is 1e-4 max abs) and radii / per-tile lists /
+    n_contrib are unchanged."""
+    global _EXACT_IMAGES
+    _EXACT_IMAGES = bool(on)
+
+
+def get_exact_images() -> bool:
+    return _EXACT_IMAGES
+
 
 
 def set_geometry_reuse(on: bool) -> None:
@@ -111,13 +127,20 @@ class FrameTicket:
         self.event.synchronize()
         c = self.slot
         return {"num_rendered": int(c[0]), "overflow": int(c[1]), "max_tile": int(c[2]), "trapped": int(c[3]),
-                "num_visible": int(c[4]), "capacity": int(self.capacity)}
+                "num_visible": int(c[4]), "foot_total": int(c[5]) & 0xffffffff, "exact_redos": int(c[6]),
+                "capacity": int(self.capacity)}
 
     def ok(self) -> bool:
         s = self.stats()
         if s["overflow"]:
-            self._state.grow(int(s["num_rendered"]))
+            self._state.grow(needed_capacity(s))
         return not s["overflow"]
+
+
+def needed_capacity(stats: Dict[str, int]) -> int:
+    """Binning capacity (instances) a frame with these counters needs: R instances, and footprint lists of at most
+    GSR_FOOT_FACTOR (= 2) entries per instance of capacity."""
+    return max(int(stats["num_rendered"]), (int(stats["foot_total"]) + 1) // 2)
 
 
 class _DeviceState:
@@ -235,7 +258,8 @@ def _fill_frame(fr: _lib.gsr_frame, P, D, M, W, H, settings, bg, means3D, shs, c
 
 def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, settings: GaussianRasterizationSettings,
                 for_backward: bool = False, sorted_keys: bool = False, sync: Optional[bool] = None, out=None,
-                tight: Optional[bool] = None, extra: Optional[torch.Tensor] = None, extra_out: Optional[torch.Tensor] = None):
+                tight: Optional[bool] = None, extra: Optional[torch.Tensor] = None, extra_out: Optional[torch.Tensor] = None,
+                exact: Optional[bool] = None):
     """One rasterizer forward through the C ABI.  Returns (color, depth, alpha, radii, workspaces, ticket, keepalive).
     ``workspaces`` = (geom, binning, image) byte tensors; fresh allocations when ``for_backward`` (they must outlive
     the call), otherwise per-(device, stream) cached buffers.  ``out`` optionally supplies preallocated
@@ -275,6 +299,9 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
         flags = (_lib.GSR_FLAG_FOR_BACKWARD if for_backward else 0) | (_lib.GSR_FLAG_SORTED_KEYS if sorted_keys else 0)
         if _TIGHT_TILES if tight is None else tight:
             flags |= _lib.GSR_FLAG_TIGHT_TILES
+        use_exact = _EXACT_IMAGES if exact is None else bool(exact)
+        if use_exact:
+            flags |= _lib.GSR_FLAG_EXACT_IMAGES
         fr = _lib.gsr_frame()
         _fill_frame(fr, P, int(settings.sh_degree), M, W, H, settings, bg, means3D, shs, colors_precomp, opacities, scales, rotations,
                     cov3D_precomp, view, proj, campos)
@@ -290,7 +317,7 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
             return None if t is None else (t.data_ptr(), t._version, tuple(t.shape))
         gkey = (tk(means3D), tk(opacities), tk(scales), tk(rotations), tk(cov3D_precomp), tk(view), tk(proj), tk(campos), W, H,
                 float(settings.tanfovx), float(settings.tanfovy), float(settings.scale_modifier), bool(settings.prefiltered),
-                bool(use_tight), geom.data_ptr(), image.data_ptr())
+                bool(use_tight), bool(use_exact), geom.data_ptr(), image.data_ptr())
         cached = st.geom_cache.get(stream.cuda_stream)
         if (_REUSE_GEOMETRY and not for_backward and not sorted_keys and colors_precomp is not None and P > 0 and cached is not None
                 and cached[0] == gkey):
@@ -336,7 +363,7 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
                 raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")  # auxiliary.h:158
             if not s["overflow"]:
                 break
-            st.grow(s["num_rendered"])  # rare: first frames of a new scene; re-run with a larger binning buffer
+            st.grow(needed_capacity(s))  # rare: first frames of a new scene; re-run with a larger binning buffer
         if not for_backward and P > 0:
             # remember which geometry the shared workspaces now hold (tensors kept alive so their storage cannot be recycled)
             st.geom_cache[stream.cuda_stream] = (gkey, (means3D, opacities, scales, rotations, cov3D_precomp, view, proj, campos), radii, binning)
@@ -346,7 +373,7 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
 
 def forward_multi(means3D, shs, colors_precomp, extra_colors, opacities, scales, rotations, cov3D_precomp,
                   settings: GaussianRasterizationSettings, sync: Optional[bool] = None, out=None, extra_out=None,
-                  tight: Optional[bool] = None):
+                  tight: Optional[bool] = None, exact: Optional[bool] = None):
     """Both rasterizer passes of one product frame in ONE pass (forward only): ``(color, depth, alpha, extra_image, radii,
     ticket)`` where ``extra_image`` [3,H,W] is bit-identical to the colour image a second
     ``GaussianRasterizer(...)(colors_precomp=extra_colors, ...)`` call would return
@@ -356,7 +383,7 @@ def forward_multi(means3D, shs, colors_precomp, extra_colors, opacities, scales,
         extra_out = torch.empty((3, H, W), dtype=torch.float32, device=means3D.device)
     color, depth, alpha, radii, _ws, ticket, _keep = forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
                                                                settings, sync=sync, out=out, tight=tight, extra=extra_colors,
-                                                               extra_out=extra_out)
+                                                               extra_out=extra_out, exact=exact)
     return color, depth, alpha, extra_out, radii, ticket
 
 
@@ -370,7 +397,7 @@ class PreparedForward:
 
     def __init__(self, means3D, shs, opacities, scales, rotations, cam: torch.Tensor, W: int, H: int, bg: torch.Tensor, sh_degree: int,
                  scale_modifier: float, out, extra: Optional[torch.Tensor] = None, extra_out: Optional[torch.Tensor] = None,
-                 tight: Optional[bool] = None):
+                 tight: Optional[bool] = None, exact: Optional[bool] = None):
         device = means3D.device
         self.device, self.st = device, _state(device)
         self.P, self.W, self.H = int(means3D.shape[0]), int(W), int(H)
@@ -398,6 +425,8 @@ class PreparedForward:
         self.extra_ptrs = (_ptr(extra) if self.P > 0 else None, _ptr(extra_out) if extra is not None and self.P > 0 else None)
         self.extra_out = extra_out
         self.flags = _lib.GSR_FLAG_TIGHT_TILES if (_TIGHT_TILES if tight is None else tight) else 0
+        if _EXACT_IMAGES if exact is None else exact:
+            self.flags |= _lib.GSR_FLAG_EXACT_IMAGES
         self._cap = -1
         self.ws = None
         self._bufs = None

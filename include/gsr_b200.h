@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GSR_ABI_VERSION 2
+#define GSR_ABI_VERSION 3
 
 enum {
     GSR_OK = 0,
@@ -60,6 +60,12 @@ enum {
     GSR_FLAG_REUSE_GEOMETRY = 8, /* second pass of a frame: the workspaces still hold the projection + binning of the previous
                                   gsr_forward on the SAME geometry / camera / image size; only colors_precomp is re-read and the
                                   blend re-run.  `radii` must point to the radii written by that previous call (input). */
+    GSR_FLAG_EXACT_IMAGES = 16, /* blend with the reference's own fp32 instruction sequence (expf, separate opacity multiply):
+                                  color / depth / alpha are bit-identical to the reference's CUDA.  Default (flag clear): alpha =
+                                  ex2.approx(power * log2e + log2(opacity)); every skip / termination decision that falls inside
+                                  the approximation's error band is detected and that warp's pixels are re-blended exactly, so
+                                  the images differ from the exact ones by ~1e-6 relative (requirement: 1e-4 max abs) and
+                                  n_contrib / all integer outputs are unchanged. */
 };
 
 /* One rasterizer invocation = the argument list of Rasterizer::forward (DGR/cuda_rasterizer/rasterizer.h:33-58). */
@@ -104,7 +110,9 @@ typedef struct gsr_counters {
     uint32_t max_tile;     /* longest per-tile list                                               */
     uint32_t trapped;      /* 1 if prefiltered was set and a point was near-culled                 */
     uint32_t num_visible;  /* Gaussians with radii > 0                                             */
-    uint32_t reserved[3];
+    uint32_t foot_total;   /* entries of the per-footprint survivor lists (<= 2 * capacity, else overflow) */
+    uint32_t exact_redos;  /* warps whose pixels were re-blended exactly (default image mode)       */
+    uint32_t reserved[1];
 } gsr_counters;
 
 size_t gsr_geom_bytes(int32_t P);

@@ -13,6 +13,16 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True, params=["exact"])
+def _image_mode(request):
+    """These tests compare images bit for bit with the compiled reference: run them with GSR_FLAG_EXACT_IMAGES.  The default
+    (fast-alpha) blend is compared with the exact one in tests/test_gpu_fast_blend.py."""
+    from autovfx_b200 import rasterizer as R
+    R.set_exact_images(True)
+    yield
+    R.set_exact_images(False)
+
+
 def _to(d, dev=DEV):
     return {k: v.to(dev) for k, v in d.items()}
 

@@ -79,8 +79,12 @@ def test_forward_bit_exact_vs_compiled_reference(dev, name):
     assert torch.equal(rec[vis][:, 0:2], rs["means2D"][vis])
     assert torch.equal(rec[vis][:, 6], rs["depths"][vis])
     assert torch.equal(rec[vis][:, 2:5].contiguous().view(torch.int32), rs["conic_opacity"][vis][:, 0:3].contiguous().view(torch.int32))
+    Hh.assert_images_close(ours, ref)  # default blend (ex2.approx alpha, guarded decisions)
+    nc_fast = v["n_contrib"].clone()
+    exact = Hh.run_ours(a, for_backward=True, exact=True)
     for k in ("color", "depth", "alpha"):
-        assert Hh.maxabs(ours[k], ref[k]) <= 1e-5, k
+        assert torch.equal(exact[k], ref[k]), k  # GSR_FLAG_EXACT_IMAGES: bit-identical images
+    assert torch.equal(exact["views"]["n_contrib"], nc_fast)
 
 
 @pytest.mark.parametrize("path", GOLDEN or [None])
@@ -96,8 +100,10 @@ def test_forward_and_backward_match_golden(dev, path):
     assert np.array_equal(ours["views"]["point_list"][:R].cpu().numpy(), gold["point_list"])
     assert np.array_equal(ours["views"]["ranges"].cpu().numpy().reshape(-1), gold["ranges"].reshape(-1))
     assert np.array_equal(ours["views"]["n_contrib"].cpu().numpy(), gold["n_contrib"])
+    Hh.assert_images_close(ours, gold)
+    exact = Hh.run_ours(a, for_backward=True, exact=True)
     for k in ("color", "depth", "alpha"):
-        assert Hh.maxabs(ours[k], gold[k]) <= 1e-5, k
+        assert np.array_equal(exact[k].cpu().numpy().reshape(gold[k].shape), gold[k]), k
     if "dL_dmeans3D" in gold:
         dc, dd, da = Hh.image_grads(a, device=dev)
         _, g = Hh.ours_backward(a, dc, dd, da)
@@ -186,8 +192,14 @@ def test_full_size_3m_1080p_properties_and_reference(dev, scene3m):
         rs = ref_cuda.state(dev)
         assert torch.equal(o2["radii"], ref["radii"]) and ref["num_rendered"] == R
         assert torch.equal(pl1, rs["point_list"]) and torch.equal(o2["views"]["ranges"], rs["ranges"])
+        Hh.assert_images_close(o2, ref)
+        nc_fast = o2["views"]["n_contrib"].clone()
+        o3 = Hh.run_ours(a, for_backward=True, debug=False, exact=True)
         for k in ("color", "depth", "alpha"):
-            assert Hh.maxabs(o2[k], ref[k]) <= IMG_TOL, k
+            assert torch.equal(o3[k], ref[k]), k
+        assert torch.equal(o3["views"]["n_contrib"], nc_fast) and torch.equal(nc_fast, rs["n_contrib"])
+        # the default mode's repair path ran on a small fraction of the 65,280 warps
+        assert 0 < o2["stats"]["exact_redos"] < 6000 and o3["stats"]["exact_redos"] == 0
 
 
 def test_p_zero_returns_zero_images(dev):
@@ -405,10 +417,11 @@ def test_degenerate_image_sizes_match_reference(dev, W, H):
     case = Hh.case_inputs("small_sh")
     case["cam"] = scene.lookat_camera((0.3, -3.0, 0.4), (0, 0, 0), W, H, 55.0)
     a = Hh.resolve(case, dev)
-    ours = Hh.run_ours(a, for_backward=True)
+    ours = Hh.run_ours(a, for_backward=True, exact=True)
     ref = Hh.run_ref(a)
     for k in ("color", "depth", "alpha", "radii"):
         assert torch.equal(ours[k], ref[k]), k
+    Hh.assert_images_close(Hh.run_ours(a, for_backward=True), ref)
     dc, dd, da = Hh.image_grads(a, device=dev)
     _, g = Hh.ours_backward(a, dc, dd, da)
     assert all(torch.isfinite(v).all() for v in g.values() if v is not None)
@@ -488,9 +501,12 @@ def test_4k_image_and_sugar_storage_against_reference(dev):
                                   opacity_mean=0.0, opacity_std=2.0, sh_degree=4)
     cam = scene.lookat_camera((3.0, -5.0, 2.0), (0, 0, 0), 3840, 2160, 60.0)
     a = Hh.resolve(dict(g=g, cam=cam, sh_degree=3, bg=(0.1, 0.2, 0.3), scale_modifier=1.0), dev)
-    ours = Hh.run_ours(a, debug=False)
+    fast = Hh.run_ours(a, debug=False)
+    fast_imgs = {k: fast[k].clone() for k in ("color", "depth", "alpha")}
+    ours = Hh.run_ours(a, debug=False, exact=True)
     Rn = ours["stats"]["num_rendered"]
     assert ours["stats"]["overflow"] == 0 and Rn > 1_000_000
+    Hh.assert_images_close(fast_imgs, ours)
     if not _have_ref():
         pytest.skip("oracle/_ref not built")
     from oracle import ref_cuda
@@ -499,12 +515,17 @@ def test_4k_image_and_sugar_storage_against_reference(dev):
     assert ref["num_rendered"] == Rn
     for k in ("color", "depth", "alpha", "radii"):
         assert torch.equal(ours[k], ref[k]), k
+    Hh.assert_images_close(fast_imgs, ref)
     assert torch.equal(ours["views"]["point_list"][:Rn], rs["point_list"]) and torch.equal(ours["views"]["ranges"], rs["ranges"])
     extra = torch.rand(600_000, 3, generator=torch.Generator().manual_seed(5)).to(dev)
-    res = R.forward_multi(a["means3D"], a["shs"], None, extra, a["opacities"], a["scales"], a["rotations"], None, Hh.settings_from(a), sync=True)
+    res = R.forward_multi(a["means3D"], a["shs"], None, extra, a["opacities"], a["scales"], a["rotations"], None, Hh.settings_from(a), sync=True,
+                          exact=True)
     b = dict(a)
     b["shs"], b["colors_precomp"] = None, extra
-    assert torch.equal(res[3], Hh.run_ref(b)["color"]) and torch.equal(res[0], ref["color"])
+    ref2 = Hh.run_ref(b)["color"]
+    assert torch.equal(res[3], ref2) and torch.equal(res[0], ref["color"])
+    resf = R.forward_multi(a["means3D"], a["shs"], None, extra, a["opacities"], a["scales"], a["rotations"], None, Hh.settings_from(a), sync=True)
+    assert Hh.maxabs(resf[3], ref2) <= 1e-5 and Hh.maxabs(resf[0], ref["color"]) <= 1e-5
 
 
 def test_debug_mode_dumps_a_snapshot_on_failure(dev, tmp_path, monkeypatch):

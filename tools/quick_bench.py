@@ -1,0 +1,103 @@
+"""Developer A/B harness: per-kernel times of the forward on the bench workload (3M Gaussians, 1080p, trajectory cameras).
+
+    GSR_BLEND=legacy GSR_BLEND_WARPS=4 python tools/quick_bench.py --frames 60 [--exact] [--tight] [--tag name]
+
+Prints one JSON line (and appends it to gpurun_out/quick_bench.jsonl).  Kernel-selection knobs are environment variables read
+once per process, so every variant is its own process.  Not the bench of record (that is bench.py)."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from autovfx_b200 import scene  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=60)
+    ap.add_argument("--gaussians", type=int, default=3_000_000)
+    ap.add_argument("--exact", action="store_true")
+    ap.add_argument("--tight", action="store_true")
+    ap.add_argument("--backward", action="store_true", help="also time forward+backward through autograd (20 iterations)")
+    ap.add_argument("--tag", default="")
+    args = ap.parse_args()
+    from autovfx_b200 import rasterizer as R, _lib
+    dev = torch.device("cuda:0")
+    g = {k: v.to(dev) for k, v in scene.config3_scene(P=args.gaussians).items()}
+    cams = scene.cameras_from_trajectory(scene.trajectory_dict(num_views=300))
+    from autovfx_b200 import render_loop as RL
+    packed = RL.pack_cameras(cams).to(dev)
+    host = packed.cpu()
+    bg = torch.zeros(3, device=dev)
+    P = g["means3D"].shape[0]
+    K = args.frames
+
+    def settings(i):
+        c = packed[i]
+        return R.GaussianRasterizationSettings(1080, 1920, float(host[i, 35]), float(host[i, 36]), bg, 1.0, c[0:16], c[16:32], 3, c[32:35], False, False)
+    S = [settings(i % 300) for i in range(K + 5)]
+    out = (torch.empty((3, 1080, 1920), device=dev), torch.empty((1, 1080, 1920), device=dev), torch.empty((1, 1080, 1920), device=dev),
+           torch.empty((P,), dtype=torch.int32, device=dev))
+
+    def frame(i, sync):
+        return R.forward_raw(g["means3D"], g["shs"], None, g["opacities"], g["scales"], g["rotations"], None, S[i], sync=sync, out=out,
+                             tight=args.tight, exact=args.exact)
+    for i in range(K + 5):
+        frame(i, True)
+    for i in range(5):
+        frame(i, False)
+    torch.cuda.synchronize()
+    _lib.check(_lib.lib.gsr_profile_begin_strided(K, 2), "profile")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    tk = [frame(5 + i, False)[5] for i in range(K)]
+    e1.record()
+    torch.cuda.synchronize()
+    ms_k = (C.c_float * 5)()
+    n = C.c_int(0)
+    _lib.check(_lib.lib.gsr_profile_end(ms_k, C.byref(n)), "profile_end")
+    st = [t.stats() for t in tk]
+    ms = e0.elapsed_time(e1) / K
+    res = {"tag": args.tag, "env": {k: os.environ.get(k) for k in ("GSR_BLEND", "GSR_BLEND_WARPS") if os.environ.get(k)},
+           "exact": args.exact, "tight": args.tight, "ms_per_frame": round(ms, 4), "fps": round(1000.0 / ms, 1),
+           "kernel_ms": {k: round(float(ms_k[i]), 4) for i, k in enumerate(["preprocess", "tile_scan", "emit", "sort_tiles", "blend"])},
+           "avg_R": sum(s["num_rendered"] for s in st) / K, "avg_foot": sum(s["foot_total"] for s in st) / K,
+           "avg_redos": sum(s["exact_redos"] for s in st) / K, "overflow": sum(s["overflow"] for s in st)}
+    if args.backward:
+        from tests import helpers as Hh  # noqa: F401
+        leaves = {k: g[k].clone().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+        gen = torch.Generator().manual_seed(7)
+        dc, dd, da = (torch.randn(c, 1080, 1920, generator=gen).to(dev) for c in (3, 1, 1))
+        R.set_exact_images(args.exact)
+
+        def step(i):
+            rast = R.GaussianRasterizer(S[i])
+            m2 = torch.zeros_like(leaves["means3D"], requires_grad=True)
+            color, depth, alpha, _ = rast(leaves["means3D"], m2, leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+            ((color * dc).sum() + (depth * dd).sum() + (alpha * da).sum()).backward()
+            for v in leaves.values():
+                v.grad = None
+        for i in range(3):
+            step(i)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(20):
+            step(3 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        res["fwd_bwd_ms"] = round(e0.elapsed_time(e1) / 20, 3)
+    line = json.dumps(res)
+    print(line, flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "quick_bench.jsonl"), "a") as f:
+        f.write(line + "\n")
+
+
+if __name__ == "__main__":
+    main()
