@@ -22,11 +22,12 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 
 // ---- workspace layouts (pure functions of P / capacity / W,H) --------------------------------------
 struct GeomLayout {
-    size_t records, ranks, cov3D, clamped, total;
+    size_t records, ranks, vis_list, cov3D, clamped, total;
     __host__ __device__ explicit GeomLayout(size_t P) {
         size_t o = 0;
         records = o; o = align_up(o + 48 * P, 256);
         ranks = o;   o = align_up(o + 32 * P, 256);  // 8 x u32 in-tile ranks for Gaussians touching <= 8 tiles
+        vis_list = o; o = align_up(o + 4 * P, 256);  // ids of the visible Gaussians (k_project -> k_color_emit)
         cov3D = o;   o = align_up(o + 24 * P, 256);
         clamped = o; o = align_up(o + P, 256);
         total = o + 256;
@@ -53,7 +54,7 @@ struct ImageLayout {
     __host__ __device__ size_t zero_bytes() const { return tile_fill; }
 };
 // bytes of binning workspace per instance of capacity: 8 (pair) + 4 (point_list) + 4 * GSR_FOOT_FACTOR (footprint lists)
-#define GSR_FOOT_FACTOR 2
+#define GSR_FOOT_FACTOR 3
 #define GSR_BIN_BYTES (12 + 4 * GSR_FOOT_FACTOR)
 struct BinLayout {
     size_t pairs, point_list, foot_list, foot_capacity, total, capacity;
@@ -177,6 +178,11 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float footprint_tau(float opacity) { return __logf(255.0f * opacity); }
 // dx, dy: splat centre minus box centre; hx, hy: half extents of the box of pixel centres
 __device__ __forceinline__ bool box_may_touch(float dx, float dy, float a, float b, float c, float tau, float hx, float hy) {
@@ -235,6 +241,67 @@ __device__ __forceinline__ uint32_t tile_foot_mask(float px, float py, float a, 
         }
     }
     return mask;
+}
+
+// ---- footprint masks from strip intervals -------------------------------------------------------------------------
+// The region where a splat can reach alpha >= 1/255 is the ellipse q(x, y) <= T around (px, py), T = 2 (tau + margins).
+// For an 8-pixel-wide column strip [X, X+7] the ellipse covers the rows [py + tlo, py + thi]: on the line x = px + s the
+// form has the roots t = (-b s +- sqrt(c T - det s^2)) / c, the upper one is largest at s = -b sqrt(T / (a det)) and the
+// lower one smallest at the opposite point, both clamped to the strip (they lie inside the ellipse's x-extent whenever the
+// strip meets it; D < 0 at both clamped points means it does not).  A footprint (strip, 4-row band) is touched iff the band
+// meets that interval.  ~22 instructions per strip + 3 per footprint instead of ~37 per footprint for the box-minimum test;
+// numerically it is a superset of it (T is inflated by 2e-3 relative for the approximate units and the cancellation in
+// det, rows by 0.01 pixel; checked on 400k random splats: 0 misses, 0.15 % more survivors).  Needs a well-conditioned
+// positive-definite conic (det > 1e-4 a c); everything else takes tile_foot_mask.
+struct StripCtx {
+    float px, py, b, det, rc, cT, sstar;
+    bool ok;   // false: use tile_foot_mask (non positive-definite / ill-conditioned conic, NaNs)
+    bool none; // the splat cannot reach alpha >= 1/255 anywhere
+};
+// um, vm: upper bounds of |x - px|, |y - py| over the pixels the masks will be asked for (rounding margin, like box_may_touch)
+__device__ __forceinline__ StripCtx strip_ctx(float px, float py, float a, float b, float c, float tau, float um, float vm) {
+    StripCtx s;
+    const float det = fmaf(a, c, -b * b);
+    const float mag = a * um * um + c * vm * vm + 2.f * fabsf(b) * um * vm;
+    const float T = 2.004f * (tau + 1.0e-3f + 4.0e-6f * mag);
+    s.ok = a > 0.f && c > 0.f && det > 1.0e-4f * (a * c) && T == T;
+    s.none = s.ok && !(T > 0.f);
+    s.px = px; s.py = py; s.b = b; s.det = det;
+    s.rc = rcp_approx(c);
+    s.cT = c * T;
+    s.sstar = b * sqrt_approx(fmaxf(T, 0.f) * rcp_approx(a * det));
+    return s;
+}
+// rows [ylo, yhi] covered inside the strip of pixel columns [X, X + w - 1]; false if the strip misses the ellipse
+__device__ __forceinline__ bool strip_rows(const StripCtx& s, float X, float w, float& ylo, float& yhi) {
+    const float sl = X - s.px, sh = sl + (w - 1.f);
+    const float st = fminf(fmaxf(-s.sstar, sl), sh), sb = fminf(fmaxf(s.sstar, sl), sh);
+    const float Dt = fmaf(-s.det, st * st, s.cT), Db = fmaf(-s.det, sb * sb, s.cT);
+    yhi = s.py + (fmaf(-s.b, st, sqrt_approx(fmaxf(Dt, 0.f))) * s.rc + 0.01f);
+    ylo = s.py + (fmaf(-s.b, sb, -sqrt_approx(fmaxf(Db, 0.f))) * s.rc - 0.01f);
+    return Dt >= 0.f || Db >= 0.f;
+}
+// mask of the eight 8x4 footprints of tile (tx, ty) from the tile's two strips
+__device__ __forceinline__ uint32_t strip_tile_mask(const StripCtx& s, int tx, int ty) {
+    uint32_t mask = 0;
+    const float Y = (float)(ty * GSR_TILE);
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        float ylo, yhi;
+        const bool v = strip_rows(s, (float)(tx * GSR_TILE + 8 * i), 8.f, ylo, yhi);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (v && ylo <= Y + (4.f * j + 3.f) && yhi >= Y + 4.f * j) mask |= 1u << (2 * j + i);
+    }
+    return mask;
+}
+// one (splat, tile) pair, any conic
+__device__ __forceinline__ uint32_t tile_foot_mask_any(float px, float py, float a, float b, float c, float tau, int tx, int ty) {
+    const float um = fabsf(px - ((float)(tx * GSR_TILE) + 7.5f)) + 7.5f, vm = fabsf(py - ((float)(ty * GSR_TILE) + 7.5f)) + 7.5f;
+    const StripCtx s = strip_ctx(px, py, a, b, c, tau, um, vm);
+    if (!s.ok) return tile_foot_mask(px, py, a, b, c, tau, tx, ty);
+    if (s.none) return 0u;
+    return strip_tile_mask(s, tx, ty);
 }
 
 // SH basis constants (auxiliary.h:22-39)

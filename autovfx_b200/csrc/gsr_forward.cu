@@ -44,7 +44,7 @@ int check_launch(const char* what, bool debug, cudaStream_t stream) {
 }
 
 // =====================================================================================================
-// Kernel 1: preprocess
+// Kernel 1: projection of every Gaussian (k_project); its colour is evaluated later, only for the visible ones (k_color_emit)
 // =====================================================================================================
 struct PreParams {
     int P, D, M, W, H, gx, gy;
@@ -58,6 +58,7 @@ struct PreParams {
     uint32_t* tile_count;
     uint32_t* tile_big;
     uint32_t* ranks;
+    uint32_t* vis_list;
     gsr_counters* counters;
 };
 
@@ -187,27 +188,15 @@ __device__ __forceinline__ void cov3d_ref_rounding(float sx, float sy, float sz,
     c3[5] = __fmaf_rn(M22, M22, __fmaf_rn(M20, M20, __fmul_rn(M21, M21)));
 }
 
-// DEG = -1: colours are precomputed.  VEC: SH rows are 16-byte aligned (M % 4 == 0) -> 16-byte staging, either one TMA
-// bulk copy per visible Gaussian issued by its own lane (BULK) or coalesced cp.async by the whole warp.  WIN (with VEC and
-// BULK): rows are only 4-byte aligned (M = 25, the SuGaR storage: 300-byte rows) — each lane bulk-copies the 16-byte aligned
-// window that contains its coefficients (one extra float4) and evaluates from its row's offset inside the window.
-template <int DEG, bool VEC, bool BULK, bool WIN = false>
-__global__ void __launch_bounds__(PRE_THREADS, 8) k_preprocess(const PreParams p) {
-    constexpr int DG = DEG < 0 ? 0 : DEG;
-    constexpr int NF = sh_nf(DG);
-    constexpr int STRIDE = sh_stride(DG, VEC, WIN);
+// Kernel 1 of 5.  DEG / VEC / BULK / WIN only matter to k_color_emit below; this kernel is colour-agnostic.
+// One thread per Gaussian: near cull, 3D covariance, EWA projection, conic, radius, tile rectangle (forward.cu:155-256 minus the
+// colour), the per-tile histogram with ranked tickets, and the compact list of visible Gaussians the colour + emission
+// kernel walks.  Only 44 bytes per Gaussian are read; the 192-byte SH row is not touched here.
+__global__ void __launch_bounds__(PRE_THREADS, 8) k_project(const PreParams p) {
     __shared__ CamConsts cam;
-    __shared__ __align__(16) float stage[DEG < 0 ? 4 : PRE_THREADS * STRIDE];
-    __shared__ __align__(8) unsigned long long stage_bar[PRE_THREADS / 32];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (BULK && lane == 0) {
-        mbar_init((uint32_t)__cvta_generic_to_shared(&stage_bar[warp]), 1u);
-        mbar_fence_init();
-    }
+    const int tid = threadIdx.x, lane = tid & 31;
     if (tid < 16) cam.view[tid] = p.view[tid];
     else if (tid < 32) cam.proj[tid - 16] = p.proj[tid - 16];
-    else if (tid < 35) cam.campos[tid - 32] = p.campos[tid - 32];
     __syncthreads();
 
     const int idx = blockIdx.x * PRE_THREADS + tid;
@@ -218,8 +207,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_preprocess(const PreParams p
     float px = 0, py = 0, depth = 0, con_a = 0, con_b = 0, con_c = 0;
     float c3[6] = {0, 0, 0, 0, 0, 0};
 
-    // all per-Gaussian inputs are requested up front (one memory round trip instead of three dependent ones);
-    // the few near-culled Gaussians pay for 32 unused bytes
+    // all per-Gaussian inputs are requested up front (one memory round trip instead of three dependent ones)
     float opacity = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
     float4 q = make_float4(0, 0, 0, 0);
     if (valid) {
@@ -282,15 +270,13 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_preprocess(const PreParams p
     }
     if (!vis) { x0 = y0 = x1 = y1 = 0; }
 
-    // Per-tile histogram.  Gaussians touching <= 8 tiles take a ranked ticket per tile (atomic with return; the
-    // results are only needed at the end of the kernel, so the round trips overlap the SH work) and store the
-    // ranks for k_emit, which then needs no atomics.  Larger rectangles are counted separately, warp-cooperatively.
-    // With p.tight, a tile of the reference's rectangle only receives an instance if the splat can reach
-    // alpha >= 1/255 at one of its pixel centres (tile_may_touch) — instances the reference creates but skips at
-    // every pixel are never emitted (opt-in: the per-tile lists then differ from the reference's, the images do not).
+    // Per-tile histogram.  Gaussians touching <= 8 tiles take a ranked ticket per tile (atomic with return) in COLUMN-major
+    // order — the order k_color_emit walks them — and store the ranks, so the emission needs no atomics.  Larger rectangles
+    // are counted separately, warp-cooperatively.  With p.tight a tile of the reference's rectangle only receives an instance
+    // if the splat can reach alpha >= 1/255 at one of its pixel centres (opt-in: lists differ from the reference's, images do not).
     const float tau = footprint_tau(opacity);
     uint32_t rk[8];
-    const int rect_w = x1 - x0, rect_n = rect_w * (y1 - y0);
+    const int rect_h = y1 - y0, rect_n = (x1 - x0) * rect_h;
     if (rect_n > 0 && rect_n <= 8) {
         int tx = x0, ty = y0;
 #pragma unroll
@@ -298,7 +284,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_preprocess(const PreParams p
             if (k < rect_n) {
                 rk[k] = 0xffffffffu;
                 if (!p.tight || tile_may_touch(px, py, con_a, con_b, con_c, tau, tx, ty)) rk[k] = atomicAdd(&p.tile_count[ty * p.gx + tx], 1u);
-                if (++tx == x1) { tx = x0; ty++; }
+                if (++ty == y1) { ty = y0; tx++; }
             }
         }
     }
@@ -315,82 +301,31 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_preprocess(const PreParams p
         });
     }
 
-    // colour
-    float rgb[3] = {0, 0, 0};
-    unsigned clamp_bits = 0;
-    if constexpr (DEG < 0) {
-        if (vis) {
-            rgb[0] = p.colors_precomp[3 * (size_t)idx];
-            rgb[1] = p.colors_precomp[3 * (size_t)idx + 1];
-            rgb[2] = p.colors_precomp[3 * (size_t)idx + 2];
-        }
-    } else {
-        // Stage the SH rows of this warp's 32 Gaussians: flat work list (Gaussian, part), consecutive lanes
-        // fetch consecutive 16-byte (or 4-byte) parts -> coalesced; rows of culled Gaussians are skipped.
-        const unsigned vismask = __ballot_sync(GSR_FULL, vis);
-        float* wstage = stage + warp * 32 * STRIDE;
-        const size_t gbase = (size_t)(blockIdx.x * PRE_THREADS + warp * 32);
-        const size_t row_floats = (size_t)p.M * 3;
-        int win_off = 0;  // floats between the start of the staged window and the row's first coefficient (WIN only)
-        if (VEC && BULK) {
-            constexpr int NV = sh_nv(DG, WIN);
-            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar[warp]);
-            if (vismask) {
-                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)__popc(vismask) * NV * 16u);
-                if (vis) {
-                    const float* src = p.shs + (gbase + lane) * row_floats;
-                    if (WIN) {
-                        win_off = (int)(((uintptr_t)src & 15u) >> 2);
-                        src -= win_off;
-                    }
-                    bulk_g2s((uint32_t)__cvta_generic_to_shared(wstage + lane * STRIDE), src, NV * 16u, bar);
-                }
-                mbar_wait(bar, 0u);
-            }
-        } else if (VEC) {
-            constexpr int NV = (NF + 3) / 4;
-#pragma unroll
-            for (int it = 0; it < NV; it++) {
-                const int item = it * 32 + lane;
-                const int gl = item / NV, part = item - gl * NV;
-                if ((vismask >> gl) & 1u) cp_async16(wstage + gl * STRIDE + part * 4, p.shs + (gbase + gl) * row_floats + part * 4);
-            }
-            cp_async_wait_all();
-        } else {
-#pragma unroll 4
-            for (int it = 0; it < NF; it++) {
-                const int item = it * 32 + lane;
-                const int gl = item / NF, part = item - gl * NF;
-                if ((vismask >> gl) & 1u) wstage[gl * STRIDE + part] = p.shs[(gbase + gl) * row_floats + part];
-            }
-        }
-        __syncwarp();
-        if (vis) sh_eval<DG>(wstage + lane * STRIDE + win_off, mean, cam.campos, rgb, clamp_bits);
-    }
-
     if (valid) {
         p.radii[idx] = radius;
         if (vis) {
             float4* rec = p.records + 3 * (size_t)idx;
             rec[0] = make_float4(px, py, con_a, con_b);
             rec[1] = make_float4(con_c, opacity, depth, tau);
-            rec[2] = make_float4(rgb[0], rgb[1], rgb[2], log2f(opacity));  // .w: log2(opacity) for the default (fast-alpha) blend
             if (rect_n <= 8) {
                 uint4* rr = reinterpret_cast<uint4*>(p.ranks + 8 * (size_t)idx);
                 rr[0] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
                 if (rect_n > 4) rr[1] = make_uint4(rk[4], rk[5], rk[6], rk[7]);
             }
-            if (p.for_backward) {
-                if (p.cov3D_precomp == nullptr) {
+            if (p.for_backward && p.cov3D_precomp == nullptr) {
 #pragma unroll
-                    for (int k = 0; k < 6; k++) p.cov3D[6 * (size_t)idx + k] = c3[k];
-                }
-                p.clamped[idx] = (uint8_t)clamp_bits;
+                for (int k = 0; k < 6; k++) p.cov3D[6 * (size_t)idx + k] = c3[k];
             }
         }
     }
-    const int nvis = __syncthreads_count(vis);
-    if (tid == 0 && nvis) atomicAdd(&p.counters->num_visible, (uint32_t)nvis);
+    // compact list of the visible Gaussians (order is irrelevant: every entry is processed independently)
+    const unsigned vm = __ballot_sync(GSR_FULL, vis);
+    if (vm) {
+        uint32_t base = 0;
+        if (lane == __ffs(vm) - 1) base = atomicAdd(&p.counters->num_visible, (uint32_t)__popc(vm));
+        base = __shfl_sync(GSR_FULL, base, __ffs(vm) - 1);
+        if (vis) p.vis_list[base + __popc(vm & ((1u << lane) - 1u))] = (uint32_t)idx;
+    }
 }
 
 // =====================================================================================================
@@ -453,66 +388,178 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
 }
 
 // =====================================================================================================
-// Kernel 3: scatter one (depth bits, Gaussian id) pair per (Gaussian, tile) instance into the tile's bucket
-// (the work of duplicateWithKeys, rasterizer_impl.cu:70-111; the tile id is implicit in the bucket)
+// Kernel 3 of 5: colour + instance emission, one thread per VISIBLE Gaussian (the compact list k_project wrote), every
+// lane busy.  (a) SH -> RGB (forward.cu:20-71) from the Gaussian's SH row, staged by ONE TMA bulk copy issued by its own
+// lane; (b) the work of duplicateWithKeys (rasterizer_impl.cu:70-111): one (depth bits, id) pair per (Gaussian, tile)
+// scattered to ranges[tile].x + rank — the ranks were drawn by k_project, so no atomics for rectangles of <= 8 tiles;
+// (c) PACKED (P <= 2^24): the pair's low word is (id << 8 | mask), mask = which of the tile's eight 8x4 warp footprints the
+// splat can touch (strip intervals, computed once per tile column of the rectangle), so k_sort_tiles needs no gather.
+// The kernel streams 192 B of SH per thread and has issue slots to spare for (c).
+// DEG = -1: colours are precomputed.  VEC: SH rows are 16-byte aligned (M % 4 == 0) -> 16-byte staging, either one TMA
+// bulk copy per Gaussian (BULK) or coalesced cp.async by the whole warp.  WIN (with VEC and BULK): rows are only 4-byte
+// aligned (M = 25, the SuGaR storage: 300-byte rows) — each lane bulk-copies the 16-byte aligned window that contains its
+// coefficients (one extra float4) and evaluates from its row's offset inside the window.
 // =====================================================================================================
-template <bool TIGHT>
-__global__ void __launch_bounds__(256) k_emit(int P, int gx, int gy, const int* __restrict__ radii,
-                                              const float4* __restrict__ records, const uint32_t* __restrict__ ranks,
-                                              const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_fill,
-                                              uint2* __restrict__ pairs, const gsr_counters* __restrict__ counters) {
-    if (counters->overflow) return;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    uint32_t dbits = 0;
+struct EmitParams {
+    int P, M, gx, gy, for_backward;
+    const float *means3D, *shs, *colors_precomp, *campos;
+    float4* records;
+    uint8_t* clamped;
+    const int* radii;
+    const uint32_t* ranks;
+    const uint32_t* vis_list;
+    const uint2* ranges;
+    uint32_t* tile_fill;
+    uint2* pairs;
+    const gsr_counters* counters;
+};
+
+template <int DEG, bool VEC, bool BULK, bool WIN, bool TIGHT, bool PACKED>
+__global__ void __launch_bounds__(PRE_THREADS, 8) k_color_emit(const EmitParams p) {
+    constexpr int DG = DEG < 0 ? 0 : DEG;
+    constexpr int NF = sh_nf(DG);
+    constexpr int STRIDE = sh_stride(DG, VEC, WIN);
+    __shared__ float campos[3];
+    __shared__ __align__(16) float stage[DEG < 0 ? 4 : PRE_THREADS * STRIDE];
+    __shared__ __align__(8) unsigned long long stage_bar[PRE_THREADS / 32];
+
+    const uint32_t nvis = p.counters->num_visible;
+    if (blockIdx.x * PRE_THREADS >= nvis) return;  // the grid is sized for P; blocks past the visible list leave at once
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (BULK && lane == 0) {
+        mbar_init((uint32_t)__cvta_generic_to_shared(&stage_bar[warp]), 1u);
+        mbar_fence_init();
+    }
+    if (tid < 3) campos[tid] = p.campos[tid];
+    __syncthreads();
+
+    const uint32_t k = blockIdx.x * PRE_THREADS + tid;
+    const bool vis = k < nvis;
+    const uint32_t idx = vis ? p.vis_list[k] : 0u;
     float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
-    if (idx < P) {
-        const int r = radii[idx];
-        if (r > 0) {
-            r0 = records[3 * (size_t)idx];
-            if (TIGHT) {
-                r1 = records[3 * (size_t)idx + 1];
-                dbits = __float_as_uint(r1.z);
-            } else {
-                dbits = __float_as_uint(records[3 * (size_t)idx + 1].z);
-            }
-            tile_rect(r0.x, r0.y, r, gx, gy, x0, y0, x1, y1);
-        }
+    int radius = 0;
+    if (vis) {
+        r0 = p.records[3 * (size_t)idx];
+        r1 = p.records[3 * (size_t)idx + 1];
+        radius = p.radii[idx];
     }
-    // <= 8 tiles: the in-tile rank of every instance was drawn by k_preprocess -> plain scatter, no atomics
-    // (rank 0xffffffff = tile culled by the tight-tile test)
-    const int w = x1 - x0, cnt = w * (y1 - y0);
-    if (cnt > 0 && cnt <= 8) {
-        const uint4* rr = reinterpret_cast<const uint4*>(ranks + 8 * (size_t)idx);
-        const uint4 ra = rr[0];
-        uint4 rb = make_uint4(0, 0, 0, 0);
-        if (cnt > 4) rb = rr[1];
-        const uint32_t rk[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-        const uint2 pr = make_uint2((uint32_t)idx, dbits);  // little endian: u64 = (depth bits << 32) | id
-        int tx = x0, ty = y0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (k < cnt) {
-                if (!TIGHT || rk[k] != 0xffffffffu) pairs[ranges[ty * gx + tx].x + rk[k]] = pr;
-                if (++tx == x1) { tx = x0; ty++; }
-            }
+
+    // ---- colour ----
+    float rgb[3] = {0, 0, 0};
+    unsigned clamp_bits = 0;
+    if constexpr (DEG < 0) {
+        if (vis) {
+            rgb[0] = p.colors_precomp[3 * (size_t)idx];
+            rgb[1] = p.colors_precomp[3 * (size_t)idx + 1];
+            rgb[2] = p.colors_precomp[3 * (size_t)idx + 2];
         }
-    }
-    // > 8 tiles: walked by the whole warp, positions from the per-tile cursor initialised by k_tile_scan; the
-    // tight-tile test is re-evaluated on the same stored values k_preprocess used (bitwise same decision)
-    const bool big = cnt > 8;
-    if (TIGHT) {
-        const uint32_t pay[8] = {(uint32_t)idx, dbits, __float_as_uint(r0.x), __float_as_uint(r0.y), __float_as_uint(r0.z),
-                                 __float_as_uint(r0.w), __float_as_uint(r1.x), __float_as_uint(r1.w)};
-        for_each_tile<0, 8>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, pay, [&](int tile, int tx, int ty, const uint32_t(&o)[8]) {
-            if (tile_may_touch(__uint_as_float(o[2]), __uint_as_float(o[3]), __uint_as_float(o[4]), __uint_as_float(o[5]),
-                               __uint_as_float(o[6]), __uint_as_float(o[7]), tx, ty))
-                pairs[atomicAdd(&tile_fill[tile], 1u)] = make_uint2(o[0], o[1]);
-        });
     } else {
-        const uint32_t pay[2] = {(uint32_t)idx, dbits};
-        for_each_tile<0, 2>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, gx, pay, [&](int tile, int, int, const uint32_t(&o)[2]) {
-            pairs[atomicAdd(&tile_fill[tile], 1u)] = make_uint2(o[0], o[1]);
+        float3 mean = {0, 0, 0};
+        if (vis) mean = make_float3(p.means3D[3 * (size_t)idx], p.means3D[3 * (size_t)idx + 1], p.means3D[3 * (size_t)idx + 2]);
+        const unsigned vismask = __ballot_sync(GSR_FULL, vis);
+        float* wstage = stage + warp * 32 * STRIDE;
+        const size_t row_floats = (size_t)p.M * 3;
+        int win_off = 0;  // floats between the start of the staged window and the row's first coefficient (WIN only)
+        if (VEC && BULK) {
+            constexpr int NV = sh_nv(DG, WIN);
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar[warp]);
+            if (vismask) {
+                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)__popc(vismask) * NV * 16u);
+                if (vis) {
+                    const float* src = p.shs + (size_t)idx * row_floats;
+                    if (WIN) {
+                        win_off = (int)(((uintptr_t)src & 15u) >> 2);
+                        src -= win_off;
+                    }
+                    bulk_g2s((uint32_t)__cvta_generic_to_shared(wstage + lane * STRIDE), src, NV * 16u, bar);
+                }
+                mbar_wait(bar, 0u);
+            }
+        } else if (VEC) {
+            constexpr int NV = (NF + 3) / 4;
+#pragma unroll
+            for (int it = 0; it < NV; it++) {
+                const int item = it * 32 + lane;
+                const int gl = item / NV, part = item - gl * NV;
+                const uint32_t gid = __shfl_sync(GSR_FULL, idx, gl);
+                if ((vismask >> gl) & 1u) cp_async16(wstage + gl * STRIDE + part * 4, p.shs + (size_t)gid * row_floats + part * 4);
+            }
+            cp_async_wait_all();
+        } else {
+#pragma unroll 4
+            for (int it = 0; it < NF; it++) {
+                const int item = it * 32 + lane;
+                const int gl = item / NF, part = item - gl * NF;
+                const uint32_t gid = __shfl_sync(GSR_FULL, idx, gl);
+                if ((vismask >> gl) & 1u) wstage[gl * STRIDE + part] = p.shs[(size_t)gid * row_floats + part];
+            }
+        }
+        __syncwarp();
+        if (vis) sh_eval<DG>(wstage + lane * STRIDE + win_off, mean, campos, rgb, clamp_bits);
+    }
+    if (vis) {
+        p.records[3 * (size_t)idx + 2] = make_float4(rgb[0], rgb[1], rgb[2], log2f(r1.y));  // .w: log2(opacity) for the default blend
+        if (p.for_backward) p.clamped[idx] = (uint8_t)clamp_bits;
+    }
+
+    // ---- emission ----
+    if (p.counters->overflow) return;  // set by k_tile_scan: the binning buffer is too small for this frame
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    if (vis) tile_rect(r0.x, r0.y, radius, p.gx, p.gy, x0, y0, x1, y1);
+    const int h = y1 - y0, cnt = (x1 - x0) * h;
+    const uint32_t dbits = __float_as_uint(r1.z);
+    const uint32_t lo_id = PACKED ? idx << 8 : idx;
+    if (cnt > 0 && cnt <= 8) {
+        StripCtx sc = {};
+        bool none = false;
+        if (PACKED) {
+            const float um = fmaxf(r0.x - (float)(x0 * GSR_TILE), (float)(x1 * GSR_TILE) - r0.x);
+            const float vm = fmaxf(r0.y - (float)(y0 * GSR_TILE), (float)(y1 * GSR_TILE) - r0.y);
+            sc = strip_ctx(r0.x, r0.y, r0.z, r0.w, r1.x, r1.w, um, vm);
+            none = sc.none;
+        }
+        const uint32_t* rk = p.ranks + 8 * (size_t)idx;
+        int kk = 0;
+        for (int tx = x0; tx < x1; tx++) {
+            float ylo0 = 0.f, yhi0 = 0.f, ylo1 = 0.f, yhi1 = 0.f;
+            bool v0 = false, v1 = false;
+            if (PACKED && sc.ok && !none) {
+                v0 = strip_rows(sc, (float)(tx * GSR_TILE), 8.f, ylo0, yhi0);
+                v1 = strip_rows(sc, (float)(tx * GSR_TILE + 8), 8.f, ylo1, yhi1);
+            }
+            for (int ty = y0; ty < y1; ty++, kk++) {
+                const uint32_t rank = rk[kk];
+                uint32_t mask = 0;
+                if (PACKED) {
+                    if (!sc.ok) mask = tile_foot_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.w, tx, ty);
+                    else {
+                        const float Y = (float)(ty * GSR_TILE);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (v0 && ylo0 <= Y + (4.f * j + 3.f) && yhi0 >= Y + 4.f * j) mask |= 1u << (2 * j);
+                            if (v1 && ylo1 <= Y + (4.f * j + 3.f) && yhi1 >= Y + 4.f * j) mask |= 2u << (2 * j);
+                        }
+                    }
+                }
+                if (!TIGHT || rank != 0xffffffffu) p.pairs[p.ranges[ty * p.gx + tx].x + rank] = make_uint2(lo_id | mask, dbits);  // little endian: u64 = depth bits << 32 | low word
+            }
+        }
+    }
+    // > 8 tiles: walked by the whole warp, positions from the per-tile cursor initialised by k_tile_scan; the tight-tile
+    // test is re-evaluated on the same stored values k_project used (bitwise same decision)
+    {
+        const bool big = cnt > 8;
+        const uint32_t pay[8] = {lo_id, dbits, __float_as_uint(r0.x), __float_as_uint(r0.y), __float_as_uint(r0.z),
+                                 __float_as_uint(r0.w), __float_as_uint(r1.x), __float_as_uint(r1.w)};
+        uint32_t* tf = p.tile_fill;
+        uint2* pr = p.pairs;
+        for_each_tile<0, 8>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, p.gx, pay, [&](int tile, int tx, int ty, const uint32_t(&o)[8]) {
+            const float ox = __uint_as_float(o[2]), oy = __uint_as_float(o[3]), oa = __uint_as_float(o[4]), ob = __uint_as_float(o[5]),
+                        oc = __uint_as_float(o[6]), ot = __uint_as_float(o[7]);
+            if (TIGHT && !tile_may_touch(ox, oy, oa, ob, oc, ot, tx, ty)) return;
+            uint32_t mask = 0;
+            if (PACKED) mask = tile_foot_mask_any(ox, oy, oa, ob, oc, ot, tx, ty);
+            pr[atomicAdd(&tf[tile], 1u)] = make_uint2(o[0] | mask, o[1]);
         });
     }
 }
@@ -571,6 +618,7 @@ __device__ void sort_smem(unsigned long long* s, uint32_t n) {
 constexpr int SORT_BUCKETS = 2048;
 constexpr int SORT_BUCKET_MAX = 24;
 
+template <bool PACKED>
 __device__ void sort_bucket(const unsigned long long* __restrict__ g, uint32_t n, uint32_t* __restrict__ out,
                             unsigned long long* __restrict__ gkeep, unsigned long long* s, uint32_t* hist /*[SORT_BUCKETS+1]*/) {
     __shared__ uint32_t red_min[SORT_THREADS / 32], red_max[SORT_THREADS / 32], wsum[SORT_THREADS / 32];
@@ -656,8 +704,9 @@ __device__ void sort_bucket(const unsigned long long* __restrict__ g, uint32_t n
     if (fallback) sort_smem(s, n);  // ends with a barrier
     for (uint32_t i = t; i < n; i += SORT_THREADS) {
         const unsigned long long x = s[i];
-        out[i] = (uint32_t)x;
-        if (gkeep) gkeep[i] = x;
+        const uint32_t id = PACKED ? (uint32_t)x >> 8 : (uint32_t)x;  // PACKED: low word = id << 8 | footprint mask
+        out[i] = id;
+        if (gkeep) gkeep[i] = (x & 0xffffffff00000000ull) | id;
     }
 }
 
@@ -678,6 +727,7 @@ struct FootArgs {
 };
 // keys: the n sorted (depth bits << 32 | id) of the tile (shared or global memory); mask8: n bytes of scratch (shared
 // memory), or nullptr to park the masks in park32[] (global, 4 bytes per entry — the large-tile path).
+template <bool PACKED>
 __device__ void foot_lists(const FootArgs& fa, const unsigned long long* keys, uint32_t n, uint32_t list_base, int tile,
                            uint8_t* mask8, uint32_t* park32) {
     __shared__ uint32_t f_cnt[GSR_FOOTS], f_off[GSR_FOOTS];
@@ -691,9 +741,12 @@ __device__ void foot_lists(const FootArgs& fa, const unsigned long long* keys, u
         const uint32_t i = base + lane;
         uint32_t m = 0;
         if (i < n) {
-            const uint32_t id = (uint32_t)keys[i];
-            const float4 r0 = fa.records[3 * (size_t)id], r1 = fa.records[3 * (size_t)id + 1];
-            m = tile_foot_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.w, tx, ty);
+            if (PACKED) m = (uint32_t)keys[i] & 0xffu;
+            else {
+                const uint32_t id = (uint32_t)keys[i];
+                const float4 r0 = fa.records[3 * (size_t)id], r1 = fa.records[3 * (size_t)id + 1];
+                m = tile_foot_mask_any(r0.x, r0.y, r0.z, r0.w, r1.x, r1.w, tx, ty);
+            }
             if (mask8) mask8[i] = (uint8_t)m; else park32[i] = m;
         }
 #pragma unroll
@@ -732,15 +785,114 @@ __device__ void foot_lists(const FootArgs& fa, const unsigned long long* keys, u
             const uint32_t m = i < n ? (mask8 ? (uint32_t)mask8[i] : park32[i]) : 0u;
             const bool keep = (m >> warp) & 1u;
             const uint32_t bal = __ballot_sync(GSR_FULL, keep);
-            if (keep) fa.foot_list[run + __popc(bal & lt)] = fa.store_pos ? list_base + i : (uint32_t)keys[i];
+            if (keep) fa.foot_list[run + __popc(bal & lt)] = fa.store_pos ? list_base + i : (PACKED ? (uint32_t)keys[i] >> 8 : (uint32_t)keys[i]);
             run += __popc(bal);
         }
     }
 }
 static_assert(SORT_THREADS / 32 == GSR_FOOTS, "one sort warp per footprint");
+static_assert(SORT_CAP / 32 * GSR_FOOTS * 4 <= SORT_BUCKETS * 4, "the ballot matrix reuses the histogram storage");
+
+// The common case (n <= SORT_CAP, keys in shared memory):
+//   1. one thread per entry: footprint mask (PACKED: the low byte of the key, written by k_color_emit; otherwise the record is
+//      gathered and the mask computed here), and the warp's eight ballots per 32-entry row go to a ballot matrix bal[row][f];
+//   2. warp f counts column f; one atomic per tile reserves the lists' storage;
+//   3. warp f walks column f: entry (row, lane) goes to list f at start + entries before it (running popc).
+template <bool PACKED>
+__device__ void foot_lists_small(const FootArgs& fa, const unsigned long long* keys, uint32_t n, uint32_t list_base, int tile,
+                                 uint32_t* bal /*[SORT_CAP / 32 * 8]*/) {
+    __shared__ uint32_t f_cnt[GSR_FOOTS], f_off[GSR_FOOTS];
+    __shared__ int f_ok;
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t rows = (n + 31) >> 5;
+    const uint32_t* klo = reinterpret_cast<const uint32_t*>(keys);  // low word of key i
+    if (PACKED) {
+        for (uint32_t rbase = warp * 32; rbase < n; rbase += SORT_THREADS) {
+            const uint32_t i = rbase + lane;
+            const uint32_t m = i < n ? klo[2 * i] & 0xffu : 0u;
+            uint32_t mine = 0;
+#pragma unroll
+            for (int f = 0; f < GSR_FOOTS; f++) {
+                const uint32_t b = __ballot_sync(GSR_FULL, (m >> f) & 1u);
+                if (lane == (uint32_t)f) mine = b;
+            }
+            if (lane < GSR_FOOTS) bal[(rbase >> 5) * GSR_FOOTS + lane] = mine;
+        }
+    } else {
+        const int ty = tile / fa.gx, tx = tile - ty * fa.gx;
+        for (uint32_t c0 = 0; c0 < n; c0 += 2 * SORT_THREADS) {  // two gathers in flight per thread
+            float4 r0[2], r1[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint32_t i = c0 + u * SORT_THREADS + t;
+                r0[u] = r1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < n) {
+                    const float4* r = fa.records + 3 * (size_t)klo[2 * i];
+                    r0[u] = r[0];
+                    r1[u] = r[1];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint32_t rbase = c0 + u * SORT_THREADS + warp * 32;  // warp-uniform
+                if (rbase < n) {
+                    const uint32_t m = rbase + lane < n ? tile_foot_mask_any(r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].w, tx, ty) : 0u;
+                    uint32_t mine = 0;
+#pragma unroll
+                    for (int f = 0; f < GSR_FOOTS; f++) {
+                        const uint32_t b = __ballot_sync(GSR_FULL, (m >> f) & 1u);
+                        if (lane == (uint32_t)f) mine = b;
+                    }
+                    if (lane < GSR_FOOTS) bal[(rbase >> 5) * GSR_FOOTS + lane] = mine;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    {   // warp f: size of list f
+        uint32_t c = 0;
+        for (uint32_t r = lane; r < rows; r += 32) c += (uint32_t)__popc(bal[r * GSR_FOOTS + warp]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(GSR_FULL, c, o);
+        if (lane == 0) f_cnt[warp] = c;
+    }
+    __syncthreads();
+    if (t == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int f = 0; f < GSR_FOOTS; f++) total += f_cnt[f];
+        uint32_t start = 0;
+        int ok = 1;
+        if (total) {
+            start = atomicAdd(&fa.counters->foot_total, total);
+            if (start + total > fa.foot_cap || start + total < start) { ok = 0; atomicExch(&fa.counters->overflow, 1u); }
+        }
+        f_ok = ok;
+        uint2* fr = fa.foot_ranges + (size_t)tile * GSR_FOOTS;
+#pragma unroll
+        for (int f = 0; f < GSR_FOOTS; f++) {
+            f_off[f] = start;
+            fr[f] = ok ? make_uint2(start, f_cnt[f]) : make_uint2(0u, 0u);
+            start += f_cnt[f];
+        }
+    }
+    __syncthreads();
+    if (!f_ok || f_cnt[warp] == 0) return;
+    uint32_t run = f_off[warp];
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t r = 0; r < rows; r++) {
+        const uint32_t b = bal[r * GSR_FOOTS + warp];
+        if ((b >> lane) & 1u) {
+            const uint32_t i = r * 32 + lane;
+            fa.foot_list[run + __popc(b & lt)] = fa.store_pos ? list_base + i : (PACKED ? klo[2 * i] >> 8 : klo[2 * i]);
+        }
+        run += (uint32_t)__popc(b);
+    }
+}
 
 // Sorts the bucket of one tile (pairs[rg.x..rg.y) by (depth bits, id)) and writes the ids to point_list.
 // s: SORT_CAP u64 of shared memory, hist: SORT_BUCKETS+1 u32.  Block-wide (SORT_THREADS threads), ends without a barrier.
+template <bool PACKED>
 __device__ void sort_tile(const uint2 rg, unsigned long long* __restrict__ pairs, uint32_t* __restrict__ point_list, int keep_pairs,
                           unsigned long long* s, uint32_t* hist, const FootArgs& fa, int tile) {
     const uint32_t n = rg.y - rg.x;
@@ -752,9 +904,9 @@ __device__ void sort_tile(const uint2 rg, unsigned long long* __restrict__ pairs
     unsigned long long* g = pairs + rg.x;
     uint32_t* out = point_list + rg.x;
     if (n <= SORT_CAP) {
-        sort_bucket(g, n, out, keep_pairs ? g : nullptr, s, hist);
-        __syncthreads();  // the histogram is dead: its storage holds the footprint masks
-        foot_lists(fa, s, n, rg.x, tile, reinterpret_cast<uint8_t*>(hist), nullptr);
+        sort_bucket<PACKED>(g, n, out, keep_pairs ? g : nullptr, s, hist);
+        __syncthreads();  // the histogram is dead: its storage holds the ballot matrix
+        foot_lists_small<PACKED>(fa, s, n, rg.x, tile, hist);
         return;
     }
     // ---- large tile: chunks sorted in shared memory, cross-chunk steps in global (L2) memory ----
@@ -788,254 +940,25 @@ __device__ void sort_tile(const uint2 rg, unsigned long long* __restrict__ pairs
         }
     }
     __syncthreads();
-    foot_lists(fa, g, n, rg.x, tile, nullptr, out);  // masks parked in point_list until the ids are written
+    foot_lists<PACKED>(fa, g, n, rg.x, tile, nullptr, out);  // masks parked in point_list until the ids are written
     __syncthreads();
-    for (uint32_t i = tid; i < n; i += SORT_THREADS) out[i] = (uint32_t)g[i];
+    for (uint32_t i = tid; i < n; i += SORT_THREADS) {
+        const unsigned long long x = g[i];
+        const uint32_t id = PACKED ? (uint32_t)x >> 8 : (uint32_t)x;
+        out[i] = id;
+        if (PACKED && keep_pairs) g[i] = (x & 0xffffffff00000000ull) | id;
+    }
 }
 
 // stand-alone per-tile sort kernel (fusing it into the blend prologue was measured and dropped, profiles/r01_experiments.md)
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const uint2* __restrict__ ranges, unsigned long long* __restrict__ pairs,
+template <bool PACKED>
+__global__ void __launch_bounds__(SORT_THREADS, 5) k_sort_tiles(const uint2* __restrict__ ranges, unsigned long long* __restrict__ pairs,
                                                              uint32_t* __restrict__ point_list,
                                                              const gsr_counters* __restrict__ counters, int keep_pairs, const FootArgs fa) {
     if (counters->overflow) return;  // set by k_tile_scan, before this kernel started
     __shared__ unsigned long long s[SORT_CAP];
     __shared__ uint32_t hist[SORT_BUCKETS + 1];
-    sort_tile(ranges[blockIdx.x], pairs, point_list, keep_pairs, s, hist, fa, (int)blockIdx.x);
-}
-
-// =====================================================================================================
-// Kernel 5: per-tile front-to-back alpha blend (forward.cu:261-378)
-// One CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel footprint.
-//   stage   : 256 list entries per batch -> 48-byte records in shared memory (registers prefetch the next batch)
-//   cull    : one splat per lane against the warp's footprint (footprint_may_touch: exact box minimum of the quadratic form), ballot
-//   compact : surviving records are copied, in order, into the warp's private queue (warp prefix via popc)
-//   blend   : the queue is walked by all 32 lanes with the reference's per-pixel arithmetic
-// =====================================================================================================
-constexpr int BLEND_THREADS = 256;
-// NX = number of extra colour channels blended with the same weights (0, or 3 for the product frame's second image)
-template <int NX>
-struct BlendCfg {
-    static constexpr int REC = 48;               // staged record bytes per splat (stride 48 B: conflict-free 128-bit accesses)
-    static constexpr int XREC = NX ? 16 : 0;     // staged extra-colour bytes per splat, kept in a separate array (a 64-byte
-                                                 // combined stride costs 4-way bank conflicts on every staged load/store)
-    static constexpr int PAIR = NX ? 112 : 96;   // queue bytes per splat pair
-    static constexpr int QCAP = 62;              // queue entries per warp, an even number (flushed when fewer than 32 slots remain)
-    static constexpr int REC_BYTES = 2 * BLEND_THREADS * REC;                  // two staged batches
-    static constexpr int XREC_BYTES = 2 * BLEND_THREADS * XREC;
-    static constexpr int Q_BYTES = (BLEND_THREADS / 32) * (QCAP / 2) * PAIR;   // per-warp survivor queues
-    static constexpr int SMEM = REC_BYTES + XREC_BYTES + Q_BYTES;              // dynamic shared memory of k_blend<NX, .>
-};
-static_assert(BlendCfg<0>::SMEM <= 48 * 1024, "k_blend<.,0> must fit the default dynamic shared memory limit");
-
-// NX  : extra colour channels `extra[P,NX]` accumulated with the same per-splat weights into `out_extra[NX,H,W]`
-//       (+ T_final * bg like the colour image) — what a second rasterizer pass with colors_precomp = extra would
-//       return (gaussian_renderer/__init__.py:151-185), without re-running projection, binning, sort and the alpha math.
-// NC  : also record n_contrib (the 1-based list position of the last blended splat) for the backward pass.
-template <int NX, bool NC>
-__global__ void __launch_bounds__(BLEND_THREADS, NX ? 0 : 4) k_blend(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                                                         const float4* __restrict__ records, const float* __restrict__ extra,
-                                                         int W, int H, int gx, const float* __restrict__ bg,
-                                                         float* __restrict__ out_color, float* __restrict__ out_depth,
-                                                         float* __restrict__ out_alpha, float* __restrict__ out_extra,
-                                                         uint32_t* __restrict__ n_contrib,
-                                                         const gsr_counters* __restrict__ counters) {
-    typedef BlendCfg<NX> Cfg;
-    constexpr int REC = Cfg::REC, PAIR = Cfg::PAIR, BLEND_QCAP = Cfg::QCAP;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* sRec = reinterpret_cast<float4*>(smem_raw);
-    float4* sQ = reinterpret_cast<float4*>(smem_raw + Cfg::REC_BYTES + Cfg::XREC_BYTES);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.y * gx + blockIdx.x;
-    const int X0 = blockIdx.x * GSR_TILE + (warp & 1) * 8, Y0 = blockIdx.y * GSR_TILE + (warp >> 1) * 4;
-    const int pxi = X0 + (lane & 7), pyi = Y0 + (lane >> 3);
-    const bool inside = pxi < W && pyi < H;
-    const float pixx = (float)pxi, pixy = (float)pyi;
-    // warp-uniform values are routed through a broadcast so that the compiler keeps them in uniform registers instead of
-    // re-deriving them from the thread / CTA ids inside the cull loop (it rematerialises them there to stay at 64 registers)
-    const float cx = __shfl_sync(GSR_FULL, (float)X0 + FOOT_HX, 0), cy = __shfl_sync(GSR_FULL, (float)Y0 + FOOT_HY, 0);  // footprint centre
-    const uint32_t rec_base = __shfl_sync(GSR_FULL, (uint32_t)__cvta_generic_to_shared(sRec), 0);
-    const uint32_t q_base = __shfl_sync(GSR_FULL, (uint32_t)__cvta_generic_to_shared(sQ) + (uint32_t)warp * ((BLEND_QCAP / 2) * PAIR), 0);
-    const unsigned lt_mask = (1u << lane) - 1u;
-
-    uint2 range = ranges[tile];
-    if (counters->overflow) range = make_uint2(0u, 0u);
-    const int n = (int)(range.y - range.x);
-    const int nb = (n + BLEND_THREADS - 1) / BLEND_THREADS;
-
-    // T is the running transmittance while the pixel is live.  When the pixel terminates (forward.cu:349-354) T flips
-    // its sign: the magnitude keeps the final transmittance, and every later splat fails the `T(1-a) < 1e-4` test on its own
-    // (the product is negative), so there is no per-iteration "done" branch.  Pixels outside the image start dead.
-    float T = inside ? 1.0f : -1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f, E0 = 0.f, E1 = 0.f, E2 = 0.f;
-    uint32_t last = 0;
-    int qn = 0;  // entries in this warp's queue (warp-uniform)
-
-    // Blend every queued splat into this lane's pixel (reference arithmetic, forward.cu:330-366), two splats per
-    // iteration.  The queue stores splats pair-interleaved ({x0,x1},{y0,y1},{a0,a1},{-b0,-b1},{c0,c1},{o0,o1},{r0,r1},
-    // {g0,g1},{b0,b1},{depth0,depth1},{pos0,pos1}[,{e0,e0'},{e1,e1'},{e2,e2'}], 96 [112] B per pair) so that the per-splat arithmetic that does not depend
-    // on the running transmittance — power, alpha, 1-alpha, colour*alpha — runs on both halves of packed fp32
-    // registers (FFMA2/FMUL2/FADD2: two IEEE-rn results per instruction, bit-identical to the scalar ops; the sign of b
-    // is folded into the stored -b so the reference's `... - b*dx*dy` needs no negation).  Only expf, the 0.99 clamp
-    // and the serial transmittance updates stay scalar.  Branch-free: the three skip rules (power > 0, alpha < 1/255,
-    // T(1-alpha) < 1e-4) are predicates and a skipped splat contributes through a weight of exactly 0.
-    const f32x2 npx2 = pk2(-pixx, -pixx), npy2 = pk2(-pixy, -pixy), mhalf2 = pk2(-0.5f, -0.5f), mone2 = pk2(-1.0f, -1.0f),
-                one2 = pk2(1.0f, 1.0f);
-    auto drain = [&]() {
-        if (qn & 1) {  // complete the last pair with a splat that can never hit (opacity 0)
-            if (lane < 11 + NX) sts32(q_base + (uint32_t)(qn >> 1) * PAIR + 4 + lane * 8, 0.0f);
-        }
-        __syncwarp();
-        uint32_t qa = q_base;
-        const int np = (qn + 1) >> 1;
-        for (int k = 0; k < np; k++, qa += PAIR) {
-            const float4 L0 = lds128(qa), L1 = lds128(qa + 16), L2 = lds128(qa + 32), L3 = lds128(qa + 48), L4 = lds128(qa + 64);
-            float4 L5, L6;  // {pos0,pos1[,e0,e0']}, {e1,e1',e2,e2'}
-            if (NX) { L5 = lds128(qa + 80); L6 = lds128(qa + 96); }
-            else { const float2 t = lds64(qa + 80); L5 = make_float4(t.x, t.y, 0.f, 0.f); L6 = L5; }
-            const f32x2 dx = add2(pk2(L0.x, L0.y), npx2), dy = add2(pk2(L0.z, L0.w), npy2);
-            const f32x2 t1 = mul2(pk2(L2.x, L2.y), dy);   // c * dy
-            const f32x2 t3 = mul2(pk2(L1.x, L1.y), dx);   // a * dx
-            const f32x2 t2 = mul2(pk2(L1.z, L1.w), dx);   // (-b) * dx
-            const f32x2 t4 = mul2(dy, t1);                // dy * (c dy)
-            const f32x2 t5 = mul2(dy, t2);                // -(dy * (b dx))
-            const f32x2 t6 = fma2(dx, t3, t4);            // a dx^2 + c dy^2
-            const f32x2 pw = fma2(t6, mhalf2, t5);        // power = -0.5 (a dx^2 + c dy^2) - b dx dy
-            float p0, p1;
-            upk2(pw, p0, p1);
-            float a0, a1;
-            upk2(mul2(pk2(L2.z, L2.w), pk2(exp(p0), exp(p1))), a0, a1);  // opacity * exp(power); a packed expf was measured slower
-            a0 = min(0.99f, a0);
-            a1 = min(0.99f, a1);
-            const bool hit0 = !(p0 > 0.0f) && !(a0 < 1.0f / 255.0f), hit1 = !(p1 > 0.0f) && !(a1 < 1.0f / 255.0f);
-            const f32x2 al = pk2(a0, a1);
-            float om0, om1;
-            upk2(fma2(al, mone2, one2), om0, om1);        // 1 - alpha
-            float cr0, cr1, cg0, cg1, cb0, cb1, cd0, cd1;
-            upk2(mul2(pk2(L3.x, L3.y), al), cr0, cr1);    // colour * alpha
-            upk2(mul2(pk2(L3.z, L3.w), al), cg0, cg1);
-            upk2(mul2(pk2(L4.x, L4.y), al), cb0, cb1);
-            upk2(mul2(pk2(L4.z, L4.w), al), cd0, cd1);
-            float ex0 = 0.f, ex1 = 0.f, ey0 = 0.f, ey1 = 0.f, ez0 = 0.f, ez1 = 0.f;
-            if (NX) {
-                upk2(mul2(pk2(L5.z, L5.w), al), ex0, ex1);
-                upk2(mul2(pk2(L6.x, L6.y), al), ey0, ey1);
-                upk2(mul2(pk2(L6.z, L6.w), al), ez0, ez1);
-            }
-            {   // first splat of the pair
-                const bool act = hit0 && T > 0.0f;              // the pixel is live and the splat is not skipped
-                const float test_T = T * om0;
-                const bool live = act && !(test_T < 0.0001f);   // ... and it does not terminate the pixel: blend it
-                const float Tw = live ? T : 0.0f;
-                C0 = fmaf(Tw, cr0, C0); C1 = fmaf(Tw, cg0, C1); C2 = fmaf(Tw, cb0, C2); Dp = fmaf(Tw, cd0, Dp);
-                if (NX) { E0 = fmaf(Tw, ex0, E0); E1 = fmaf(Tw, ey0, E1); E2 = fmaf(Tw, ez0, E2); }
-                T = act ? (live ? test_T : -T) : T;             // blended / terminated (sign flip) / untouched
-                if (NC) last = live ? __float_as_uint(L5.x) : last;
-            }
-            {   // second splat of the pair
-                const bool act = hit1 && T > 0.0f;
-                const float test_T = T * om1;
-                const bool live = act && !(test_T < 0.0001f);
-                const float Tw = live ? T : 0.0f;
-                C0 = fmaf(Tw, cr1, C0); C1 = fmaf(Tw, cg1, C1); C2 = fmaf(Tw, cb1, C2); Dp = fmaf(Tw, cd1, Dp);
-                if (NX) { E0 = fmaf(Tw, ex1, E0); E1 = fmaf(Tw, ey1, E1); E2 = fmaf(Tw, ez1, E2); }
-                T = act ? (live ? test_T : -T) : T;
-                if (NC) last = live ? __float_as_uint(L5.y) : last;
-            }
-        }
-        qn = 0;
-        __syncwarp();
-    };
-
-    // Software pipeline over batches of 256 list entries, double-buffered in shared memory with ONE barrier per batch:
-    // while batch b is culled/blended out of buffer b&1, the records of batch b+1 (already in registers, gathered
-    // during batch b-1) are stored into the other buffer and the gather of batch b+2 is issued.
-    float4 ra = make_float4(0, 0, 0, 0), rb = ra, rc = ra, rd = ra;
-    uint32_t id_next = 0;
-    auto gather = [&](int batch, uint32_t id) {  // records of list entry (batch, tid) -> registers
-        if (batch * BLEND_THREADS + tid < n) {
-            const float4* r = records + 3 * (size_t)id;
-            ra = r[0]; rb = r[1]; rc = r[2];
-            rc.w = __uint_as_float((uint32_t)(batch * BLEND_THREADS + tid + 1));  // 1-based position in the tile list
-            if (NX) {
-                const float* e = extra + 3 * (size_t)id;
-                rd = make_float4(e[0], e[1], e[2], 0.0f);
-            }
-        }
-    };
-    auto stage = [&](int batch) {  // registers -> buffer batch&1
-        if (batch * BLEND_THREADS + tid < n) {
-            const uint32_t sa = rec_base + (uint32_t)((batch & 1) * BLEND_THREADS + tid) * REC;
-            sts128(sa, ra); sts128(sa + 16, rb); sts128(sa + 32, rc);
-            if (NX) sts128(rec_base + Cfg::REC_BYTES + (uint32_t)((batch & 1) * BLEND_THREADS + tid) * 16, rd);
-        }
-    };
-    if (tid < n) gather(0, point_list[range.x + tid]);
-    if (BLEND_THREADS + tid < n) id_next = point_list[range.x + BLEND_THREADS + tid];
-    stage(0);
-    gather(1, id_next);
-    if (2 * BLEND_THREADS + tid < n) id_next = point_list[range.x + 2 * BLEND_THREADS + tid];
-    __syncthreads();
-    bool warp_done = false;
-
-    for (int b = 0; b < nb; b++) {
-        const int cnt = min(BLEND_THREADS, n - b * BLEND_THREADS);
-        const uint32_t buf = rec_base + (uint32_t)((b & 1) * BLEND_THREADS) * REC;
-        if (!warp_done) {
-            for (int base = 0; base < cnt; base += 32) {
-                const int s = base + lane;
-                const uint32_t sa = buf + (uint32_t)s * REC;
-                bool keep = false;
-                float4 A, B;
-                if (s < cnt) {
-                    A = lds128(sa); B = lds128(sa + 16);
-                    keep = footprint_may_touch(A.x - cx, A.y - cy, A.z, A.w, B.x, B.w);
-                }
-                const unsigned mask = __ballot_sync(GSR_FULL, keep);
-                if (mask) {
-                    if (keep) {
-                        const uint32_t q = (uint32_t)(qn + __popc(mask & lt_mask));
-                        const uint32_t qa = q_base + (q >> 1) * PAIR + (q & 1) * 4;
-                        const float4 Cc = lds128(sa + 32);
-                        sts32(qa, A.x); sts32(qa + 8, A.y); sts32(qa + 16, A.z); sts32(qa + 24, -A.w);
-                        sts32(qa + 32, B.x); sts32(qa + 40, B.y); sts32(qa + 48, Cc.x); sts32(qa + 56, Cc.y);
-                        sts32(qa + 64, Cc.z); sts32(qa + 72, B.z); sts32(qa + 80, Cc.w);
-                        if (NX) {
-                            const float4 Dd = lds128(rec_base + Cfg::REC_BYTES + (uint32_t)((b & 1) * BLEND_THREADS + s) * 16);
-                            sts32(qa + 88, Dd.x); sts32(qa + 96, Dd.y); sts32(qa + 104, Dd.z);
-                        }
-                    }
-                    qn += __popc(mask);
-                    if (qn > BLEND_QCAP - 32) {
-                        drain();
-                        if (__all_sync(GSR_FULL, T < 0.0f)) { warp_done = true; break; }
-                    }
-                }
-            }
-        }
-        if (b + 1 < nb) {
-            stage(b + 1);
-            gather(b + 2, id_next);
-            if ((b + 3) * BLEND_THREADS + tid < n) id_next = point_list[range.x + (b + 3) * BLEND_THREADS + tid];
-            // whole tile finished?  (also publishes buffer (b+1)&1 and retires buffer b&1)
-            if (__syncthreads_count(T < 0.0f) == BLEND_THREADS) break;
-        }
-    }
-    if (qn) drain();
-    if (inside) {
-        const float T_out = fabsf(T);  // final transmittance, whether the pixel terminated or the list ran out
-        const size_t pid = (size_t)W * pyi + pxi;
-        const size_t HW = (size_t)H * W;
-        out_alpha[pid] = 1 - T_out;
-        if (NC) n_contrib[pid] = last;
-        out_color[pid] = C0 + T_out * bg[0];
-        out_color[HW + pid] = C1 + T_out * bg[1];
-        out_color[2 * HW + pid] = C2 + T_out * bg[2];
-        out_depth[pid] = Dp;
-        if (NX) {
-            out_extra[pid] = E0 + T_out * bg[0];
-            out_extra[HW + pid] = E1 + T_out * bg[1];
-            out_extra[2 * HW + pid] = E2 + T_out * bg[2];
-        }
-    }
+    sort_tile<PACKED>(ranges[blockIdx.x], pairs, point_list, keep_pairs, s, hist, fa, (int)blockIdx.x);
 }
 
 // =====================================================================================================
@@ -1115,42 +1038,22 @@ static int sh_bulk_mode() {  // GSR_SH_STAGING=cpasync selects the LDGSTS path, 
     }
     return mode;
 }
+template <int DEG, bool TIGHT, bool PACKED>
+static void launch_ce_v(bool vec, bool win, const EmitParams& ep, cudaStream_t st) {
+    const int grid = (ep.P + PRE_THREADS - 1) / PRE_THREADS;  // sized for P; blocks past the visible list exit at once
+    if (DEG < 0) k_color_emit<-1, false, false, false, TIGHT, PACKED><<<grid, PRE_THREADS, 0, st>>>(ep);
+    else if (win && sh_bulk_mode()) k_color_emit<DEG, true, true, true, TIGHT, PACKED><<<grid, PRE_THREADS, 0, st>>>(ep);
+    else if (vec && sh_bulk_mode()) k_color_emit<DEG, true, true, false, TIGHT, PACKED><<<grid, PRE_THREADS, 0, st>>>(ep);
+    else if (vec) k_color_emit<DEG, true, false, false, TIGHT, PACKED><<<grid, PRE_THREADS, 0, st>>>(ep);
+    else k_color_emit<DEG, false, false, false, TIGHT, PACKED><<<grid, PRE_THREADS, 0, st>>>(ep);
+}
 template <int DEG>
-static void launch_pre(bool vec, bool win, const PreParams& pp, cudaStream_t st) {
-    const int grid = (pp.P + PRE_THREADS - 1) / PRE_THREADS;
-    if (win && sh_bulk_mode()) k_preprocess<DEG, true, true, true><<<grid, PRE_THREADS, 0, st>>>(pp);
-    else if (vec && sh_bulk_mode()) k_preprocess<DEG, true, true><<<grid, PRE_THREADS, 0, st>>>(pp);
-    else if (vec) k_preprocess<DEG, true, false><<<grid, PRE_THREADS, 0, st>>>(pp);
-    else k_preprocess<DEG, false, false><<<grid, PRE_THREADS, 0, st>>>(pp);
+static void launch_color_emit(bool vec, bool win, bool tight, bool packed, const EmitParams& ep, cudaStream_t st) {
+    if (tight) { if (packed) launch_ce_v<DEG, true, true>(vec, win, ep, st); else launch_ce_v<DEG, true, false>(vec, win, ep, st); }
+    else       { if (packed) launch_ce_v<DEG, false, true>(vec, win, ep, st); else launch_ce_v<DEG, false, false>(vec, win, ep, st); }
 }
 
-template <int NX, bool NC>
-static void launch_blend_t(const BlendArgs& a, cudaStream_t st) {
-    typedef BlendCfg<NX> Cfg;
-    if (NX) {  // > 48 KB of dynamic shared memory: opt in once per device
-        static bool configured[64] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev >= 0 && dev < 64 && !configured[dev]) {
-            cudaFuncSetAttribute(k_blend<NX, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-            configured[dev] = true;
-        }
-    }
-    k_blend<NX, NC><<<dim3(a.gx, a.gy), BLEND_THREADS, Cfg::SMEM, st>>>(a.ranges, a.point_list, a.records, a.extra, a.W, a.H, a.gx, a.bg,
-                                                                       a.out_color, a.out_depth, a.out_alpha, a.out_extra, a.n_contrib, a.counters);
-}
-// The 6-channel variant runs at 70 registers / 3 CTAs per SM; holding it to 64 registers / 4 CTAs (shorter queues, 92 B of
-// spills) was measured slower: 780 vs 862 product frames/s (profiles/r01_experiments.md).
-static int blend_legacy() {  // GSR_BLEND=legacy: the round-1 tile-staged blend (bit-exact only), kept for A/B measurements
-    static int m = -1;
-    if (m < 0) { const char* e = getenv("GSR_BLEND"); m = (e && strcmp(e, "legacy") == 0) ? 1 : 0; }
-    return m;
-}
-static void launch_blend(const BlendArgs& a, cudaStream_t st) {
-    if (!blend_legacy()) { launch_blend_lists(a, st); return; }
-    if (a.extra) { if (a.n_contrib) launch_blend_t<3, true>(a, st); else launch_blend_t<3, false>(a, st); }
-    else         { if (a.n_contrib) launch_blend_t<0, true>(a, st); else launch_blend_t<0, false>(a, st); }
-}
+static void launch_blend(const BlendArgs& a, cudaStream_t st) { launch_blend_lists(a, st); }
 
 int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,
                  int32_t* radii, const float* extra_colors, float* out_extra, int flags, cudaStream_t st) {
@@ -1225,20 +1128,10 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     pp.radii = radii; pp.tile_count = (uint32_t*)(img + il.tile_count); pp.tile_big = (uint32_t*)(img + il.tile_big);
     pp.ranks = (uint32_t*)(geo + gl.ranks); pp.counters = counters;
 
-    if (f->colors_precomp) launch_pre<-1>(false, false, pp, st);
-    else {
-        const bool vec = (f->M % 4 == 0) && (((uintptr_t)f->shs & 15) == 0);
-        // 4-byte aligned rows (e.g. M = 25): the aligned window of sh_nv(D, true) float4 must fit inside every row
-        const bool win = !vec && (((uintptr_t)f->shs & 15) == 0) && (size_t)f->M * 12 >= (size_t)sh_nv(D, true) * 16;
-        switch (D) {
-            case 0: launch_pre<0>(vec, win, pp, st); break;
-            case 1: launch_pre<1>(vec, win, pp, st); break;
-            case 2: launch_pre<2>(vec, win, pp, st); break;
-            default: launch_pre<3>(vec, win, pp, st); break;
-        }
-    }
+    pp.vis_list = (uint32_t*)(geo + gl.vis_list);
+    k_project<<<(f->P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, st>>>(pp);
     prof_mark(1, st);
-    int rc = check_launch("gsr_forward/preprocess", debug, st);
+    int rc = check_launch("gsr_forward/project", debug, st);
     if (rc) return rc;
 
     uint2* ranges = (uint2*)(img + il.ranges);
@@ -1246,20 +1139,37 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     prof_mark(2, st);
     if ((rc = check_launch("gsr_forward/tile_scan", debug, st))) return rc;
 
-    if (pp.tight)
-        k_emit<true><<<(f->P + 255) / 256, 256, 0, st>>>(f->P, il.gx, il.gy, radii, pp.records, pp.ranks, ranges, (uint32_t*)(img + il.tile_fill),
-                                                         (uint2*)(bin + bl.pairs), counters);
-    else
-        k_emit<false><<<(f->P + 255) / 256, 256, 0, st>>>(f->P, il.gx, il.gy, radii, pp.records, pp.ranks, ranges, (uint32_t*)(img + il.tile_fill),
-                                                          (uint2*)(bin + bl.pairs), counters);
+    // footprint masks travel in the low byte of the pair's id word when the ids fit 24 bits; GSR_PACKED_KEYS=0 forces the
+    // general path (masks computed by k_sort_tiles from gathered records), which is what P > 2^24 uses
+    static int packed_ok = -1;
+    if (packed_ok < 0) { const char* e = getenv("GSR_PACKED_KEYS"); packed_ok = (e && e[0] == '0') ? 0 : 1; }
+    const bool packed = packed_ok && f->P <= (1 << 24);
+    EmitParams ep;
+    ep.P = f->P; ep.M = f->M; ep.gx = il.gx; ep.gy = il.gy; ep.for_backward = pp.for_backward;
+    ep.means3D = f->means3D; ep.shs = f->shs; ep.colors_precomp = f->colors_precomp; ep.campos = f->campos;
+    ep.records = pp.records; ep.clamped = pp.clamped; ep.radii = radii; ep.ranks = pp.ranks; ep.vis_list = pp.vis_list;
+    ep.ranges = ranges; ep.tile_fill = (uint32_t*)(img + il.tile_fill); ep.pairs = (uint2*)(bin + bl.pairs); ep.counters = counters;
+    if (f->colors_precomp) launch_color_emit<-1>(false, false, pp.tight, packed, ep, st);
+    else {
+        const bool vec = (f->M % 4 == 0) && (((uintptr_t)f->shs & 15) == 0);
+        // 4-byte aligned rows (e.g. M = 25): the aligned window of sh_nv(D, true) float4 must fit inside every row
+        const bool win = !vec && (((uintptr_t)f->shs & 15) == 0) && (size_t)f->M * 12 >= (size_t)sh_nv(D, true) * 16;
+        switch (D) {
+            case 0: launch_color_emit<0>(vec, win, pp.tight, packed, ep, st); break;
+            case 1: launch_color_emit<1>(vec, win, pp.tight, packed, ep, st); break;
+            case 2: launch_color_emit<2>(vec, win, pp.tight, packed, ep, st); break;
+            default: launch_color_emit<3>(vec, win, pp.tight, packed, ep, st); break;
+        }
+    }
     prof_mark(3, st);
-    if ((rc = check_launch("gsr_forward/emit", debug, st))) return rc;
+    if ((rc = check_launch("gsr_forward/color_emit", debug, st))) return rc;
 
     const int keep_pairs = (flags & GSR_FLAG_SORTED_KEYS) ? 1 : 0;
     uint32_t* n_contrib = (flags & GSR_FLAG_FOR_BACKWARD) ? (uint32_t*)(img + il.n_contrib) : nullptr;
     FootArgs fa{pp.records, (uint32_t*)(bin + bl.foot_list), (uint2*)(img + il.foot_ranges), counters,
                 (uint32_t)(bl.foot_capacity > 0xffffffffull ? 0xffffffffull : bl.foot_capacity), n_contrib ? 1 : 0, il.gx};
-    k_sort_tiles<<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters, keep_pairs, fa);
+    if (packed) k_sort_tiles<true><<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters, keep_pairs, fa);
+    else k_sort_tiles<false><<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters, keep_pairs, fa);
     prof_mark(4, st);
     if ((rc = check_launch("gsr_forward/sort", debug, st))) return rc;
     BlendArgs ba{ranges, (const uint32_t*)(bin + bl.point_list), pp.records, extra_colors, f->W, f->H, il.gx, il.gy, f->bg,

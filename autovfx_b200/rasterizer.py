@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import collections
 import ctypes as C
+import weakref
 from typing import Dict, NamedTuple, Optional, Tuple
 
 import torch
@@ -114,18 +115,26 @@ def get_tight_tiles() -> bool:
 class FrameTicket:
     """Handle on the device-side counters of one forward call (gsr_counters, include/gsr_b200.h)."""
 
-    __slots__ = ("event", "slot", "capacity", "_state")
+    __slots__ = ("event", "slot", "capacity", "_state", "_snap", "__weakref__")
 
     def __init__(self, event, slot, capacity, state):
         self.event, self.slot, self.capacity, self._state = event, slot, capacity, state
+        self._snap = None
 
     def ready(self) -> bool:
         return self.event.query()
 
+    def snapshot(self) -> None:
+        """Copy the counters out of the shared pinned ring slot (called on first use, and by the ring before it recycles
+        the slot, so a ticket held across more than RING later forwards still reads its own frame)."""
+        if self._snap is None:
+            self.event.synchronize()
+            self._snap = [int(x) for x in self.slot.tolist()]
+
     def stats(self) -> Dict[str, int]:
         """Blocks until the frame's counters have reached the host."""
-        self.event.synchronize()
-        c = self.slot
+        self.snapshot()
+        c = self._snap
         return {"num_rendered": int(c[0]), "overflow": int(c[1]), "max_tile": int(c[2]), "trapped": int(c[3]),
                 "num_visible": int(c[4]), "foot_total": int(c[5]) & 0xffffffff, "exact_redos": int(c[6]),
                 "capacity": int(self.capacity)}
@@ -139,8 +148,8 @@ class FrameTicket:
 
 def needed_capacity(stats: Dict[str, int]) -> int:
     """Binning capacity (instances) a frame with these counters needs: R instances, and footprint lists of at most
-    GSR_FOOT_FACTOR (= 2) entries per instance of capacity."""
-    return max(int(stats["num_rendered"]), (int(stats["foot_total"]) + 1) // 2)
+    GSR_FOOT_FACTOR (= 3) entries per instance of capacity."""
+    return max(int(stats["num_rendered"]), (int(stats["foot_total"]) + 2) // 3)
 
 
 class _DeviceState:
@@ -151,6 +160,7 @@ class _DeviceState:
         self.capacity = 1 << 20
         self.pinned = torch.zeros((self.RING, 8), dtype=torch.int32).pin_memory()
         self.events = [None] * self.RING
+        self.tickets = [None] * self.RING  # weak references to the ticket reading each slot
         self.cursor = 0
         self.cache: Dict[Tuple, torch.Tensor] = {}
         self.last_ticket: Optional[FrameTicket] = None
@@ -171,9 +181,23 @@ class _DeviceState:
         ev = self.events[i]
         if ev is not None:
             ev.synchronize()  # the slot is only reused once its previous copy has landed
+            old = self.tickets[i]() if self.tickets[i] is not None else None
+            if old is not None:
+                old.snapshot()  # a ticket still alive keeps its own counters
         ev = torch.cuda.Event()
         self.events[i] = ev
         return self.pinned[i], ev
+
+    def issue_ticket(self, counters: torch.Tensor, stream, capacity: int) -> "FrameTicket":
+        """Async copy of a frame's 32-byte counters into the next pinned ring slot + the event that says it has landed."""
+        i = self.cursor
+        slot, ev = self.next_slot()
+        slot.copy_(counters, non_blocking=True)
+        ev.record(stream)
+        ticket = FrameTicket(ev, slot, capacity, self)
+        self.tickets[i] = weakref.ref(ticket)
+        self.last_ticket = ticket
+        return ticket
 
     def workspace(self, kind: str, nbytes: int, fresh: bool) -> torch.Tensor:
         if fresh:
@@ -332,15 +356,13 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
                 radii = radii_prev.clone()
             elif radii.data_ptr() != radii_prev.data_ptr():
                 radii.copy_(radii_prev)
-            slot, ev = st.next_slot()
-            slot.copy_(image[:32].view(torch.int32), non_blocking=True)
-            ev.record(stream)
-            ticket = FrameTicket(ev, slot, _L.gsr_binning_capacity(binning.numel()), st)
-            st.last_ticket = ticket
+            ticket = st.issue_ticket(image[:32].view(torch.int32), stream, _L.gsr_binning_capacity(binning.numel()))
             if do_sync and ticket.stats()["overflow"]:
                 raise RuntimeError("autovfx_b200: reused geometry pass found an overflowed first pass")
             keep = (means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, view, proj, campos, extra)
             return color, depth, alpha, radii, (geom, binning, image), ticket, keep
+        if not for_backward:
+            st.geom_cache.pop(stream.cuda_stream, None)  # the shared workspaces are about to be rewritten (also by a P == 0 call)
         while True:
             cap = st.capacity
             binning = st.workspace("binning", _L.gsr_binning_bytes(cap), for_backward)
@@ -351,11 +373,7 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
                                       radii.data_ptr() if P > 0 else None, _ptr(extra) if P > 0 else None,
                                       _ptr(extra_out) if extra is not None and P > 0 else None, flags, C.c_void_p(stream.cuda_stream))
             _lib.check(rc, "gsr_forward")
-            slot, ev = st.next_slot()
-            slot.copy_(image[:32].view(torch.int32), non_blocking=True)
-            ev.record(stream)
-            ticket = FrameTicket(ev, slot, _L.gsr_binning_capacity(binning.numel()), st)
-            st.last_ticket = ticket
+            ticket = st.issue_ticket(image[:32].view(torch.int32), stream, _L.gsr_binning_capacity(binning.numel()))
             if not do_sync:
                 break
             s = ticket.stats()
@@ -467,12 +485,7 @@ class PreparedForward:
         rc = _L.gsr_forward_multi(C.byref(fr), C.byref(self.ws), self.out_ptrs[0], self.out_ptrs[1], self.out_ptrs[2], self.out_ptrs[3],
                                   self.extra_ptrs[0], self.extra_ptrs[1], self.flags, C.c_void_p(stream.cuda_stream))
         _lib.check(rc, "gsr_forward")
-        slot, ev = st.next_slot()
-        slot.copy_(self._counters, non_blocking=True)
-        ev.record(stream)
-        ticket = FrameTicket(ev, slot, self._capacity_instances, st)
-        st.last_ticket = ticket
-        return ticket
+        return st.issue_ticket(self._counters, stream, self._capacity_instances)
 
 
 def _cpu_copy(items):
@@ -481,14 +494,17 @@ def _cpu_copy(items):
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
-    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings)
+    # Whether a backward can follow is decided HERE: inside autograd.Function.forward grad mode is always off, and the
+    # reference's eval loops (scene_representation.py:355 render_from_3DGS) pass nn.Parameters under torch.no_grad().
+    need_bw = torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in
+                                              (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings,
+                                     need_bw)
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
-        need_bw = any(isinstance(t, torch.Tensor) and t.requires_grad for t in
-                      (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings, need_bw=True):
         if raster_settings.debug:
             # reference debug behaviour (__init__.py:83-90): keep a CPU copy of the arguments and dump it if the call fails
             cpu_args = _cpu_copy((raster_settings.bg, means3D, colors_precomp, opacities, scales, rotations, raster_settings.scale_modifier,
@@ -509,6 +525,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.ticket = ticket
         ctx.has = (sh.numel() != 0, colors_precomp.numel() != 0, scales.numel() != 0, cov3Ds_precomp.numel() != 0)
         ctx.needs = need_bw
+        ctx.in_shapes = tuple(tuple(t.shape) for t in (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
         k_means3D, k_shs, k_colors, _k_op, k_scales, k_rot, k_cov, k_bg, k_view, k_proj, k_campos, _k_extra = keep
         e = torch.empty(0, device=means3D.device)
         ctx.save_for_backward(k_colors if k_colors is not None else e, k_means3D, k_scales if k_scales is not None else e,
@@ -520,7 +537,7 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out_color, grad_out_depth, grad_out_alpha, _):
         if not ctx.needs:
-            return (None,) * 9
+            return (None,) * 10
         s = ctx.raster_settings
         (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, image, alpha, bg, view, proj,
          campos) = ctx.saved_tensors
@@ -530,6 +547,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         P = means3D.size(0)
         H, W = int(s.image_height), int(s.image_width)
         M = sh.size(1) if sh.numel() else 0
+        has_sh, has_col, has_scale, has_cov = ctx.has
+        if P == 0:  # empty scene: the reference returns empty gradients (rasterize_points.cu:158-168 with P = 0)
+            return tuple(torch.zeros(shp, dtype=torch.float32, device=device) for shp in ctx.in_shapes) + (None, None)
         with torch.cuda.device(device):
             def img_grad(g, c):
                 if g is None:
@@ -560,10 +580,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                                       s.tanfovy, g_color, g_depth, g_alpha, sh, s.sh_degree, campos, alpha, s.debug)), "snapshot_bw.dump")
                 print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
             _lib.check(rc, "gsr_backward")
-        has_sh, has_col, has_scale, has_cov = ctx.has
         # reference order (__init__.py:146-156): means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, settings
         return (dL_dmeans3D, dL_dmeans2D, dL_dsh if has_sh else None, dL_dcolors if has_col else None, dL_dopacity,
-                dL_dscales if has_scale else None, dL_drotations if has_scale else None, dL_dcov3D if has_cov else None, None)
+                dL_dscales if has_scale else None, dL_drotations if has_scale else None, dL_dcov3D if has_cov else None, None, None)
 
 
 class GaussianRasterizer(nn.Module):

@@ -278,6 +278,8 @@ class FrameLoop:
             i, slot, ticket, ev = entry
             if not ticket.ok():  # binning overflow: re-render this frame synchronously with the grown capacity
                 self.rerendered += 1
+                if ev is not None:
+                    ev.synchronize()  # the earlier (useless) async copy of this slot must not race the re-render / re-copy
                 if before_frame is not None:  # later frames may have edited the resident arrays: restore frame i's scene first
                     g_i = before_frame(i)
                     if g_i is not None:

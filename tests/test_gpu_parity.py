@@ -543,3 +543,52 @@ def test_debug_mode_dumps_a_snapshot_on_failure(dev, tmp_path, monkeypatch):
     # and a correct call in debug mode still works (synchronous error checking after every stage)
     out = rast(a["means3D"], torch.zeros_like(a["means3D"]), a["opacities"], shs=a["shs"], scales=a["scales"], rotations=a["rotations"])
     assert torch.equal(out[0], Hh.run_ours(a)["color"])
+
+
+def test_parameters_under_no_grad_take_the_inference_path(dev):
+    """The reference's eval loops pass nn.Parameters under torch.no_grad() (scene_representation.py:355): no backward buffers
+    are kept and the second pass of the product frame reuses the first pass's geometry."""
+    from autovfx_b200 import rasterizer as R
+    from autovfx_b200.rasterizer import GaussianRasterizer
+    a = Hh.resolve(Hh.case_inputs("config1"), dev)
+    par = {k: torch.nn.Parameter(a[k].clone()) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+    rast = GaussianRasterizer(Hh.settings_from(a))
+    m2 = torch.zeros_like(a["means3D"])
+    normals = (torch.nn.functional.normalize(a["means3D"]) * 0.5 + 0.5).contiguous()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.no_grad():
+        first = rast(par["means3D"], m2, par["opacities"], shs=par["shs"], scales=par["scales"], rotations=par["rotations"])
+        key = R._state(dev).geom_cache[stream][0]  # the inference path remembered the geometry ...
+        second = rast(par["means3D"], m2, par["opacities"], colors_precomp=normals, scales=par["scales"], rotations=par["rotations"])
+        assert R._state(dev).geom_cache[stream][0] == key  # ... and the second pass hit it (cache untouched)
+    assert not first[0].requires_grad and first[0].grad_fn is None
+    assert torch.equal(first[1], second[1]) and torch.equal(first[3], second[3])
+    # with gradients enabled the same call keeps its buffers and differentiates
+    out = rast(par["means3D"], torch.zeros_like(m2, requires_grad=True), par["opacities"], shs=par["shs"], scales=par["scales"], rotations=par["rotations"])
+    out[0].sum().backward()
+    assert par["means3D"].grad is not None and torch.equal(out[0].detach(), first[0])
+
+
+def test_backward_with_no_gaussians_returns_empty_grads(dev):
+    from autovfx_b200.rasterizer import GaussianRasterizer
+    a = Hh.resolve(Hh.case_inputs("small_sh"), dev)
+    r = GaussianRasterizer(Hh.settings_from(a))
+    leaf = lambda *s: torch.zeros(s, device=dev, requires_grad=True)  # noqa: E731
+    m3, m2, op, sh, sc, ro = leaf(0, 3), leaf(0, 3), leaf(0, 1), leaf(0, 16, 3), leaf(0, 3), leaf(0, 4)
+    color, depth, alpha, radii = r(m3, m2, op, shs=sh, scales=sc, rotations=ro)
+    (color.sum() + depth.sum() + alpha.sum()).backward()
+    for t in (m3, m2, op, sh, sc, ro):
+        assert t.grad is not None and t.grad.shape == t.shape
+
+
+def test_ticket_outlives_the_counter_ring(dev):
+    """A FrameTicket read after more than RING later forwards still reports its own frame's counters."""
+    from autovfx_b200 import rasterizer as R
+    a = Hh.resolve(Hh.case_inputs("small_sh"), dev)
+    b = Hh.resolve(Hh.case_inputs("config1"), dev)
+    sa, sb = Hh.settings_from(a), Hh.settings_from(b)
+    want = Hh.run_ours(a)["stats"]["num_rendered"]
+    held = R.forward_raw(a["means3D"], a["shs"], None, a["opacities"], a["scales"], a["rotations"], None, sa, sync=False)[5]
+    for _ in range(R._DeviceState.RING + 6):
+        R.forward_raw(b["means3D"], b["shs"], None, b["opacities"], b["scales"], b["rotations"], None, sb, sync=False)
+    assert held.stats()["num_rendered"] == want

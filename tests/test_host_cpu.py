@@ -35,8 +35,8 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_workspace_size_queries():
     from autovfx_b200._lib import lib
     assert lib.gsr_geom_bytes(0) > 0
-    assert 3_000_000 * (48 + 32 + 24 + 1) <= lib.gsr_geom_bytes(3_000_000) < 3_000_000 * 106
-    assert lib.gsr_binning_bytes(1000) == 20 * 1000  # 8 (pair) + 4 (list) + 2x4 (footprint lists) B/instance (reference: 24 B + sort temp)
+    assert 3_000_000 * (48 + 32 + 24 + 1) <= lib.gsr_geom_bytes(3_000_000) < 3_000_000 * 110
+    assert lib.gsr_binning_bytes(1000) == 24 * 1000  # 8 (pair) + 4 (list) + 3x4 (footprint lists) B/instance (reference: 24 B + sort temp)
     assert lib.gsr_binning_capacity(lib.gsr_binning_bytes(12345)) == 12345
     a, b = lib.gsr_image_bytes(1920, 1080), lib.gsr_image_bytes(256, 256)
     assert a > b > 256 * 256 * 4
