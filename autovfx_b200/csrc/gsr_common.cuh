@@ -34,7 +34,7 @@ struct GeomLayout {
     }
 };
 struct ImageLayout {
-    size_t counters, tile_count, tile_big, tile_fill, ranges, foot_ranges, n_contrib, total;
+    size_t counters, tile_count, tile_big, tile_fill, ranges, n_contrib, total;
     int gx, gy, tiles;
     __host__ __device__ ImageLayout(int W, int H) {
         gx = (W + GSR_TILE - 1) / GSR_TILE;
@@ -46,27 +46,27 @@ struct ImageLayout {
         tile_big = o;   o = align_up(o + 4 * (size_t)tiles, 256);  // instances of Gaussians touching > 8 tiles
         tile_fill = o;  o = align_up(o + 4 * (size_t)tiles, 256);  // cursor for the latter, written by the scan
         ranges = o;     o = align_up(o + 8 * (size_t)tiles, 256);
-        foot_ranges = o; o = align_up(o + 8 * (size_t)GSR_FOOTS * tiles, 256);  // {start, count} of every warp footprint's list
         n_contrib = o;  o = align_up(o + 4 * (size_t)W * H, 256);
         total = o + 256;
     }
     // bytes [0, zero_bytes) are cleared at the start of every frame (counters + tile_count + tile_big)
     __host__ __device__ size_t zero_bytes() const { return tile_fill; }
 };
-// bytes of binning workspace per instance of capacity: 8 (pair) + 4 (point_list) + 4 * GSR_FOOT_FACTOR (footprint lists)
-#define GSR_FOOT_FACTOR 3
-#define GSR_BIN_BYTES (12 + 4 * GSR_FOOT_FACTOR)
+// Binning workspace: 8 (pair) + 4 (point_list) bytes per instance of capacity, plus the footprint ballot matrix: one 32-byte
+// row per 32 list entries, rows of tile t starting at (ranges[t].x >> 5) + t -> at most capacity / 32 + tiles + 1 rows.
+#define GSR_BAL_SLACK_TILES 131072  // tile count the fixed part of the workspace provides rows for (e.g. 8192 x 4096 pixels)
 struct BinLayout {
-    size_t pairs, point_list, foot_list, foot_capacity, total, capacity;
+    size_t pairs, point_list, bal, bal_rows, total, capacity;
     __host__ __device__ explicit BinLayout(size_t cap) {
         capacity = cap;
         pairs = 0;
         point_list = 8 * cap;
-        foot_list = 12 * cap;             // per-footprint survivor lists, allocated by k_sort_tiles from one cursor
-        foot_capacity = GSR_FOOT_FACTOR * cap;
-        total = (size_t)GSR_BIN_BYTES * cap;
+        bal = align_up(12 * cap, 256);
+        bal_rows = cap / 32 + GSR_BAL_SLACK_TILES + 2;
+        total = 13 * cap + fixed_bytes();  // >= bal + 32 * bal_rows
     }
-    __host__ __device__ static size_t capacity_of(size_t bytes) { return bytes / GSR_BIN_BYTES; }
+    __host__ __device__ static size_t fixed_bytes() { return 32 * (size_t)GSR_BAL_SLACK_TILES + 512; }
+    __host__ __device__ static size_t capacity_of(size_t bytes) { return bytes > fixed_bytes() ? (bytes - fixed_bytes()) / 13 : 0; }
 };
 
 // ---- camera block staged in shared memory ------------------------------------------------------------
@@ -318,10 +318,11 @@ struct BlendArgs {
     const uint2* ranges; const uint32_t* point_list; const float4* records; const float* extra;
     int W, H, gx, gy; const float* bg; float *out_color, *out_depth, *out_alpha, *out_extra; uint32_t* n_contrib;
     gsr_counters* counters;
-    const uint2* foot_ranges; const uint32_t* foot_list;
+    const uint32_t* bal;  // footprint ballot matrix [rows][GSR_FOOTS], rows of tile t from bal_row_base(ranges[t].x, t)
     int exact;  // GSR_FLAG_EXACT_IMAGES
 };
 void launch_blend_lists(const BlendArgs& a, cudaStream_t st);
+__host__ __device__ inline size_t bal_row_base(uint32_t range_x, int tile) { return (size_t)(range_x >> 5) + (size_t)tile; }
 
 void set_error(const char* fmt, ...);
 const char* last_error();

@@ -192,7 +192,8 @@ __device__ __forceinline__ void cov3d_ref_rounding(float sx, float sy, float sz,
 // One thread per Gaussian: near cull, 3D covariance, EWA projection, conic, radius, tile rectangle (forward.cu:155-256 minus the
 // colour), the per-tile histogram with ranked tickets, and the compact list of visible Gaussians the colour + emission
 // kernel walks.  Only 44 bytes per Gaussian are read; the 192-byte SH row is not touched here.
-__global__ void __launch_bounds__(PRE_THREADS, 8) k_project(const PreParams p) {
+template <int MINB>
+__global__ void __launch_bounds__(PRE_THREADS, MINB) k_project(const PreParams p) {
     __shared__ CamConsts cam;
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid < 16) cam.view[tid] = p.view[tid];
@@ -546,19 +547,36 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_color_emit(const EmitParams 
         }
     }
     // > 8 tiles: walked by the whole warp, positions from the per-tile cursor initialised by k_tile_scan; the tight-tile
-    // test is re-evaluated on the same stored values k_project used (bitwise same decision)
+    // test is re-evaluated on the same stored values k_project used (bitwise same decision).  The owner computes the strip
+    // context once; the warp's lanes then only evaluate the two strips of their tile.
     {
         const bool big = cnt > 8;
-        const uint32_t pay[8] = {lo_id, dbits, __float_as_uint(r0.x), __float_as_uint(r0.y), __float_as_uint(r0.z),
-                                 __float_as_uint(r0.w), __float_as_uint(r1.x), __float_as_uint(r1.w)};
+        StripCtx bc = {};
+        if (PACKED && big) {
+            const float um = fmaxf(r0.x - (float)(x0 * GSR_TILE), (float)(x1 * GSR_TILE) - r0.x);
+            const float vm = fmaxf(r0.y - (float)(y0 * GSR_TILE), (float)(y1 * GSR_TILE) - r0.y);
+            bc = strip_ctx(r0.x, r0.y, r0.z, r0.w, r1.x, r1.w, um, vm);
+        }
+        const uint32_t pay[14] = {lo_id, dbits, __float_as_uint(r0.x), __float_as_uint(r0.y), __float_as_uint(r0.z),
+                                  __float_as_uint(r0.w), __float_as_uint(r1.x), __float_as_uint(r1.w),
+                                  __float_as_uint(bc.det), __float_as_uint(bc.rc), __float_as_uint(bc.cT), __float_as_uint(bc.sstar),
+                                  (uint32_t)bc.ok, (uint32_t)bc.none};
         uint32_t* tf = p.tile_fill;
         uint2* pr = p.pairs;
-        for_each_tile<0, 8>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, p.gx, pay, [&](int tile, int tx, int ty, const uint32_t(&o)[8]) {
+        for_each_tile<0, 14>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, p.gx, pay, [&](int tile, int tx, int ty, const uint32_t(&o)[14]) {
             const float ox = __uint_as_float(o[2]), oy = __uint_as_float(o[3]), oa = __uint_as_float(o[4]), ob = __uint_as_float(o[5]),
                         oc = __uint_as_float(o[6]), ot = __uint_as_float(o[7]);
             if (TIGHT && !tile_may_touch(ox, oy, oa, ob, oc, ot, tx, ty)) return;
             uint32_t mask = 0;
-            if (PACKED) mask = tile_foot_mask_any(ox, oy, oa, ob, oc, ot, tx, ty);
+            if (PACKED) {
+                if (!o[12]) mask = tile_foot_mask(ox, oy, oa, ob, oc, ot, tx, ty);
+                else if (!o[13]) {
+                    StripCtx c2;
+                    c2.px = ox; c2.py = oy; c2.b = ob; c2.det = __uint_as_float(o[8]); c2.rc = __uint_as_float(o[9]);
+                    c2.cT = __uint_as_float(o[10]); c2.sstar = __uint_as_float(o[11]); c2.ok = true; c2.none = false;
+                    mask = strip_tile_mask(c2, tx, ty);
+                }
+            }
             pr[atomicAdd(&tf[tile], 1u)] = make_uint2(o[0] | mask, o[1]);
         });
     }
@@ -710,183 +728,58 @@ __device__ void sort_bucket(const unsigned long long* __restrict__ g, uint32_t n
     }
 }
 
-// ---- per-footprint survivor lists ---------------------------------------------------------------------------
-// After the sort, every entry of the tile is tested ONCE against the tile's eight 8x4-pixel warp footprints (one thread
-// per entry, tile_foot_mask) and the survivors of footprint f are written, in list order, to a compact list that the
-// blend warp owning that footprint walks on its own — the blend kernel has no block-level staging, barrier or cull left.
-// Lists are carved from one global cursor (counters->foot_total), one atomic per tile; foot_ranges[tile*8+f] = {start, count}.
-// A list entry is the Gaussian id, or (store_pos, when a backward pass follows) the absolute position in point_list.
+// ---- footprint ballot matrix ------------------------------------------------------------------------------------
+// After the sort every entry of the tile carries an 8-bit mask: which of the tile's eight 8x4-pixel warp footprints the splat
+// can touch (PACKED: the low byte of the key, computed by k_color_emit; otherwise the record is gathered and the mask computed
+// here).  The masks of 32 consecutive list entries are transposed by eight ballots into one ROW of the ballot matrix:
+// bal[row][f] = bit i set iff entry 32 row + i touches footprint f.  The blend warp that owns footprint f reads column f — one
+// word per 32 entries — and expands it into the positions of its survivors on the fly, so the blend has no per-entry cull
+// and no lists have to be allocated.  Rows of tile t start at (ranges[t].x >> 5) + t.
 struct FootArgs {
     const float4* records;
-    uint32_t* foot_list;
-    uint2* foot_ranges;
-    gsr_counters* counters;
-    uint32_t foot_cap;
-    int store_pos;
+    uint32_t* bal;  // [rows][GSR_FOOTS]
     int gx;
 };
-// keys: the n sorted (depth bits << 32 | id) of the tile (shared or global memory); mask8: n bytes of scratch (shared
-// memory), or nullptr to park the masks in park32[] (global, 4 bytes per entry — the large-tile path).
-template <bool PACKED>
-__device__ void foot_lists(const FootArgs& fa, const unsigned long long* keys, uint32_t n, uint32_t list_base, int tile,
-                           uint8_t* mask8, uint32_t* park32) {
-    __shared__ uint32_t f_cnt[GSR_FOOTS], f_off[GSR_FOOTS];
-    __shared__ int f_ok;
-    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int ty = tile / fa.gx, tx = tile - ty * fa.gx;
-    if (t < GSR_FOOTS) f_cnt[t] = 0;
-    __syncthreads();
-    uint32_t acc = 0;  // lane f (< 8) of every warp counts footprint f
-    for (uint32_t base = warp * 32; base < n; base += SORT_THREADS) {
-        const uint32_t i = base + lane;
-        uint32_t m = 0;
-        if (i < n) {
-            if (PACKED) m = (uint32_t)keys[i] & 0xffu;
-            else {
-                const uint32_t id = (uint32_t)keys[i];
-                const float4 r0 = fa.records[3 * (size_t)id], r1 = fa.records[3 * (size_t)id + 1];
-                m = tile_foot_mask_any(r0.x, r0.y, r0.z, r0.w, r1.x, r1.w, tx, ty);
-            }
-            if (mask8) mask8[i] = (uint8_t)m; else park32[i] = m;
-        }
-#pragma unroll
-        for (int f = 0; f < GSR_FOOTS; f++) {
-            const uint32_t c = __popc(__ballot_sync(GSR_FULL, (m >> f) & 1u));
-            if (lane == (uint32_t)f) acc += c;
-        }
-    }
-    if (lane < GSR_FOOTS && acc) atomicAdd(&f_cnt[lane], acc);
-    __syncthreads();
-    if (t == 0) {
-        uint32_t total = 0;
-#pragma unroll
-        for (int f = 0; f < GSR_FOOTS; f++) total += f_cnt[f];
-        uint32_t start = 0;
-        int ok = 1;
-        if (total) {
-            start = atomicAdd(&fa.counters->foot_total, total);
-            if (start + total > fa.foot_cap || start + total < start) { ok = 0; atomicExch(&fa.counters->overflow, 1u); }
-        }
-        f_ok = ok;
-        uint2* fr = fa.foot_ranges + (size_t)tile * GSR_FOOTS;
-#pragma unroll
-        for (int f = 0; f < GSR_FOOTS; f++) {
-            f_off[f] = start;
-            fr[f] = ok ? make_uint2(start, f_cnt[f]) : make_uint2(0u, 0u);
-            start += f_cnt[f];
-        }
-    }
-    __syncthreads();
-    if (f_ok && warp < GSR_FOOTS && f_cnt[warp]) {  // warp f compacts footprint f (SORT_THREADS / 32 == GSR_FOOTS)
-        uint32_t run = f_off[warp];
-        const uint32_t lt = (1u << lane) - 1u;
-        for (uint32_t base = 0; base < n; base += 32) {
-            const uint32_t i = base + lane;
-            const uint32_t m = i < n ? (mask8 ? (uint32_t)mask8[i] : park32[i]) : 0u;
-            const bool keep = (m >> warp) & 1u;
-            const uint32_t bal = __ballot_sync(GSR_FULL, keep);
-            if (keep) fa.foot_list[run + __popc(bal & lt)] = fa.store_pos ? list_base + i : (PACKED ? (uint32_t)keys[i] >> 8 : (uint32_t)keys[i]);
-            run += __popc(bal);
-        }
-    }
-}
-static_assert(SORT_THREADS / 32 == GSR_FOOTS, "one sort warp per footprint");
-static_assert(SORT_CAP / 32 * GSR_FOOTS * 4 <= SORT_BUCKETS * 4, "the ballot matrix reuses the histogram storage");
 
-// The common case (n <= SORT_CAP, keys in shared memory):
-//   1. one thread per entry: footprint mask (PACKED: the low byte of the key, written by k_color_emit; otherwise the record is
-//      gathered and the mask computed here), and the warp's eight ballots per 32-entry row go to a ballot matrix bal[row][f];
-//   2. warp f counts column f; one atomic per tile reserves the lists' storage;
-//   3. warp f walks column f: entry (row, lane) goes to list f at start + entries before it (running popc).
+// keys: the n sorted keys of the tile (shared or global memory)
 template <bool PACKED>
-__device__ void foot_lists_small(const FootArgs& fa, const unsigned long long* keys, uint32_t n, uint32_t list_base, int tile,
-                                 uint32_t* bal /*[SORT_CAP / 32 * 8]*/) {
-    __shared__ uint32_t f_cnt[GSR_FOOTS], f_off[GSR_FOOTS];
-    __shared__ int f_ok;
+__device__ void foot_ballots(const FootArgs& fa, const unsigned long long* keys, uint32_t n, uint32_t range_x, int tile) {
     const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const uint32_t rows = (n + 31) >> 5;
     const uint32_t* klo = reinterpret_cast<const uint32_t*>(keys);  // low word of key i
-    if (PACKED) {
-        for (uint32_t rbase = warp * 32; rbase < n; rbase += SORT_THREADS) {
-            const uint32_t i = rbase + lane;
-            const uint32_t m = i < n ? klo[2 * i] & 0xffu : 0u;
-            uint32_t mine = 0;
+    uint32_t* bal = fa.bal + bal_row_base(range_x, tile) * GSR_FOOTS;
+    const int ty = tile / fa.gx, tx = tile - ty * fa.gx;
+    for (uint32_t c0 = 0; c0 < n; c0 += 2 * SORT_THREADS) {
+        float4 r0[2], r1[2];
+        uint32_t lo[2];
 #pragma unroll
-            for (int f = 0; f < GSR_FOOTS; f++) {
-                const uint32_t b = __ballot_sync(GSR_FULL, (m >> f) & 1u);
-                if (lane == (uint32_t)f) mine = b;
-            }
-            if (lane < GSR_FOOTS) bal[(rbase >> 5) * GSR_FOOTS + lane] = mine;
-        }
-    } else {
-        const int ty = tile / fa.gx, tx = tile - ty * fa.gx;
-        for (uint32_t c0 = 0; c0 < n; c0 += 2 * SORT_THREADS) {  // two gathers in flight per thread
-            float4 r0[2], r1[2];
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const uint32_t i = c0 + u * SORT_THREADS + t;
-                r0[u] = r1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < n) {
-                    const float4* r = fa.records + 3 * (size_t)klo[2 * i];
+        for (int u = 0; u < 2; u++) {  // two gathers in flight per thread on the general path
+            const uint32_t i = c0 + u * SORT_THREADS + t;
+            r0[u] = r1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            lo[u] = 0;
+            if (i < n) {
+                lo[u] = klo[2 * i];
+                if (!PACKED) {
+                    const float4* r = fa.records + 3 * (size_t)lo[u];
                     r0[u] = r[0];
                     r1[u] = r[1];
                 }
             }
+        }
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const uint32_t rbase = c0 + u * SORT_THREADS + warp * 32;  // warp-uniform
-                if (rbase < n) {
-                    const uint32_t m = rbase + lane < n ? tile_foot_mask_any(r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].w, tx, ty) : 0u;
-                    uint32_t mine = 0;
+        for (int u = 0; u < 2; u++) {
+            const uint32_t rbase = c0 + u * SORT_THREADS + warp * 32;  // warp-uniform
+            if (rbase < n) {
+                uint32_t m = 0;
+                if (rbase + lane < n) m = PACKED ? lo[u] & 0xffu : tile_foot_mask_any(r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].w, tx, ty);
+                uint32_t mine = 0;
 #pragma unroll
-                    for (int f = 0; f < GSR_FOOTS; f++) {
-                        const uint32_t b = __ballot_sync(GSR_FULL, (m >> f) & 1u);
-                        if (lane == (uint32_t)f) mine = b;
-                    }
-                    if (lane < GSR_FOOTS) bal[(rbase >> 5) * GSR_FOOTS + lane] = mine;
+                for (int f = 0; f < GSR_FOOTS; f++) {
+                    const uint32_t b = __ballot_sync(GSR_FULL, (m >> f) & 1u);
+                    if (lane == (uint32_t)f) mine = b;
                 }
+                if (lane < GSR_FOOTS) bal[(rbase >> 5) * GSR_FOOTS + lane] = mine;  // one 32-byte row
             }
         }
-    }
-    __syncthreads();
-    {   // warp f: size of list f
-        uint32_t c = 0;
-        for (uint32_t r = lane; r < rows; r += 32) c += (uint32_t)__popc(bal[r * GSR_FOOTS + warp]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(GSR_FULL, c, o);
-        if (lane == 0) f_cnt[warp] = c;
-    }
-    __syncthreads();
-    if (t == 0) {
-        uint32_t total = 0;
-#pragma unroll
-        for (int f = 0; f < GSR_FOOTS; f++) total += f_cnt[f];
-        uint32_t start = 0;
-        int ok = 1;
-        if (total) {
-            start = atomicAdd(&fa.counters->foot_total, total);
-            if (start + total > fa.foot_cap || start + total < start) { ok = 0; atomicExch(&fa.counters->overflow, 1u); }
-        }
-        f_ok = ok;
-        uint2* fr = fa.foot_ranges + (size_t)tile * GSR_FOOTS;
-#pragma unroll
-        for (int f = 0; f < GSR_FOOTS; f++) {
-            f_off[f] = start;
-            fr[f] = ok ? make_uint2(start, f_cnt[f]) : make_uint2(0u, 0u);
-            start += f_cnt[f];
-        }
-    }
-    __syncthreads();
-    if (!f_ok || f_cnt[warp] == 0) return;
-    uint32_t run = f_off[warp];
-    const uint32_t lt = (1u << lane) - 1u;
-    for (uint32_t r = 0; r < rows; r++) {
-        const uint32_t b = bal[r * GSR_FOOTS + warp];
-        if ((b >> lane) & 1u) {
-            const uint32_t i = r * 32 + lane;
-            fa.foot_list[run + __popc(b & lt)] = fa.store_pos ? list_base + i : (PACKED ? klo[2 * i] >> 8 : klo[2 * i]);
-        }
-        run += (uint32_t)__popc(b);
     }
 }
 
@@ -897,16 +790,12 @@ __device__ void sort_tile(const uint2 rg, unsigned long long* __restrict__ pairs
                           unsigned long long* s, uint32_t* hist, const FootArgs& fa, int tile) {
     const uint32_t n = rg.y - rg.x;
     const uint32_t tid = threadIdx.x;
-    if (n == 0) {
-        if (tid < GSR_FOOTS) fa.foot_ranges[(size_t)tile * GSR_FOOTS + tid] = make_uint2(0u, 0u);
-        return;
-    }
+    if (n == 0) return;
     unsigned long long* g = pairs + rg.x;
     uint32_t* out = point_list + rg.x;
     if (n <= SORT_CAP) {
         sort_bucket<PACKED>(g, n, out, keep_pairs ? g : nullptr, s, hist);
-        __syncthreads();  // the histogram is dead: its storage holds the ballot matrix
-        foot_lists_small<PACKED>(fa, s, n, rg.x, tile, hist);
+        foot_ballots<PACKED>(fa, s, n, rg.x, tile);  // s[] still holds the sorted keys (only read after the sort's last barrier)
         return;
     }
     // ---- large tile: chunks sorted in shared memory, cross-chunk steps in global (L2) memory ----
@@ -940,7 +829,7 @@ __device__ void sort_tile(const uint2 rg, unsigned long long* __restrict__ pairs
         }
     }
     __syncthreads();
-    foot_lists<PACKED>(fa, g, n, rg.x, tile, nullptr, out);  // masks parked in point_list until the ids are written
+    foot_ballots<PACKED>(fa, g, n, rg.x, tile);
     __syncthreads();
     for (uint32_t i = tid; i < n; i += SORT_THREADS) {
         const unsigned long long x = g[i];
@@ -1090,9 +979,14 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     if (f->shs && (D + 1) * (D + 1) > f->M) { set_error("gsr_forward: sh degree %d needs %d coefficients, shs has M=%d", D, (D + 1) * (D + 1), f->M); return GSR_ERR_INVALID; }
     const GeomLayout gl((size_t)f->P);
     if (!ws->geom || ws->geom_bytes < gl.total) { set_error("gsr_forward: geometry workspace too small (%zu < %zu)", ws->geom_bytes, gl.total); return GSR_ERR_WORKSPACE; }
-    const size_t cap = ws->binning ? BinLayout::capacity_of(ws->binning_bytes) : 0;
+    const size_t cap_nominal = ws->binning ? BinLayout::capacity_of(ws->binning_bytes) : 0;
+    if (cap_nominal < 1) { set_error("gsr_forward: binning workspace too small"); return GSR_ERR_WORKSPACE; }
+    const BinLayout bl(cap_nominal);
+    // the ballot matrix needs capacity / 32 + tiles + 1 rows: images with more tiles than the fixed slack covers lower the usable capacity
+    size_t cap = cap_nominal;
+    if ((size_t)il.tiles + 1 > bl.bal_rows) { set_error("gsr_forward: binning workspace too small for %d tiles", il.tiles); return GSR_ERR_WORKSPACE; }
+    if (cap / 32 + (size_t)il.tiles + 1 > bl.bal_rows) cap = 32 * (bl.bal_rows - (size_t)il.tiles - 1);
     if (cap < 1) { set_error("gsr_forward: binning workspace too small"); return GSR_ERR_WORKSPACE; }
-    const BinLayout bl(cap);
     char* geo = (char*)ws->geom;
     char* bin = (char*)ws->binning;
 
@@ -1105,7 +999,7 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
         if (rc0) return rc0;
         BlendArgs ba{(const uint2*)(img + il.ranges), (const uint32_t*)(bin + bl.point_list), (const float4*)(geo + gl.records), extra_colors,
                      f->W, f->H, il.gx, il.gy, f->bg, out_color, out_depth, out_alpha, out_extra, nullptr, counters,
-                     (const uint2*)(img + il.foot_ranges), (const uint32_t*)(bin + bl.foot_list), (flags & GSR_FLAG_EXACT_IMAGES) ? 1 : 0};
+                     (const uint32_t*)(bin + bl.bal), (flags & GSR_FLAG_EXACT_IMAGES) ? 1 : 0};
         launch_blend(ba, st);
         return check_launch("gsr_forward/blend(reuse)", debug, st);
     }
@@ -1129,7 +1023,14 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     pp.ranks = (uint32_t*)(geo + gl.ranks); pp.counters = counters;
 
     pp.vis_list = (uint32_t*)(geo + gl.vis_list);
-    k_project<<<(f->P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, st>>>(pp);
+    {
+        static int minb = -1;  // GSR_PROJ_MINB=8|10|12: resident CTAs per SM the kernel is compiled for (experiment knob)
+        if (minb < 0) { const char* e = getenv("GSR_PROJ_MINB"); minb = e ? atoi(e) : 8; }
+        const int grid = (f->P + PRE_THREADS - 1) / PRE_THREADS;
+        if (minb == 12) k_project<12><<<grid, PRE_THREADS, 0, st>>>(pp);
+        else if (minb == 10) k_project<10><<<grid, PRE_THREADS, 0, st>>>(pp);
+        else k_project<8><<<grid, PRE_THREADS, 0, st>>>(pp);
+    }
     prof_mark(1, st);
     int rc = check_launch("gsr_forward/project", debug, st);
     if (rc) return rc;
@@ -1166,15 +1067,14 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
 
     const int keep_pairs = (flags & GSR_FLAG_SORTED_KEYS) ? 1 : 0;
     uint32_t* n_contrib = (flags & GSR_FLAG_FOR_BACKWARD) ? (uint32_t*)(img + il.n_contrib) : nullptr;
-    FootArgs fa{pp.records, (uint32_t*)(bin + bl.foot_list), (uint2*)(img + il.foot_ranges), counters,
-                (uint32_t)(bl.foot_capacity > 0xffffffffull ? 0xffffffffull : bl.foot_capacity), n_contrib ? 1 : 0, il.gx};
+    FootArgs fa{pp.records, (uint32_t*)(bin + bl.bal), il.gx};
     if (packed) k_sort_tiles<true><<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters, keep_pairs, fa);
     else k_sort_tiles<false><<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters, keep_pairs, fa);
     prof_mark(4, st);
     if ((rc = check_launch("gsr_forward/sort", debug, st))) return rc;
     BlendArgs ba{ranges, (const uint32_t*)(bin + bl.point_list), pp.records, extra_colors, f->W, f->H, il.gx, il.gy, f->bg,
-                 out_color, out_depth, out_alpha, out_extra, n_contrib, counters,
-                 (const uint2*)(img + il.foot_ranges), (const uint32_t*)(bin + bl.foot_list), (flags & GSR_FLAG_EXACT_IMAGES) ? 1 : 0};
+                 out_color, out_depth, out_alpha, out_extra, n_contrib, counters, (const uint32_t*)(bin + bl.bal),
+                 (flags & GSR_FLAG_EXACT_IMAGES) ? 1 : 0};
     launch_blend(ba, st);
     prof_mark(5, st);
     if (g_prof.on) {

@@ -147,9 +147,8 @@ class FrameTicket:
 
 
 def needed_capacity(stats: Dict[str, int]) -> int:
-    """Binning capacity (instances) a frame with these counters needs: R instances, and footprint lists of at most
-    GSR_FOOT_FACTOR (= 3) entries per instance of capacity."""
-    return max(int(stats["num_rendered"]), (int(stats["foot_total"]) + 2) // 3)
+    """Binning capacity (instances) a frame with these counters needs."""
+    return int(stats["num_rendered"])
 
 
 class _DeviceState:

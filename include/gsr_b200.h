@@ -110,7 +110,7 @@ typedef struct gsr_counters {
     uint32_t max_tile;     /* longest per-tile list                                               */
     uint32_t trapped;      /* 1 if prefiltered was set and a point was near-culled                 */
     uint32_t num_visible;  /* Gaussians with radii > 0                                             */
-    uint32_t foot_total;   /* entries of the per-footprint survivor lists (<= 3 * capacity, else overflow) */
+    uint32_t foot_total;   /* reserved (0)                                                          */
     uint32_t exact_redos;  /* warps whose pixels were re-blended exactly (default image mode)       */
     uint32_t reserved[1];
 } gsr_counters;

@@ -36,8 +36,11 @@ def test_workspace_size_queries():
     from autovfx_b200._lib import lib
     assert lib.gsr_geom_bytes(0) > 0
     assert 3_000_000 * (48 + 32 + 24 + 1) <= lib.gsr_geom_bytes(3_000_000) < 3_000_000 * 110
-    assert lib.gsr_binning_bytes(1000) == 24 * 1000  # 8 (pair) + 4 (list) + 3x4 (footprint lists) B/instance (reference: 24 B + sort temp)
-    assert lib.gsr_binning_capacity(lib.gsr_binning_bytes(12345)) == 12345
+    # 8 (pair) + 4 (list) + 1 (footprint ballot matrix) bytes per instance + a fixed 4 MiB of ballot rows (reference: 24 B + sort temp)
+    per = (lib.gsr_binning_bytes(2_000_000) - lib.gsr_binning_bytes(1_000_000)) / 1_000_000
+    assert 12.9 < per < 13.1 and lib.gsr_binning_bytes(1000) < 5 * 2 ** 20
+    for c in (1, 1000, 12345, 7_000_000):
+        assert lib.gsr_binning_capacity(lib.gsr_binning_bytes(c)) == c
     a, b = lib.gsr_image_bytes(1920, 1080), lib.gsr_image_bytes(256, 256)
     assert a > b > 256 * 256 * 4
     assert lib.gsr_dist2_bytes(100000) > 4 * 4 * 100000

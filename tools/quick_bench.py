@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--exact", action="store_true")
     ap.add_argument("--tight", action="store_true")
     ap.add_argument("--backward", action="store_true", help="also time forward+backward through autograd (20 iterations)")
+    ap.add_argument("--streams", type=int, default=1, help="issue consecutive frames round-robin on this many CUDA streams")
     ap.add_argument("--tag", default="")
     args = ap.parse_args()
     from autovfx_b200 import rasterizer as R, _lib
@@ -42,12 +43,16 @@ def main():
         c = packed[i]
         return R.GaussianRasterizationSettings(1080, 1920, float(host[i, 35]), float(host[i, 36]), bg, 1.0, c[0:16], c[16:32], 3, c[32:35], False, False)
     S = [settings(i % 300) for i in range(K + 5)]
-    out = (torch.empty((3, 1080, 1920), device=dev), torch.empty((1, 1080, 1920), device=dev), torch.empty((1, 1080, 1920), device=dev),
-           torch.empty((P,), dtype=torch.int32, device=dev))
+    NS = max(1, args.streams)
+    outs = [(torch.empty((3, 1080, 1920), device=dev), torch.empty((1, 1080, 1920), device=dev), torch.empty((1, 1080, 1920), device=dev),
+             torch.empty((P,), dtype=torch.int32, device=dev)) for _ in range(NS)]
+    streams = [torch.cuda.current_stream(dev)] if NS == 1 else [torch.cuda.Stream(dev) for _ in range(NS)]
 
     def frame(i, sync):
-        return R.forward_raw(g["means3D"], g["shs"], None, g["opacities"], g["scales"], g["rotations"], None, S[i], sync=sync, out=out,
-                             tight=args.tight, exact=args.exact)
+        with torch.cuda.stream(streams[i % NS]):
+            return R.forward_raw(g["means3D"], g["shs"], None, g["opacities"], g["scales"], g["rotations"], None, S[i], sync=sync, out=outs[i % NS],
+                                 tight=args.tight, exact=args.exact)
+    torch.cuda.synchronize()
     for i in range(K + 5):
         frame(i, True)
     for i in range(5):
@@ -55,17 +60,28 @@ def main():
     torch.cuda.synchronize()
     _lib.check(_lib.lib.gsr_profile_begin_strided(K, 2), "profile")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if NS > 1:
+        _lib.lib.gsr_profile_end((C.c_float * 5)(), None)  # per-kernel events assume one stream
     e0.record()
+    if NS > 1:
+        for st_ in streams:
+            st_.wait_event(e0)
     tk = [frame(5 + i, False)[5] for i in range(K)]
+    if NS > 1:
+        for st_ in streams:
+            ev = torch.cuda.Event()
+            ev.record(st_)
+            torch.cuda.current_stream(dev).wait_event(ev)
     e1.record()
     torch.cuda.synchronize()
     ms_k = (C.c_float * 5)()
     n = C.c_int(0)
-    _lib.check(_lib.lib.gsr_profile_end(ms_k, C.byref(n)), "profile_end")
+    if NS == 1:
+        _lib.check(_lib.lib.gsr_profile_end(ms_k, C.byref(n)), "profile_end")
     st = [t.stats() for t in tk]
     ms = e0.elapsed_time(e1) / K
     res = {"tag": args.tag, "env": {k: os.environ.get(k) for k in ("GSR_BLEND", "GSR_BLEND_WARPS") if os.environ.get(k)},
-           "exact": args.exact, "tight": args.tight, "ms_per_frame": round(ms, 4), "fps": round(1000.0 / ms, 1),
+           "exact": args.exact, "tight": args.tight, "streams": NS, "ms_per_frame": round(ms, 4), "fps": round(1000.0 / ms, 1),
            "kernel_ms": {k: round(float(ms_k[i]), 4) for i, k in enumerate(["project", "tile_scan", "color_emit", "sort_tiles", "blend"])},
            "avg_R": sum(s["num_rendered"] for s in st) / K, "avg_foot": sum(s["foot_total"] for s in st) / K,
            "avg_redos": sum(s["exact_redos"] for s in st) / K, "overflow": sum(s["overflow"] for s in st)}
