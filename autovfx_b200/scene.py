@@ -226,6 +226,25 @@ def config3_scene(P: int = 3_000_000, seed: int = 1234):
                                opacity_mean=0.0, opacity_std=2.0)
 
 
+def config2_raw(P: int = 1_000_000, seed: int = 1) -> Dict[str, torch.Tensor]:
+    """BASELINE config 2 stand-in (the Garden .ply is not available offline): P = 1M, seed 1, the config-3
+    distributions scaled to a 4-unit scene, as RAW (pre-activation) GaussianModel parameters — xyz [P,3], f_dc [P,1,3],
+    f_rest [P,15,3], opacity [P,1] (logit), scaling [P,3] (log), rotation [P,4] (unnormalised) — i.e. what a 3DGS .ply stores."""
+    g = torch.Generator().manual_seed(seed)
+    ext = torch.tensor((2.0, 2.0, 0.5))
+    return {"xyz": ((torch.rand(P, 3, generator=g) * 2 - 1) * ext).contiguous(),
+            "scaling": (torch.randn(P, 3, generator=g) * 0.5 + math.log(0.005)).contiguous(),
+            "rotation": torch.randn(P, 4, generator=g).contiguous(),
+            "opacity": (torch.randn(P, 1, generator=g) * 2.0).contiguous(),
+            "f_dc": (torch.randn(P, 1, 3, generator=g) * 0.5).contiguous(),
+            "f_rest": (torch.randn(P, 15, 3, generator=g) * 0.1).contiguous()}
+
+
+def config2_camera() -> "Camera":
+    """One 1920x1080 camera, 60 degrees horizontal FoV, looking at the centre of the config-2 scene from its rim."""
+    return lookat_camera((1.6, -2.6, 1.1), (0.0, 0.0, 0.0), 1920, 1080, 60.0)
+
+
 # ----------------------------------------------------------------------------- .ply (3DGS layout)
 def _ply_props(M: int) -> List[str]:
     props = ["x", "y", "z", "nx", "ny", "nz", "f_dc_0", "f_dc_1", "f_dc_2"]
