@@ -121,9 +121,9 @@ class FrameLoop:
                        image and the normal / pseudo-normal maps, as gsr_axis_normals -> one 6-channel forward ->
                        gsr_normal_maps; the finished frame is a dict ``{"frame" [5,H,W], "normal" [H,W,3], "pseudo_normal"
                        [H,W,3]}``.
-    ``pack8=True``   : (with ``product``) hand the frame off as the bytes the reference's loop gives its encoders
-                       (scene_representation.py:424-438): ``{"rgba8" [H,W,4], "depth" [H,W] f32, "depth8" [H,W], "normal8"
-                       [H,W,3]}`` — 24.9 MB instead of 66 MB of fp32 over PCIe per 1080p frame.
+    ``pack8=True``   : hand the frame off as the bytes the reference's loop gives its encoders (scene_representation.py:424-438):
+                       ``{"rgba8" [H,W,4], "depth" [H,W] f32, "depth8" [H,W]}`` (+ ``"normal8" [H,W,3]`` with ``product``) —
+                       18.7 MB (24.9 MB) instead of 41.5 MB (66 MB) of fp32 over PCIe per 1080p frame.
     """
 
     def __init__(self, gaussians: Dict[str, torch.Tensor], sh_degree: int, width: int, height: int, bg=(0.0, 0.0, 0.0),
@@ -131,8 +131,6 @@ class FrameLoop:
                  product: bool = False, pack8: bool = False, depth_scale: float = 3.0):
         from . import rasterizer as R  # requires the CUDA library
         self._R = R
-        if pack8 and not product:
-            raise ValueError("pack8 needs product=True (it packs the normal map as well)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.g = {k: v.to(self.device).float().contiguous() for k, v in gaussians.items()}
         self.sh_degree, self.W, self.H, self.scale_modifier = sh_degree, width, height, scale_modifier
@@ -155,8 +153,11 @@ class FrameLoop:
             self.nmaps = [(torch.empty((H, W, 3), dtype=torch.float32, device=dev), torch.empty((H, W, 3), dtype=torch.float32, device=dev))
                           for _ in range(ring)]
         for s in range(ring):
-            if not product:
+            if not product and not pack8:
                 self.outputs.append({"frame": self.frames[s]})
+            elif not product:
+                self.outputs.append({"rgba8": torch.empty((H, W, 4), dtype=torch.uint8, device=dev), "depth": self.frames[s][3],
+                                     "depth8": torch.empty((H, W), dtype=torch.uint8, device=dev)})
             elif not pack8:
                 self.outputs.append({"frame": self.frames[s], "normal": self.nmaps[s][0], "pseudo_normal": self.nmaps[s][1]})
             else:
@@ -191,6 +192,11 @@ class FrameLoop:
         if not self.product:
             ent["fwd"] = R.PreparedForward(g["means3D"], g["shs"], g["opacities"], g["scales"], g["rotations"], cam, self.W, self.H, self.bg,
                                            self.sh_degree, self.scale_modifier, out, tight=self.tight_tiles)
+            if self.pack8:
+                o = self.outputs[slot]
+                ent["pack"] = (self.W, self.H, f[0:3].data_ptr(), f[4].data_ptr(), f[3].data_ptr(), None, float(self.depth_scale),
+                               o["rgba8"].data_ptr(), None, o["depth8"].data_ptr())
+                ent["L"], ent["check"], ent["C"] = _lib.lib, _lib.check, C
         else:
             normals = self.normals[:P]
             ent["fwd"] = R.PreparedForward(g["means3D"], g["shs"], g["opacities"], g["scales"], g["rotations"], cam, self.W, self.H, self.bg,
@@ -225,6 +231,10 @@ class FrameLoop:
             ticket = fwd.launch(tfx, tfy)
             while sync and not ticket.ok():  # ok() waits for the counters and grows the capacity after an overflow
                 ticket = fwd.launch(tfx, tfy)
+            if self.pack8:
+                with torch.cuda.device(self.device):
+                    ent["check"](ent["L"].gsr_pack_frame(*ent["pack"], ent["C"].c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                                 "gsr_pack_frame")
             return ticket
         L, check, C = ent["L"], ent["check"], ent["C"]
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -246,7 +256,7 @@ class FrameLoop:
 
     def _finished(self, slot: int):
         src = self.host[slot] if self.to_host else self.outputs[slot]
-        return src["frame"] if not self.product else src
+        return src["frame"] if not (self.product or self.pack8) else src
 
     def set_gaussians(self, gaussians: Dict[str, torch.Tensor]) -> None:
         """Swap the (activated) parameter tensors the next frames read — e.g. the views ``edit.ResidentScene.compose`` returns
@@ -306,7 +316,7 @@ class FrameLoop:
             ev = None
             if self.to_host:
                 done = ticket.event
-                if self.product:  # the ticket's event was recorded after the forward; the post kernels come later on the stream
+                if self.product or self.pack8:  # the ticket's event was recorded after the forward; the post kernels come later on the stream
                     done = torch.cuda.Event()
                     done.record(cur)
                 self.copy_stream.wait_event(done)

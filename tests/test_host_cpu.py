@@ -193,7 +193,7 @@ def test_frame_sharding_is_a_partition(n, world, mode):
 
 
 def test_bench_clock_sampler_windows():
-    """bench.ClockSampler.stop(t0, t1): samples inside the timed region when there are at least two, otherwise the whole loaded window."""
+    """bench.ClockSampler.report(t0, t1): samples inside the timed region when there are at least two, otherwise the loaded window so far."""
     import importlib
     import sys
     import time
@@ -203,24 +203,13 @@ def test_bench_clock_sampler_windows():
         bench = importlib.import_module("bench")
     finally:
         sys.argv = argv
-
-    class _P:
-        def terminate(self):
-            pass
-
-        def wait(self, timeout=None):
-            pass
-
     now = time.time()
-    lines = [(now - 1.0, "1965, 1965, 700.0, Not Active, Not Active, Not Active, Active"),
-             (now - 0.5, "1950, 1965, 710.0, Not Active, Not Active, Not Active, Not Active"),
-             (now - 0.45, "1965, 1965, 710.0, Not Active, Not Active, Not Active, Not Active")]
-    s = bench.ClockSampler(0)
-    s.proc, s.lines = _P(), list(lines)
-    r = s.stop(now - 0.6, now - 0.4)
-    assert r["window"] == "timed region" and r["samples"] == 2 and r["reasons"] == [] and r["sm_max_mhz"] == 1965.0
-    s.proc, s.lines = _P(), list(lines)
-    r = s.stop(now - 0.1, now)
-    assert r["samples"] == 3 and r["reasons"] == ["sw_power_cap"] and r["window"].startswith("pre-pass")
-    s = bench.ClockSampler(0)
-    assert s.stop()["reasons"] == ["unavailable"]
+    s = bench.ClockSampler.__new__(bench.ClockSampler)  # no NVML on the CPU box: fill the sample list by hand
+    s.ok, s.max_mhz, s.stop_flag = True, 1965.0, True
+    s.samples = [(now - 1.0, 1965.0, 0x4, 700.0), (now - 0.5, 1950.0, 0, 710.0), (now - 0.45, 1965.0, 0, 710.0)]
+    r = s.report(now - 0.6, now - 0.4)
+    assert r["window"] == "timed region" and r["samples"] == 2 and r["reasons"] == [] and r["sm_max_mhz"] == 1965.0 and r["sm_mhz"] == 1965.0
+    r = s.report(now - 0.1, now)
+    assert r["samples"] == 3 and r["reasons"] == ["sw_power_cap"] and r["window"].startswith("warm-up")
+    s.ok = False
+    assert s.report(0, 1)["reasons"] == ["unavailable"]

@@ -155,3 +155,18 @@ def test_oracle_against_reference_golden(path):
         for k in ("dL_dmeans3D", "dL_dmeans2D", "dL_dopacity", "dL_dsh", "dL_dscales", "dL_drotations", "dL_dcolors", "dL_dcov3D"):
             if k in gold and gold[k].size:
                 assert Hh.relerr(og[k].reshape(gold[k].shape), gold[k]) < 5e-3, k
+
+
+def test_torch_cpu_rasterize_loop_matches_the_c_oracle():
+    """The pure-CPU PyTorch rasterize loop that bench.py times as `torch_cpu_baseline` (oracle/torch_cpu_raster.py) renders the
+    same images as the C oracle (and hence the reference) on BASELINE config 1 and a small ragged-image case."""
+    import torch
+    from oracle import torch_cpu_raster as TR
+    from tests import helpers as Hh
+    for name in ("config1", "small_sh"):
+        a = Hh.resolve(Hh.case_inputs(name))
+        c, d, al, r = TR.rasterize(a["means3D"], a["scales"], a["rotations"], a["opacities"], a["shs"], a["view"], a["proj"], a["campos"], a["W"], a["H"],
+                                   a["tanfovx"], a["tanfovy"], a["sh_degree"], a["scale_modifier"], tuple(float(v) for v in a["bg"]))
+        o = Hh.run_oracle(a)
+        assert Hh.maxabs(c, o["color"]) <= 1e-4 and Hh.maxabs(d, o["depth"]) <= 1e-4 and Hh.maxabs(al, o["alpha"]) <= 1e-4
+        assert int((r != torch.from_numpy(o["radii"])).sum()) <= 1
