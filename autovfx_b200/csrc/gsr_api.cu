@@ -1,5 +1,13 @@
 // gsr_b200 — extern "C" surface declared in include/gsr_b200.h.
 #include "gsr_common.cuh"
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: the ranges cost nothing unless a profiler is attached
+
+namespace {
+struct NvtxRange {  // one named range per C-ABI call (the reference has no instrumentation; this build adds NVTX)
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
 
 namespace gsr {
 int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,
@@ -42,32 +50,38 @@ size_t gsr_image_bytes(int32_t W, int32_t H) { return gsr::ImageLayout(W < 1 ? 1
 
 int gsr_forward(const gsr_frame* frame, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,
                 int32_t* radii, int flags, void* stream) {
+    NvtxRange nvtx_("gsr_forward");
     return gsr::forward_impl(frame, ws, out_color, out_depth, out_alpha, radii, nullptr, nullptr, flags, (cudaStream_t)stream);
 }
 
 int gsr_forward_multi(const gsr_frame* frame, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,
                       int32_t* radii, const float* extra_colors, float* out_extra, int flags, void* stream) {
+    NvtxRange nvtx_("gsr_forward_multi");
     return gsr::forward_impl(frame, ws, out_color, out_depth, out_alpha, radii, extra_colors, out_extra, flags, (cudaStream_t)stream);
 }
 
 int gsr_axis_normals(int32_t P, const float* means3D, const float* scales, const float* rotations, const float* campos, int remap01,
                      float* out, void* stream) {
+    NvtxRange nvtx_("gsr_axis_normals");
     return gsr::axis_normals_impl(P, means3D, scales, rotations, campos, remap01, out, (cudaStream_t)stream);
 }
 
 int gsr_normal_maps(int32_t W, int32_t H, const float* normal_img, const float* depth, const float* c2w, float fx, float fy, float cx,
                     float cy, float* out_normal, float* out_pseudo, void* stream) {
+    NvtxRange nvtx_("gsr_normal_maps");
     return gsr::normal_maps_impl(W, H, normal_img, depth, c2w, fx, fy, cx, cy, out_normal, out_pseudo, (cudaStream_t)stream);
 }
 
 int gsr_pack_frame(int32_t W, int32_t H, const float* rgb, const float* alpha, const float* depth, const float* normal_hwc,
                    float depth_scale, uint8_t* rgba8, uint8_t* normal8, uint8_t* depth8, void* stream) {
+    NvtxRange nvtx_("gsr_pack_frame");
     return gsr::pack_frame_impl(W, H, rgb, alpha, depth, normal_hwc, depth_scale, rgba8, normal8, depth8, (cudaStream_t)stream);
 }
 
 int gsr_activate_gaussians(int32_t N, int32_t M, const float* xyz, const float* f_dc, const float* f_rest, const float* opacity_raw,
                            const float* scaling_raw, const float* rotation_raw, const gsr_object_xform* xform, float* means3D, float* shs,
                            float* opacities, float* scales, float* rotations, void* stream) {
+    NvtxRange nvtx_("gsr_activate_gaussians");
     return gsr::compose_impl(N, M, xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, xform, means3D, shs, opacities, scales, rotations,
                              (cudaStream_t)stream);
 }
@@ -75,6 +89,7 @@ int gsr_activate_gaussians(int32_t N, int32_t M, const float* xyz, const float* 
 int gsr_backward(const gsr_frame* frame, const gsr_workspace* ws, const int32_t* radii, const float* out_alpha,
                  const float* dL_dout_color, const float* dL_dout_depth, const float* dL_dout_alpha, const gsr_grads* grads,
                  void* stream) {
+    NvtxRange nvtx_("gsr_backward");
     return gsr::backward_impl(frame, ws, radii, out_alpha, dL_dout_color, dL_dout_depth, dL_dout_alpha, grads, (cudaStream_t)stream);
 }
 
@@ -89,6 +104,7 @@ int gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, c
 
 size_t gsr_dist2_bytes(int32_t P) { return gsr::dist2_bytes(P); }
 int gsr_dist2(int32_t P, const float* points, float* mean_dists, void* workspace, size_t workspace_bytes, void* stream) {
+    NvtxRange nvtx_("gsr_dist2");
     return gsr::dist2_impl(P, points, mean_dists, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

@@ -5,7 +5,8 @@
 //   k_gaussian_backward  <- computeCov2DCUDA + BACKWARD::preprocessCUDA (backward.cu:144-274, :346-412,
 //                           with the SH backward :20-139 and the scale/rotation backward :278-341)
 //
-// Differences in mechanism (the mathematics and the per-pixel recursion are the reference's):
+// The per-pixel recursion of the blend backward is the reference's (it must replay the forward's decisions); the per-Gaussian
+// chain rule is derived here in matrix form (see sh_grad, geometry_grad, cov3d_grad).  Differences in mechanism:
 //   * the reference issues 10 global atomicAdds per contributing (pixel, Gaussian) pair; here each warp
 //     (an 8x4 pixel footprint) reduces the 10 partial gradients with shuffles and issues one global
 //     reduction per (warp, Gaussian, component);
@@ -261,64 +262,186 @@ struct GBParams {
 constexpr int GB_THREADS = 128;
 constexpr int GB_STRIDE = 49;  // 48 SH floats per row, odd stride -> conflict-free
 
-__device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {  // auxiliary.h:106-118
-    float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
-    float invsum32 = 1.0f / sqrt(sum2 * sum2 * sum2);
-    float3 o;
-    o.x = ((+sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y - v.z * v.x * dv.z) * invsum32;
-    o.y = (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y - v.z * v.y * dv.z) * invsum32;
-    o.z = (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * invsum32;
+// ---- SH colour backward ------------------------------------------------------------------------------------------
+// rgb_c = 0.5 + sum_k Y_k(d) sh[k][c] with d = (pos - campos) / |pos - campos| (forward.cu:20-71).  Two results:
+//   * dL/dsh[k][c] = Y_k(d) g_c, written over the staged row (coefficients beyond the active degree get 0);
+//   * dL/dpos: the three channels are contracted FIRST, u_k = sum_c g_c sh[k][c] (one scalar per basis function), so the
+//     gradient of the basis is evaluated once instead of once per channel: dL/dd = sum_k u_k grad Y_k(d), and the
+//     normalisation contributes the projector (I - d d^T) / |pos - campos|.
+// g_c is the colour gradient with the channels the forward clamped at 0 masked out (clamp_bits, forward.cu:63-70).
+__device__ float3 sh_grad(int deg, float* sh, float3 pos, const float* campos, unsigned clamp_bits, float3 dL_dcolor) {
+    const float vx = pos.x - campos[0], vy = pos.y - campos[1], vz = pos.z - campos[2];
+    const float inv_len = 1.0f / sqrtf(vx * vx + vy * vy + vz * vz);
+    const float x = vx * inv_len, y = vy * inv_len, z = vz * inv_len;
+    const float g[3] = {(clamp_bits & 1u) ? 0.f : dL_dcolor.x, (clamp_bits & 2u) ? 0.f : dL_dcolor.y, (clamp_bits & 4u) ? 0.f : dL_dcolor.z};
+    const int ncoef = (deg + 1) * (deg + 1);
+    const float xx = x * x, yy = y * y, zz = z * z;
+    // basis values Y_k(d) (real SH up to degree 3, the constants of auxiliary.h:22-39)
+    float Y[16];
+    Y[0] = SH_C0;
+    Y[1] = -SH_C1 * y; Y[2] = SH_C1 * z; Y[3] = -SH_C1 * x;
+    const float q = 2.f * zz - xx - yy, r4 = 4.f * zz - xx - yy, dxy = xx - yy;
+    Y[4] = SH_C2_0 * x * y; Y[5] = SH_C2_1 * y * z; Y[6] = SH_C2_2 * q; Y[7] = SH_C2_3 * x * z; Y[8] = SH_C2_4 * dxy;
+    Y[9] = SH_C3_0 * y * (3.f * xx - yy); Y[10] = SH_C3_1 * x * y * z; Y[11] = SH_C3_2 * y * r4;
+    Y[12] = SH_C3_3 * z * (q - 2.f * (xx + yy)); Y[13] = SH_C3_4 * x * r4; Y[14] = SH_C3_5 * z * dxy; Y[15] = SH_C3_6 * x * (xx - 3.f * yy);
+    // channel contraction u_k, then the row is overwritten with dL/dsh
+    float u[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        float* row = sh + 3 * k;
+        u[k] = k < ncoef ? g[0] * row[0] + g[1] * row[1] + g[2] * row[2] : 0.f;
+        const float yk = k < ncoef ? Y[k] : 0.f;
+        row[0] = yk * g[0]; row[1] = yk * g[1]; row[2] = yk * g[2];
+    }
+    // dL/dd = sum_k u_k grad Y_k  (u_k = 0 beyond the active degree, so no branches are needed)
+    float gx = -SH_C1 * u[3], gy = -SH_C1 * u[1], gz = SH_C1 * u[2];
+    gx += SH_C2_0 * y * u[4] - 2.f * SH_C2_2 * x * u[6] + SH_C2_3 * z * u[7] + 2.f * SH_C2_4 * x * u[8];
+    gy += SH_C2_0 * x * u[4] + SH_C2_1 * z * u[5] - 2.f * SH_C2_2 * y * u[6] - 2.f * SH_C2_4 * y * u[8];
+    gz += SH_C2_1 * y * u[5] + 4.f * SH_C2_2 * z * u[6] + SH_C2_3 * x * u[7];
+    const float xy = x * y, yz = y * z, xz = x * z;
+    gx += 6.f * SH_C3_0 * xy * u[9] + SH_C3_1 * yz * u[10] - 2.f * SH_C3_2 * xy * u[11] - 6.f * SH_C3_3 * xz * u[12] +
+          SH_C3_4 * (r4 - 2.f * xx) * u[13] + 2.f * SH_C3_5 * xz * u[14] + 3.f * SH_C3_6 * dxy * u[15];
+    gy += 3.f * SH_C3_0 * dxy * u[9] + SH_C3_1 * xz * u[10] + SH_C3_2 * (r4 - 2.f * yy) * u[11] - 6.f * SH_C3_3 * yz * u[12] -
+          2.f * SH_C3_4 * xy * u[13] - 2.f * SH_C3_5 * yz * u[14] - 6.f * SH_C3_6 * xy * u[15];
+    gz += SH_C3_1 * xy * u[10] + 8.f * SH_C3_2 * yz * u[11] + 3.f * SH_C3_3 * q * u[12] + 8.f * SH_C3_4 * xz * u[13] + SH_C3_5 * dxy * u[14];
+    // through d = v / |v|:  (I - d d^T) grad / |v|
+    const float along = x * gx + y * gy + z * gz;
+    return make_float3((gx - x * along) * inv_len, (gy - y * along) * inv_len, (gz - z * along) * inv_len);
+}
+
+// ---- geometry backward -------------------------------------------------------------------------------------------
+// Forward chain (forward.cu:74-152, 196-237):  t = W m + w0 (view space, W[k][j] = view[4 j + k]);  (u, v) = t.xy clamped to
+// +-1.3 tan(fov) t.z;  A = J W with J = [[fx/tz, 0, -fx u/tz^2], [0, fy/tz, -fy v/tz^2]] (2x3);  S = A Sigma A^T + 0.3 I (2x2);
+// conic K = adj(S) / det S.   Given the symmetric gradient G of K (dL_dconic holds G00, G01, -, G11 with G01 the gradient of
+// ONE off-diagonal entry):
+//     dL/dS     = -q adj(S) G adj(S),  q = 1 / (det^2 + 1e-7)   (the reference regularises 1/det^2 this way, backward.cu:203)
+//     dL/dSigma = A^T H A                (H = dL/dS; the six outputs double the off-diagonal entries, each stands for two)
+//     dL/dA     = 2 H A Sigma
+//     dL/dJ     = (dL/dA) W^T, only J00, J02, J11, J12 are functions of t
+// and from the screen position (ndc = P^T m / w) and the view-space depth the remaining two terms of dL/dm.
+struct GeoGrad {
+    float3 dmean;
+    float dcov[6];
+};
+__device__ __forceinline__ GeoGrad geometry_grad(const float3 m, const float* c3, const float* view, const float* proj, float fx, float fy,
+                                                 float limx, float limy, float G00, float G01, float G11, float d2x, float d2y, float ddepth) {
+    GeoGrad o;
+    // view-space position and the clamped image-plane coordinates
+    const float tx = view[0] * m.x + view[4] * m.y + view[8] * m.z + view[12];
+    const float ty = view[1] * m.x + view[5] * m.y + view[9] * m.z + view[13];
+    const float tz = view[2] * m.x + view[6] * m.y + view[10] * m.z + view[14];
+    const float itz = 1.f / tz;
+    const float rx = tx * itz, ry = ty * itz;
+    const bool in_x = !(rx < -limx || rx > limx), in_y = !(ry < -limy || ry > limy);
+    const float u = fminf(limx, fmaxf(-limx, rx)) * tz, v = fminf(limy, fmaxf(-limy, ry)) * tz;
+    const float j00 = fx * itz, j11 = fy * itz, j02 = -fx * u * itz * itz, j12 = -fy * v * itz * itz;
+    // A = J W: row 0 = j00 W[0][:] + j02 W[2][:], row 1 = j11 W[1][:] + j12 W[2][:]   (W[k][j] = view[4 j + k])
+    float A0[3], A1[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        A0[j] = j00 * view[4 * j] + j02 * view[4 * j + 2];
+        A1[j] = j11 * view[4 * j + 1] + j12 * view[4 * j + 2];
+    }
+    // B = A Sigma (2x3), S = B A^T + 0.3 I
+    const float Sg[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
+    float B0[3], B1[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        B0[j] = A0[0] * Sg[0][j] + A0[1] * Sg[1][j] + A0[2] * Sg[2][j];
+        B1[j] = A1[0] * Sg[0][j] + A1[1] * Sg[1][j] + A1[2] * Sg[2][j];
+    }
+    const float a = B0[0] * A0[0] + B0[1] * A0[1] + B0[2] * A0[2] + 0.3f;
+    const float b = B0[0] * A1[0] + B0[1] * A1[1] + B0[2] * A1[2];
+    const float c = B1[0] * A1[0] + B1[1] * A1[1] + B1[2] * A1[2] + 0.3f;
+    const float det = a * c - b * b;
+    const float q = 1.0f / (det * det + 0.0000001f);
+    // H = -q adj(S) G adj(S), adj(S) = [[c, -b], [-b, a]]
+    const float e0 = c * G00 - b * G01, e1 = c * G01 - b * G11;    // (adj G) row 0
+    const float f0 = a * G01 - b * G00, f1 = a * G11 - b * G01;    // (adj G) row 1
+    const float H00 = -q * (e0 * c - e1 * b), H01 = -q * (e1 * a - e0 * b), H11 = -q * (f1 * a - f0 * b);
+    // P = H A (2x3);  dL/dSigma = A^T P
+    float P0[3], P1[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        P0[j] = H00 * A0[j] + H01 * A1[j];
+        P1[j] = H01 * A0[j] + H11 * A1[j];
+    }
+    o.dcov[0] = A0[0] * P0[0] + A1[0] * P1[0];
+    o.dcov[3] = A0[1] * P0[1] + A1[1] * P1[1];
+    o.dcov[5] = A0[2] * P0[2] + A1[2] * P1[2];
+    o.dcov[1] = 2.f * (A0[0] * P0[1] + A1[0] * P1[1]);
+    o.dcov[2] = 2.f * (A0[0] * P0[2] + A1[0] * P1[2]);
+    o.dcov[4] = 2.f * (A0[1] * P0[2] + A1[1] * P1[2]);
+    // dL/dA = 2 H B;  dL/dJ entries = rows of dL/dA against rows of W
+    float dA0[3], dA1[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        dA0[j] = 2.f * (H00 * B0[j] + H01 * B1[j]);
+        dA1[j] = 2.f * (H01 * B0[j] + H11 * B1[j]);
+    }
+    const float dJ00 = dA0[0] * view[0] + dA0[1] * view[4] + dA0[2] * view[8];
+    const float dJ02 = dA0[0] * view[2] + dA0[1] * view[6] + dA0[2] * view[10];
+    const float dJ11 = dA1[0] * view[1] + dA1[1] * view[5] + dA1[2] * view[9];
+    const float dJ12 = dA1[0] * view[2] + dA1[1] * view[6] + dA1[2] * view[10];
+    // J(t): J00 = fx/tz, J11 = fy/tz, J02 = -fx u/tz^2, J12 = -fy v/tz^2; the clamp removes the u / v dependence on t.xy
+    const float itz2 = itz * itz;
+    const float du = in_x ? -fx * itz2 * dJ02 : 0.f, dv = in_y ? -fy * itz2 * dJ12 : 0.f;
+    const float dtz = -itz2 * (fx * dJ00 + fy * dJ11) + 2.f * itz2 * itz * (fx * u * dJ02 + fy * v * dJ12);
+    // back to world space: W^T (du, dv, dtz)
+    float3 dm;
+    dm.x = view[0] * du + view[1] * dv + view[2] * dtz;
+    dm.y = view[4] * du + view[5] * dv + view[6] * dtz;
+    dm.z = view[8] * du + view[9] * dv + view[10] * dtz;
+    // screen position: ndc = (h.x, h.y) / (h.w + 1e-7), h = P^T m; d2x, d2y are gradients in ndc units (backward.cu:376-391)
+    const float hx = proj[0] * m.x + proj[4] * m.y + proj[8] * m.z + proj[12];
+    const float hy = proj[1] * m.x + proj[5] * m.y + proj[9] * m.z + proj[13];
+    const float hw = proj[3] * m.x + proj[7] * m.y + proj[11] * m.z + proj[15];
+    const float iw = 1.0f / (hw + 0.0000001f);
+    const float dhx = d2x * iw, dhy = d2y * iw, dhw = -(d2x * hx + d2y * hy) * iw * iw;
+    dm.x += proj[0] * dhx + proj[1] * dhy + proj[3] * dhw;
+    dm.y += proj[4] * dhx + proj[5] * dhy + proj[7] * dhw;
+    dm.z += proj[8] * dhx + proj[9] * dhy + proj[11] * dhw;
+    // depth image: the reference differentiates z / w of the view transform at w = 1 (backward.cu:393-398)
+    dm.x += (view[2] - view[3] * tz) * ddepth;
+    dm.y += (view[6] - view[7] * tz) * ddepth;
+    dm.z += (view[10] - view[11] * tz) * ddepth;
+    o.dmean = dm;
     return o;
 }
 
-// SH backward for one Gaussian (backward.cu:20-139): reads its coefficients from `sh` and overwrites the
-// same row with dL/dsh (entries beyond the active degree become 0).  Returns dL/dmean from the view direction.
-__device__ float3 sh_backward(int deg, float* sh, float3 pos, const float* campos, unsigned clamp_bits, float3 dL_dcolor) {
-    float3 dir_orig = {pos.x - campos[0], pos.y - campos[1], pos.z - campos[2]};
-    float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
-    const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
-    float dRGB[3] = {dL_dcolor.x * ((clamp_bits & 1u) ? 0.f : 1.f), dL_dcolor.y * ((clamp_bits & 2u) ? 0.f : 1.f),
-                     dL_dcolor.z * ((clamp_bits & 4u) ? 0.f : 1.f)};
-    float ddir[3] = {0, 0, 0};
-    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-    float w[16];
-    w[0] = SH_C0;
-    w[1] = -SH_C1 * y; w[2] = SH_C1 * z; w[3] = -SH_C1 * x;
-    w[4] = SH_C2_0 * xy; w[5] = SH_C2_1 * yz; w[6] = SH_C2_2 * (2.f * zz - xx - yy); w[7] = SH_C2_3 * xz; w[8] = SH_C2_4 * (xx - yy);
-    w[9] = SH_C3_0 * y * (3.f * xx - yy); w[10] = SH_C3_1 * xy * z; w[11] = SH_C3_2 * y * (4.f * zz - xx - yy);
-    w[12] = SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy); w[13] = SH_C3_4 * x * (4.f * zz - xx - yy);
-    w[14] = SH_C3_5 * z * (xx - yy); w[15] = SH_C3_6 * x * (xx - 3.f * yy);
-    const int ncoef = (deg + 1) * (deg + 1);
+// Sigma = L L^T with L = R(q) diag(s), s = scale_modifier * scale (forward.cu:118-152).  D = dL/dSigma as a symmetric matrix
+// (off-diagonals = half of the stored doubled entries):  dL/dL = 2 D L;  dL/ds_j = sum_i (dL/dL)_ij R_ij;  dL/dR_ij = (dL/dL)_ij s_j,
+// and the quaternion gradient from the antisymmetric / symmetric parts of dL/dR.  The reference returns dL/ds for the EFFECTIVE
+// scale (it omits the factor scale_modifier, backward.cu:318-321) and does not normalise q; both are kept.
+__device__ __forceinline__ void cov3d_grad(const float* dcov, float3 scale, float mod, float4 qt, float3& dscale, float4& drot) {
+    const float r = qt.x, x = qt.y, y = qt.z, z = qt.w;
+    const float R[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+                           {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+                           {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+    const float s[3] = {mod * scale.x, mod * scale.y, mod * scale.z};
+    const float D[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]}, {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]}, {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+    // E = D R (3x3); dL/dL_ij = 2 E_ij s_j
+    float E[3][3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-#define S(k) sh[(k)*3 + c]
-        float dx = 0, dy = 0, dz = 0;
-        if (deg > 0) {
-            dx = -SH_C1 * S(3);
-            dy = -SH_C1 * S(1);
-            dz = SH_C1 * S(2);
-            if (deg > 1) {
-                dx += SH_C2_0 * y * S(4) + SH_C2_2 * 2.f * -x * S(6) + SH_C2_3 * z * S(7) + SH_C2_4 * 2.f * x * S(8);
-                dy += SH_C2_0 * x * S(4) + SH_C2_1 * z * S(5) + SH_C2_2 * 2.f * -y * S(6) + SH_C2_4 * 2.f * -y * S(8);
-                dz += SH_C2_1 * y * S(5) + SH_C2_2 * 2.f * 2.f * z * S(6) + SH_C2_3 * x * S(7);
-                if (deg > 2) {
-                    dx += (SH_C3_0 * S(9) * 3.f * 2.f * xy + SH_C3_1 * S(10) * yz + SH_C3_2 * S(11) * -2.f * xy + SH_C3_3 * S(12) * -3.f * 2.f * xz +
-                           SH_C3_4 * S(13) * (-3.f * xx + 4.f * zz - yy) + SH_C3_5 * S(14) * 2.f * xz + SH_C3_6 * S(15) * 3.f * (xx - yy));
-                    dy += (SH_C3_0 * S(9) * 3.f * (xx - yy) + SH_C3_1 * S(10) * xz + SH_C3_2 * S(11) * (-3.f * yy + 4.f * zz - xx) +
-                           SH_C3_3 * S(12) * -3.f * 2.f * yz + SH_C3_4 * S(13) * -2.f * xy + SH_C3_5 * S(14) * -2.f * yz + SH_C3_6 * S(15) * -3.f * 2.f * xy);
-                    dz += (SH_C3_1 * S(10) * xy + SH_C3_2 * S(11) * 4.f * 2.f * yz + SH_C3_3 * S(12) * 3.f * (2.f * zz - xx - yy) +
-                           SH_C3_4 * S(13) * 4.f * 2.f * xz + SH_C3_5 * S(14) * (xx - yy));
-                }
-            }
-        }
-        ddir[0] += dx * dRGB[c];
-        ddir[1] += dy * dRGB[c];
-        ddir[2] += dz * dRGB[c];
+    for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int k = 0; k < 16; k++) S(k) = k < ncoef ? w[k] * dRGB[c] : 0.f;
-#undef S
-    }
-    return dnormvdv3(dir_orig, make_float3(ddir[0], ddir[1], ddir[2]));
+        for (int j = 0; j < 3; j++) E[i][j] = D[i][0] * R[0][j] + D[i][1] * R[1][j] + D[i][2] * R[2][j];
+    float ds[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) ds[j] = 2.f * s[j] * (E[0][j] * R[0][j] + E[1][j] * R[1][j] + E[2][j] * R[2][j]);
+    dscale = make_float3(ds[0], ds[1], ds[2]);
+    // G = dL/dR, G_ij = 2 E_ij s_j^2
+    float Gm[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) Gm[i][j] = 2.f * E[i][j] * s[j] * s[j];
+    const float ax = Gm[2][1] - Gm[1][2], ay = Gm[0][2] - Gm[2][0], az = Gm[1][0] - Gm[0][1];
+    const float sxy = Gm[0][1] + Gm[1][0], sxz = Gm[0][2] + Gm[2][0], syz = Gm[1][2] + Gm[2][1];
+    drot.x = 2.f * (x * ax + y * ay + z * az);
+    drot.y = 2.f * (r * ax + y * sxy + z * sxz) - 4.f * x * (Gm[1][1] + Gm[2][2]);
+    drot.z = 2.f * (r * ay + x * sxy + z * syz) - 4.f * y * (Gm[0][0] + Gm[2][2]);
+    drot.w = 2.f * (r * az + x * sxz + y * syz) - 4.f * z * (Gm[0][0] + Gm[1][1]);
 }
 
 // M16: shs has exactly 16 coefficients (48 floats, 16-byte aligned rows): rows move as float4 with compile-time indexing
@@ -371,115 +494,28 @@ __global__ void __launch_bounds__(GB_THREADS) k_gaussian_backward(const GBParams
     float4 drot = {0, 0, 0, 0};
     if (vis) {
         const float3 mean = {p.means3D[3 * (size_t)idx], p.means3D[3 * (size_t)idx + 1], p.means3D[3 * (size_t)idx + 2]};
-        // ---------------- computeCov2DCUDA (backward.cu:144-274) ----------------
-        {
-            float c3[6];
+        float c3[6];
 #pragma unroll
-            for (int k = 0; k < 6; k++) c3[k] = p.cov3Ds[6 * (size_t)idx + k];
-            const float3 dL_dconic = {p.dL_dconic[4 * (size_t)idx], p.dL_dconic[4 * (size_t)idx + 1], p.dL_dconic[4 * (size_t)idx + 3]};
-            float3 t = xform4x3(mean, view);
-            const float limx = 1.3f * p.tanfovx, limy = 1.3f * p.tanfovy;
-            const float txtz = t.x / t.z, tytz = t.y / t.z;
-            t.x = min(limx, max(-limx, txtz)) * t.z;
-            t.y = min(limy, max(-limy, tytz)) * t.z;
-            const float x_grad_mul = txtz < -limx || txtz > limx ? 0 : 1;
-            const float y_grad_mul = tytz < -limy || tytz > limy ? 0 : 1;
-            m3 J = m3_make(p.h_x / t.z, 0.0f, -(p.h_x * t.x) / (t.z * t.z), 0.0f, p.h_y / t.z, -(p.h_y * t.y) / (t.z * t.z), 0, 0, 0);
-            m3 Wm = m3_make(view[0], view[4], view[8], view[1], view[5], view[9], view[2], view[6], view[10]);
-            m3 Vrk = m3_make(c3[0], c3[1], c3[2], c3[1], c3[3], c3[4], c3[2], c3[4], c3[5]);
-            m3 T = m3_mul(Wm, J);
-            m3 cov2D = m3_mul(m3_mul(m3_t(T), m3_t(Vrk)), T);
-            const float a = cov2D.m[0][0] + 0.3f, b = cov2D.m[0][1], c = cov2D.m[1][1] + 0.3f;
-            const float denom = a * c - b * b;
-            float dL_da = 0, dL_db = 0, dL_dc = 0;
-            const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-#define TT(c_, r_) T.m[c_][r_]
-#define VV(c_, r_) Vrk.m[c_][r_]
-            if (denom2inv != 0) {
-                dL_da = denom2inv * (-c * c * dL_dconic.x + 2 * b * c * dL_dconic.y + (denom - a * c) * dL_dconic.z);
-                dL_dc = denom2inv * (-a * a * dL_dconic.z + 2 * a * b * dL_dconic.y + (denom - a * c) * dL_dconic.x);
-                dL_db = denom2inv * 2 * (b * c * dL_dconic.x - (denom + 2 * b * b) * dL_dconic.y + a * b * dL_dconic.z);
-                dcov[0] = (TT(0, 0) * TT(0, 0) * dL_da + TT(0, 0) * TT(1, 0) * dL_db + TT(1, 0) * TT(1, 0) * dL_dc);
-                dcov[3] = (TT(0, 1) * TT(0, 1) * dL_da + TT(0, 1) * TT(1, 1) * dL_db + TT(1, 1) * TT(1, 1) * dL_dc);
-                dcov[5] = (TT(0, 2) * TT(0, 2) * dL_da + TT(0, 2) * TT(1, 2) * dL_db + TT(1, 2) * TT(1, 2) * dL_dc);
-                dcov[1] = 2 * TT(0, 0) * TT(0, 1) * dL_da + (TT(0, 0) * TT(1, 1) + TT(0, 1) * TT(1, 0)) * dL_db + 2 * TT(1, 0) * TT(1, 1) * dL_dc;
-                dcov[2] = 2 * TT(0, 0) * TT(0, 2) * dL_da + (TT(0, 0) * TT(1, 2) + TT(0, 2) * TT(1, 0)) * dL_db + 2 * TT(1, 0) * TT(1, 2) * dL_dc;
-                dcov[4] = 2 * TT(0, 2) * TT(0, 1) * dL_da + (TT(0, 1) * TT(1, 2) + TT(0, 2) * TT(1, 1)) * dL_db + 2 * TT(1, 1) * TT(1, 2) * dL_dc;
-            }
-            const float dL_dT00 = 2 * (TT(0, 0) * VV(0, 0) + TT(0, 1) * VV(0, 1) + TT(0, 2) * VV(0, 2)) * dL_da + (TT(1, 0) * VV(0, 0) + TT(1, 1) * VV(0, 1) + TT(1, 2) * VV(0, 2)) * dL_db;
-            const float dL_dT01 = 2 * (TT(0, 0) * VV(1, 0) + TT(0, 1) * VV(1, 1) + TT(0, 2) * VV(1, 2)) * dL_da + (TT(1, 0) * VV(1, 0) + TT(1, 1) * VV(1, 1) + TT(1, 2) * VV(1, 2)) * dL_db;
-            const float dL_dT02 = 2 * (TT(0, 0) * VV(2, 0) + TT(0, 1) * VV(2, 1) + TT(0, 2) * VV(2, 2)) * dL_da + (TT(1, 0) * VV(2, 0) + TT(1, 1) * VV(2, 1) + TT(1, 2) * VV(2, 2)) * dL_db;
-            const float dL_dT10 = 2 * (TT(1, 0) * VV(0, 0) + TT(1, 1) * VV(0, 1) + TT(1, 2) * VV(0, 2)) * dL_dc + (TT(0, 0) * VV(0, 0) + TT(0, 1) * VV(0, 1) + TT(0, 2) * VV(0, 2)) * dL_db;
-            const float dL_dT11 = 2 * (TT(1, 0) * VV(1, 0) + TT(1, 1) * VV(1, 1) + TT(1, 2) * VV(1, 2)) * dL_dc + (TT(0, 0) * VV(1, 0) + TT(0, 1) * VV(1, 1) + TT(0, 2) * VV(1, 2)) * dL_db;
-            const float dL_dT12 = 2 * (TT(1, 0) * VV(2, 0) + TT(1, 1) * VV(2, 1) + TT(1, 2) * VV(2, 2)) * dL_dc + (TT(0, 0) * VV(2, 0) + TT(0, 1) * VV(2, 1) + TT(0, 2) * VV(2, 2)) * dL_db;
-#undef TT
-#undef VV
-            const float dL_dJ00 = Wm.m[0][0] * dL_dT00 + Wm.m[0][1] * dL_dT01 + Wm.m[0][2] * dL_dT02;
-            const float dL_dJ02 = Wm.m[2][0] * dL_dT00 + Wm.m[2][1] * dL_dT01 + Wm.m[2][2] * dL_dT02;
-            const float dL_dJ11 = Wm.m[1][0] * dL_dT10 + Wm.m[1][1] * dL_dT11 + Wm.m[1][2] * dL_dT12;
-            const float dL_dJ12 = Wm.m[2][0] * dL_dT10 + Wm.m[2][1] * dL_dT11 + Wm.m[2][2] * dL_dT12;
-            const float tz = 1.f / t.z, tz2 = tz * tz, tz3 = tz2 * tz;
-            const float dL_dtx = x_grad_mul * -p.h_x * tz2 * dL_dJ02;
-            const float dL_dty = y_grad_mul * -p.h_y * tz2 * dL_dJ12;
-            const float dL_dtz = -p.h_x * tz2 * dL_dJ00 - p.h_y * tz2 * dL_dJ11 + (2 * p.h_x * t.x) * tz3 * dL_dJ02 + (2 * p.h_y * t.y) * tz3 * dL_dJ12;
-            // transformVec4x3Transpose (auxiliary.h:89-97)
-            dmean.x = view[0] * dL_dtx + view[1] * dL_dty + view[2] * dL_dtz;
-            dmean.y = view[4] * dL_dtx + view[5] * dL_dty + view[6] * dL_dtz;
-            dmean.z = view[8] * dL_dtx + view[9] * dL_dty + view[10] * dL_dtz;
+        for (int k = 0; k < 6; k++) c3[k] = p.cov3Ds[6 * (size_t)idx + k];
+        const float4 gK = (((uintptr_t)p.dL_dconic & 15) == 0) ? reinterpret_cast<const float4*>(p.dL_dconic)[idx]  // (G00, G01, -, G11)
+                                                                : make_float4(p.dL_dconic[4 * (size_t)idx], p.dL_dconic[4 * (size_t)idx + 1], 0.f,
+                                                                              p.dL_dconic[4 * (size_t)idx + 3]);
+        const GeoGrad gg = geometry_grad(mean, c3, view, proj, p.h_x, p.h_y, 1.3f * p.tanfovx, 1.3f * p.tanfovy, gK.x, gK.y, gK.w,
+                                         p.dL_dmean2D[3 * (size_t)idx], p.dL_dmean2D[3 * (size_t)idx + 1], p.dL_ddepth[idx]);
+        dmean = gg.dmean;
+#pragma unroll
+        for (int k = 0; k < 6; k++) dcov[k] = gg.dcov[k];
+        if (p.shs) {
+            const float3 dcol = {p.dL_dcolor[3 * (size_t)idx], p.dL_dcolor[3 * (size_t)idx + 1], p.dL_dcolor[3 * (size_t)idx + 2]};
+            const float3 dm = sh_grad(p.D, wstage + lane * GB_STRIDE, mean, cam.campos, p.clamped[idx], dcol);
+            dmean.x += dm.x; dmean.y += dm.y; dmean.z += dm.z;
         }
-        // ---------------- preprocessCUDA backward (backward.cu:346-412) ----------------
-        {
-            const float3 m = mean;
-            const float4 m_hom = xform4x4(m, proj);
-            const float m_w = 1.0f / (m_hom.w + 0.0000001f);
-            const float mul1 = (proj[0] * m.x + proj[4] * m.y + proj[8] * m.z + proj[12]) * m_w * m_w;
-            const float mul2 = (proj[1] * m.x + proj[5] * m.y + proj[9] * m.z + proj[13]) * m_w * m_w;
-            const float d2x = p.dL_dmean2D[3 * (size_t)idx], d2y = p.dL_dmean2D[3 * (size_t)idx + 1];
-            float3 dL_dmean;
-            dL_dmean.x = (proj[0] * m_w - proj[3] * mul1) * d2x + (proj[1] * m_w - proj[3] * mul2) * d2y;
-            dL_dmean.y = (proj[4] * m_w - proj[7] * mul1) * d2x + (proj[5] * m_w - proj[7] * mul2) * d2y;
-            dL_dmean.z = (proj[8] * m_w - proj[11] * mul1) * d2x + (proj[9] * m_w - proj[11] * mul2) * d2y;
-            dmean.x += dL_dmean.x; dmean.y += dL_dmean.y; dmean.z += dL_dmean.z;
-            const float mul3 = view[2] * m.x + view[6] * m.y + view[10] * m.z + view[14];
-            const float dd = p.dL_ddepth[idx];
-            dmean.x += (view[2] - view[3] * mul3) * dd;
-            dmean.y += (view[6] - view[7] * mul3) * dd;
-            dmean.z += (view[10] - view[11] * mul3) * dd;
-            if (p.shs) {
-                const float3 dcol = {p.dL_dcolor[3 * (size_t)idx], p.dL_dcolor[3 * (size_t)idx + 1], p.dL_dcolor[3 * (size_t)idx + 2]};
-                const float3 dm = sh_backward(p.D, wstage + lane * GB_STRIDE, m, cam.campos, p.clamped[idx], dcol);
-                dmean.x += dm.x; dmean.y += dm.y; dmean.z += dm.z;
-            }
-            if (p.scales) {  // computeCov3D backward (backward.cu:278-341)
-                const float sx = p.scales[3 * (size_t)idx], sy = p.scales[3 * (size_t)idx + 1], sz = p.scales[3 * (size_t)idx + 2];
-                const float r = p.rotations[4 * (size_t)idx], x = p.rotations[4 * (size_t)idx + 1], y = p.rotations[4 * (size_t)idx + 2], z = p.rotations[4 * (size_t)idx + 3];
-                m3 R = m3_make(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
-                               2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
-                               2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
-                const float s0 = p.scale_modifier * sx, s1 = p.scale_modifier * sy, s2 = p.scale_modifier * sz;
-                m3 S = m3_make(s0, 0.0f, 0.0f, 0.0f, s1, 0.0f, 0.0f, 0.0f, s2);
-                m3 Mm = m3_mul(S, R);
-                m3 dL_dSigma = m3_make(dcov[0], 0.5f * dcov[1], 0.5f * dcov[2], 0.5f * dcov[1], dcov[3], 0.5f * dcov[4],
-                                       0.5f * dcov[2], 0.5f * dcov[4], dcov[5]);
-                m3 M2;
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-#pragma unroll
-                    for (int rr = 0; rr < 3; rr++) M2.m[c][rr] = 2.0f * Mm.m[c][rr];
-                m3 dL_dM = m3_mul(M2, dL_dSigma);
-                m3 Rt = m3_t(R), dMt = m3_t(dL_dM);
-                dscale.x = Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2];
-                dscale.y = Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2];
-                dscale.z = Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2];
-#pragma unroll
-                for (int rr = 0; rr < 3; rr++) { dMt.m[0][rr] *= s0; dMt.m[1][rr] *= s1; dMt.m[2][rr] *= s2; }
-#define Dm(c_, r_) dMt.m[c_][r_]
-                drot.x = 2 * z * (Dm(0, 1) - Dm(1, 0)) + 2 * y * (Dm(2, 0) - Dm(0, 2)) + 2 * x * (Dm(1, 2) - Dm(2, 1));
-                drot.y = 2 * y * (Dm(1, 0) + Dm(0, 1)) + 2 * z * (Dm(2, 0) + Dm(0, 2)) + 2 * r * (Dm(1, 2) - Dm(2, 1)) - 4 * x * (Dm(2, 2) + Dm(1, 1));
-                drot.z = 2 * x * (Dm(1, 0) + Dm(0, 1)) + 2 * r * (Dm(2, 0) - Dm(0, 2)) + 2 * z * (Dm(1, 2) + Dm(2, 1)) - 4 * y * (Dm(2, 2) + Dm(0, 0));
-                drot.w = 2 * r * (Dm(0, 1) - Dm(1, 0)) + 2 * x * (Dm(2, 0) + Dm(0, 2)) + 2 * y * (Dm(1, 2) + Dm(2, 1)) - 4 * z * (Dm(1, 1) + Dm(0, 0));
-#undef Dm
-            }
+        if (p.scales) {
+            const float3 sc = {p.scales[3 * (size_t)idx], p.scales[3 * (size_t)idx + 1], p.scales[3 * (size_t)idx + 2]};
+            const float4 qt = (((uintptr_t)p.rotations & 15) == 0) ? reinterpret_cast<const float4*>(p.rotations)[idx]
+                                                                  : make_float4(p.rotations[4 * (size_t)idx], p.rotations[4 * (size_t)idx + 1],
+                                                                                p.rotations[4 * (size_t)idx + 2], p.rotations[4 * (size_t)idx + 3]);
+            cov3d_grad(dcov, sc, p.scale_modifier, qt, dscale, drot);
         }
     }
     if (valid) {

@@ -128,13 +128,19 @@ class FrameLoop:
 
     def __init__(self, gaussians: Dict[str, torch.Tensor], sh_degree: int, width: int, height: int, bg=(0.0, 0.0, 0.0),
                  scale_modifier: float = 1.0, device=None, ring: int = 3, to_host: bool = True, tight_tiles: Optional[bool] = None,
-                 product: bool = False, pack8: bool = False, depth_scale: float = 3.0):
+                 product: bool = False, pack8: bool = False, depth_scale: float = 3.0, streams: int = 1):
         from . import rasterizer as R  # requires the CUDA library
         self._R = R
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.g = {k: v.to(self.device).float().contiguous() for k, v in gaussians.items()}
         self.sh_degree, self.W, self.H, self.scale_modifier = sh_degree, width, height, scale_modifier
         self.bg = torch.tensor(bg, dtype=torch.float32, device=self.device)
+        # streams > 1: consecutive frames are issued on different CUDA streams (ring slot s always uses stream s % streams), so the
+        # tail of one frame's kernels overlaps the head of the next frame's; the ring is rounded up to a multiple of `streams`.
+        # Frames edited per frame through `before_frame` share one set of resident arrays and fall back to a single stream.
+        self.nstreams = max(1, int(streams))
+        if self.nstreams > 1:
+            ring = ((max(ring, self.nstreams) + self.nstreams - 1) // self.nstreams) * self.nstreams
         self.ring = ring
         self.to_host = to_host
         self.tight_tiles = tight_tiles  # None: follow rasterizer.set_tight_tiles()
@@ -148,7 +154,9 @@ class FrameLoop:
         if product:
             from . import renderer as RD
             self._RD = RD
-            self.normals = torch.empty((P, 3), dtype=torch.float32, device=dev)  # per-Gaussian normal*0.5+0.5 of the current frame
+            # per-Gaussian normal*0.5+0.5 of the frame in flight, one buffer per compute stream
+            self.normals_s = [torch.empty((P, 3), dtype=torch.float32, device=dev) for _ in range(self.nstreams)]
+            self.normals = self.normals_s[0]
             self.extra = [torch.empty((3, H, W), dtype=torch.float32, device=dev) for _ in range(ring)]
             self.nmaps = [(torch.empty((H, W, 3), dtype=torch.float32, device=dev), torch.empty((H, W, 3), dtype=torch.float32, device=dev))
                           for _ in range(ring)]
@@ -166,6 +174,7 @@ class FrameLoop:
                                      "normal8": torch.empty((H, W, 3), dtype=torch.uint8, device=dev)})
         self.host = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in self.outputs[s].items()} for s in range(ring)] if to_host else None
         self.copy_stream = torch.cuda.Stream(self.device) if to_host else None
+        self.compute_streams = [torch.cuda.Stream(self.device) for _ in range(self.nstreams)] if self.nstreams > 1 else None
         # per-frame host->device payload: the 37 camera floats, plus (product mode) the 4x4 inverse of the view matrix that the
         # pseudo-normal needs — inverted on the host in float64 (the reference calls torch.inverse on the GPU every frame)
         self._cam_floats = CAM_FLOATS + (16 if product else 0)
@@ -198,7 +207,7 @@ class FrameLoop:
                                o["rgba8"].data_ptr(), None, o["depth8"].data_ptr())
                 ent["L"], ent["check"], ent["C"] = _lib.lib, _lib.check, C
         else:
-            normals = self.normals[:P]
+            normals = self.normals_s[slot % self.nstreams][:P]
             ent["fwd"] = R.PreparedForward(g["means3D"], g["shs"], g["opacities"], g["scales"], g["rotations"], cam, self.W, self.H, self.bg,
                                            self.sh_degree, self.scale_modifier, out, extra=normals, extra_out=self.extra[slot], tight=self.tight_tiles)
             L = _lib.lib
@@ -268,7 +277,8 @@ class FrameLoop:
         if P > self.radii[0].shape[0]:
             self.radii = [torch.empty((P,), dtype=torch.int32, device=self.device) for _ in range(self.ring)]
             if self.product:
-                self.normals = torch.empty((P, 3), dtype=torch.float32, device=self.device)
+                self.normals_s = [torch.empty((P, 3), dtype=torch.float32, device=self.device) for _ in range(self.nstreams)]
+                self.normals = self.normals_s[0]
         del P_old
 
     def render(self, packed_cams: torch.Tensor, consume: Optional[Callable] = None,
@@ -283,6 +293,15 @@ class FrameLoop:
         stats: List[Optional[Dict[str, int]]] = [None] * n
         inflight = []  # (frame index, slot, ticket, copy_done_event)
         cur = torch.cuda.current_stream(self.device)
+        multi = self.compute_streams is not None and before_frame is None
+        if multi:  # the compute streams start after whatever the caller queued on its stream (parameter uploads, edits)
+            start = torch.cuda.Event()
+            start.record(cur)
+            for cs in self.compute_streams:
+                cs.wait_event(start)
+
+        def stream_of(slot):
+            return self.compute_streams[slot % self.nstreams] if multi else cur
 
         def retire(entry):
             i, slot, ticket, ev = entry
@@ -294,10 +313,11 @@ class FrameLoop:
                     g_i = before_frame(i)
                     if g_i is not None:
                         self.set_gaussians(g_i)
-                ticket = self._issue(slot, packed_cams[i], sync=True)
-                if self.to_host:
-                    self._copy_out(slot)
-                    cur.synchronize()
+                with torch.cuda.stream(stream_of(slot)):
+                    ticket = self._issue(slot, packed_cams[i], sync=True)
+                    if self.to_host:
+                        self._copy_out(slot)
+                stream_of(slot).synchronize()
             elif ev is not None:
                 ev.synchronize()
             stats[i] = ticket.stats()
@@ -312,19 +332,26 @@ class FrameLoop:
                 g_i = before_frame(i)
                 if g_i is not None:
                     self.set_gaussians(g_i)
-            ticket = self._issue(slot, packed_cams[i], sync=False)
-            ev = None
-            if self.to_host:
-                done = ticket.event
-                if self.product or self.pack8:  # the ticket's event was recorded after the forward; the post kernels come later on the stream
-                    done = torch.cuda.Event()
-                    done.record(cur)
-                self.copy_stream.wait_event(done)
-                with torch.cuda.stream(self.copy_stream):
-                    self._copy_out(slot)
-                    ev = torch.cuda.Event()
-                    ev.record(self.copy_stream)
+            cs = stream_of(slot)
+            with torch.cuda.stream(cs):
+                ticket = self._issue(slot, packed_cams[i], sync=False)
+                ev = None
+                if self.to_host:
+                    done = ticket.event
+                    if self.product or self.pack8:  # the ticket's event was recorded after the forward; the post kernels come later on the stream
+                        done = torch.cuda.Event()
+                        done.record(cs)
+                    self.copy_stream.wait_event(done)
+                    with torch.cuda.stream(self.copy_stream):
+                        self._copy_out(slot)
+                        ev = torch.cuda.Event()
+                        ev.record(self.copy_stream)
             inflight.append((i, slot, ticket, ev))
         while inflight:
             retire(inflight.pop(0))
+        if multi:  # later work on the caller's stream is ordered after the frames
+            for cs in self.compute_streams:
+                e = torch.cuda.Event()
+                e.record(cs)
+                cur.wait_event(e)
         return stats  # type: ignore[return-value]

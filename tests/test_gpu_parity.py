@@ -592,3 +592,30 @@ def test_ticket_outlives_the_counter_ring(dev):
     for _ in range(R._DeviceState.RING + 6):
         R.forward_raw(b["means3D"], b["shs"], None, b["opacities"], b["scales"], b["rotations"], None, sb, sync=False)
     assert held.stats()["num_rendered"] == want
+
+
+def test_frame_loop_two_streams_and_pack8(dev, scene3m):
+    """FrameLoop(streams=2): consecutive frames on alternating CUDA streams, same frames bit for bit; pack8 without the product frame
+    hands off RGBA8 + fp32 depth + the 8-bit depth index."""
+    from autovfx_b200 import render_loop as RL, renderer as RD
+    g, cams = scene3m
+    gs = {k: v[:150000] for k, v in g.items()}
+    sel = [cams[i] for i in (3, 40, 77, 120, 180, 250, 299)]
+    one = RL.FrameLoop(gs, 3, 1920, 1080, device=dev, ring=3, to_host=True)
+    want = {}
+    one.render(RL.pack_cameras(sel), lambda i, f, s: want.__setitem__(i, f.clone()))
+    two = RL.FrameLoop(gs, 3, 1920, 1080, device=dev, ring=3, to_host=True, streams=2)
+    assert two.ring == 4
+    got = {}
+    st = two.render(RL.pack_cameras(sel), lambda i, f, s: got.__setitem__(i, f.clone()))
+    assert len(got) == len(sel) and all(s["overflow"] == 0 for s in st)
+    for i in range(len(sel)):
+        assert torch.equal(got[i], want[i]), i
+    p8 = RL.FrameLoop(gs, 3, 1920, 1080, device=dev, ring=4, to_host=True, pack8=True, streams=2)
+    got8 = {}
+    p8.render(RL.pack_cameras(sel), lambda i, f, s: got8.__setitem__(i, {k: v.clone() for k, v in f.items()}))
+    for i in range(len(sel)):
+        fr = want[i].to(dev)
+        packed = RD.pack_frame(fr[0:3], fr[4], fr[3], None, depth_scale=3.0)
+        assert torch.equal(got8[i]["rgba8"].to(dev), packed["rgba8"]) and torch.equal(got8[i]["depth8"].to(dev), packed["depth8"])
+        assert torch.equal(got8[i]["depth"], want[i][3])
