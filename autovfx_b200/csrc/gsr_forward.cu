@@ -188,50 +188,123 @@ __device__ __forceinline__ void cov3d_ref_rounding(float sx, float sy, float sz,
     c3[5] = __fmaf_rn(M22, M22, __fmaf_rn(M20, M20, __fmul_rn(M21, M21)));
 }
 
-// Kernel 1 of 5.  DEG / VEC / BULK / WIN only matter to k_color_emit below; this kernel is colour-agnostic.
-// One thread per Gaussian: near cull, 3D covariance, EWA projection, conic, radius, tile rectangle (forward.cu:155-256 minus the
-// colour), the per-tile histogram with ranked tickets, and the compact list of visible Gaussians the colour + emission
-// kernel walks.  Only 44 bytes per Gaussian are read; the 192-byte SH row is not touched here.
+// Kernel 1 of 5 (colour-agnostic; DEG / VEC / BULK / WIN only matter to k_color_emit below).
+// Phase 1, one thread per Gaussian: load the 44 bytes of geometry, near cull, and a cheap CONSERVATIVE screen test — an upper
+// bound of the splat radius (trace and norm bounds, see radius_bound) against the image rectangle; a Gaussian it rejects has an
+// empty tile rectangle in the reference too (forward.cu:236), so it gets radius 0 without the projection math.  The survivors of
+// the CTA are compacted through shared memory.  Phase 2, one thread per survivor (whole warps retire early): 3D covariance, EWA
+// projection, conic, radius, tile rectangle (forward.cu:155-256 minus the colour), the per-tile histogram with ranked tickets,
+// and the compact list of visible Gaussians the colour + emission kernel walks.  The 192-byte SH row is not touched here.
+struct ProjCand {  // one phase-1 survivor
+    float mx, my, mz, opacity;
+    float a0, a1, a2, a3, a4, a5, a6;  // scale.xyz + rotation.rxyz, or cov3D[0..5]
+    int idx;
+};
+
 template <int MINB>
 __global__ void __launch_bounds__(PRE_THREADS, MINB) k_project(const PreParams p) {
     __shared__ CamConsts cam;
-    const int tid = threadIdx.x, lane = tid & 31;
+    __shared__ float s_w2;                       // upper bound of the squared spectral norm of the view matrix's 3x3 part
+    __shared__ ProjCand s_cand[PRE_THREADS];
+    __shared__ int s_wcnt[PRE_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 16) cam.view[tid] = p.view[tid];
     else if (tid < 32) cam.proj[tid - 16] = p.proj[tid - 16];
     __syncthreads();
+    if (tid == 0) {
+        // rigid view matrices have orthonormal rows: then the norm is 1; anything else falls back to the Frobenius norm
+        const float* v = cam.view;
+        float dev = 0.f, frob = 0.f;
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                const float d = v[i] * v[j] + v[4 + i] * v[4 + j] + v[8 + i] * v[8 + j] - (i == j ? 1.f : 0.f);
+                dev = fmaxf(dev, fabsf(d));
+                frob += v[4 * j + i] * v[4 * j + i];
+            }
+        s_w2 = dev < 1.0e-3f ? 1.01f : frob * 1.01f;
+    }
+    __syncthreads();
 
-    const int idx = blockIdx.x * PRE_THREADS + tid;
-    const bool valid = idx < p.P;
+    const int idx0 = blockIdx.x * PRE_THREADS + tid;
+    const bool valid0 = idx0 < p.P;
+    bool cand = false;
+    ProjCand me;
+    me.idx = idx0;
+    if (valid0) {
+        // all per-Gaussian inputs are requested up front (one memory round trip instead of three dependent ones)
+        me.mx = p.means3D[3 * (size_t)idx0]; me.my = p.means3D[3 * (size_t)idx0 + 1]; me.mz = p.means3D[3 * (size_t)idx0 + 2];
+        me.opacity = p.opacities[idx0];
+        if (p.cov3D_precomp != nullptr) {
+            const float* c = p.cov3D_precomp + 6 * (size_t)idx0;
+            me.a0 = c[0]; me.a1 = c[1]; me.a2 = c[2]; me.a3 = c[3]; me.a4 = c[4]; me.a5 = c[5]; me.a6 = 0.f;
+        } else {
+            me.a0 = p.scales[3 * (size_t)idx0]; me.a1 = p.scales[3 * (size_t)idx0 + 1]; me.a2 = p.scales[3 * (size_t)idx0 + 2];
+            float4 q;
+            if (p.rot_vec) q = reinterpret_cast<const float4*>(p.rotations)[idx0];
+            else q = make_float4(p.rotations[4 * (size_t)idx0], p.rotations[4 * (size_t)idx0 + 1], p.rotations[4 * (size_t)idx0 + 2], p.rotations[4 * (size_t)idx0 + 3]);
+            me.a3 = q.x; me.a4 = q.y; me.a5 = q.z; me.a6 = q.w;
+        }
+        const float3 mean = {me.mx, me.my, me.mz};
+        const float3 p_view = xform4x3(mean, cam.view);
+        if (p_view.z <= 0.2f) {  // near cull (auxiliary.h:139-164): only view-space z is tested
+            if (p.prefiltered) p.counters->trapped = 1;
+        } else {
+            // upper bound of the radius: lambda_max(cov2D) <= trace <= |J|_F^2 |W|_2^2 lambda_max(Sigma) + 0.6, and
+            // lambda1 = mid + sqrt(max(0.1, mid^2 - det)) <= 2 mid + 0.32
+            float lam;
+            if (p.cov3D_precomp != nullptr) lam = me.a0 + me.a3 + me.a5;  // trace(Sigma)
+            else {
+                const float s2 = p.scale_modifier * p.scale_modifier * fmaxf(me.a0 * me.a0, fmaxf(me.a1 * me.a1, me.a2 * me.a2));
+                const float n = me.a3 * me.a3 + me.a4 * me.a4 + me.a5 * me.a5 + me.a6 * me.a6;       // |q|^2 (not normalised by the rasterizer)
+                const float r2 = fabsf(n - 1.f) < 1.0e-3f ? 1.01f : 9.f * (1.f + 2.f * n) * (1.f + 2.f * n);  // |R|_2^2 <= |R|_F^2 bound
+                lam = s2 * r2;
+            }
+            const float limx = 1.3f * p.tanfovx, limy = 1.3f * p.tanfovy;
+            const float cj = p.focal_x * p.focal_x * (1.f + limx * limx) + p.focal_y * p.focal_y * (1.f + limy * limy);
+            const float l1 = cj * s_w2 * lam / (p_view.z * p_view.z) * 1.01f + 0.92f;
+            const float rmax = ceilf(3.f * sqrtf(l1)) + 2.f;
+            const float4 p_hom = xform4x4(mean, cam.proj);
+            const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+            const float px = ((p_hom.x * p_w + 1.0f) * p.W - 1.0f) * 0.5f, py = ((p_hom.y * p_w + 1.0f) * p.H - 1.0f) * 0.5f;
+            // empty tile rectangle (auxiliary.h:46-56): px + r < 1 or px - r >= 16 gx (same in y); one pixel of slack for the float evaluation
+            const bool off = (px + rmax < -1.f) || (px - rmax > (float)(p.gx * GSR_TILE) + 1.f) || (py + rmax < -1.f) || (py - rmax > (float)(p.gy * GSR_TILE) + 1.f);
+            cand = !off;
+        }
+        if (!cand) p.radii[idx0] = 0;
+    }
+    // ---- CTA-level compaction of the candidates ----
+    const unsigned cm = __ballot_sync(GSR_FULL, cand);
+    if (lane == 0) s_wcnt[warp] = __popc(cm);
+    __syncthreads();
+    int base = 0, ncand = 0;
+#pragma unroll
+    for (int w = 0; w < PRE_THREADS / 32; w++) {
+        if (w < warp) base += s_wcnt[w];
+        ncand += s_wcnt[w];
+    }
+    if (cand) s_cand[base + __popc(cm & ((1u << lane) - 1u))] = me;
+    __syncthreads();
+    if (warp * 32 >= ncand) return;  // whole warp without work
+
+    // ---- phase 2 ----
+    const bool valid = tid < ncand;
+    const ProjCand c = s_cand[valid ? tid : 0];
+    const int idx = c.idx;
     bool vis = false;
     int radius = 0, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    float3 mean = {0, 0, 0};
     float px = 0, py = 0, depth = 0, con_a = 0, con_b = 0, con_c = 0;
     float c3[6] = {0, 0, 0, 0, 0, 0};
-
-    // all per-Gaussian inputs are requested up front (one memory round trip instead of three dependent ones)
-    float opacity = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
-    float4 q = make_float4(0, 0, 0, 0);
+    const float opacity = c.opacity;
     if (valid) {
-        mean = make_float3(p.means3D[3 * (size_t)idx], p.means3D[3 * (size_t)idx + 1], p.means3D[3 * (size_t)idx + 2]);
-        opacity = p.opacities[idx];
-        if (p.cov3D_precomp != nullptr) {
-#pragma unroll
-            for (int k = 0; k < 6; k++) c3[k] = p.cov3D_precomp[6 * (size_t)idx + k];
-        } else {
-            sx = p.scales[3 * (size_t)idx]; sy = p.scales[3 * (size_t)idx + 1]; sz = p.scales[3 * (size_t)idx + 2];
-            if (p.rot_vec) q = reinterpret_cast<const float4*>(p.rotations)[idx];
-            else q = make_float4(p.rotations[4 * (size_t)idx], p.rotations[4 * (size_t)idx + 1], p.rotations[4 * (size_t)idx + 2], p.rotations[4 * (size_t)idx + 3]);
-        }
-        // near cull (auxiliary.h:139-164): only view-space z is tested
+        const float3 mean = {c.mx, c.my, c.mz};
+        if (p.cov3D_precomp != nullptr) { c3[0] = c.a0; c3[1] = c.a1; c3[2] = c.a2; c3[3] = c.a3; c3[4] = c.a4; c3[5] = c.a5; }
         float4 p_hom = xform4x4(mean, cam.proj);
         float p_w = 1.0f / (p_hom.w + 0.0000001f);
         float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
         float3 p_view = xform4x3(mean, cam.view);
-        if (p_view.z <= 0.2f) {
-            if (p.prefiltered) p.counters->trapped = 1;
-        } else {
+        {
             // 3D covariance (forward.cu:118-152)
-            if (p.cov3D_precomp == nullptr) cov3d_ref_rounding(sx, sy, sz, p.scale_modifier, q, c3);
+            if (p.cov3D_precomp == nullptr) cov3d_ref_rounding(c.a0, c.a1, c.a2, p.scale_modifier, make_float4(c.a3, c.a4, c.a5, c.a6), c3);
             // EWA 2D covariance (forward.cu:74-113)
             float3 t = xform4x3(mean, cam.view);
             const float limx = 1.3f * p.tanfovx, limy = 1.3f * p.tanfovy;
@@ -322,10 +395,10 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) k_project(const PreParams p
     // compact list of the visible Gaussians (order is irrelevant: every entry is processed independently)
     const unsigned vm = __ballot_sync(GSR_FULL, vis);
     if (vm) {
-        uint32_t base = 0;
-        if (lane == __ffs(vm) - 1) base = atomicAdd(&p.counters->num_visible, (uint32_t)__popc(vm));
-        base = __shfl_sync(GSR_FULL, base, __ffs(vm) - 1);
-        if (vis) p.vis_list[base + __popc(vm & ((1u << lane) - 1u))] = (uint32_t)idx;
+        uint32_t vbase = 0;
+        if (lane == __ffs(vm) - 1) vbase = atomicAdd(&p.counters->num_visible, (uint32_t)__popc(vm));
+        vbase = __shfl_sync(GSR_FULL, vbase, __ffs(vm) - 1);
+        if (vis) p.vis_list[vbase + __popc(vm & ((1u << lane) - 1u))] = (uint32_t)idx;
     }
 }
 
@@ -421,7 +494,9 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_color_emit(const EmitParams 
     constexpr int NF = sh_nf(DG);
     constexpr int STRIDE = sh_stride(DG, VEC, WIN);
     __shared__ float campos[3];
-    __shared__ __align__(16) float stage[DEG < 0 ? 4 : PRE_THREADS * STRIDE];
+    // per warp: the SH staging rows of its 32 Gaussians, later reused as the emission's owner table (16 words per Gaussian)
+    constexpr int WSTAGE = (DEG < 0 || 32 * STRIDE < 16 * 32) ? 16 * 32 : 32 * STRIDE;
+    __shared__ __align__(16) float stage[(PRE_THREADS / 32) * WSTAGE];
     __shared__ __align__(8) unsigned long long stage_bar[PRE_THREADS / 32];
 
     const uint32_t nvis = p.counters->num_visible;
@@ -448,6 +523,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_color_emit(const EmitParams 
     // ---- colour ----
     float rgb[3] = {0, 0, 0};
     unsigned clamp_bits = 0;
+    float* wstage = stage + warp * WSTAGE;
     if constexpr (DEG < 0) {
         if (vis) {
             rgb[0] = p.colors_precomp[3 * (size_t)idx];
@@ -458,7 +534,6 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_color_emit(const EmitParams 
         float3 mean = {0, 0, 0};
         if (vis) mean = make_float3(p.means3D[3 * (size_t)idx], p.means3D[3 * (size_t)idx + 1], p.means3D[3 * (size_t)idx + 2]);
         const unsigned vismask = __ballot_sync(GSR_FULL, vis);
-        float* wstage = stage + warp * 32 * STRIDE;
         const size_t row_floats = (size_t)p.M * 3;
         int win_off = 0;  // floats between the start of the staged window and the row's first coefficient (WIN only)
         if (VEC && BULK) {
@@ -504,81 +579,98 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_color_emit(const EmitParams 
     }
 
     // ---- emission ----
+    // The (Gaussian, tile column) pairs of the warp's 32 Gaussians are FLATTENED into one work list and dealt to the lanes round
+    // robin, so a lane whose Gaussian covers one tile does not idle while its neighbour walks a 3x3 rectangle: every owner parks
+    // its rectangle, strip context and key words in shared memory, a warp scan of the per-Gaussian item counts gives each item
+    // its owner (binary search over 32 prefix sums), and the item's lane evaluates the two strips of its column once and walks
+    // the column's (at most 8) tiles.  Columns taller than 8 tiles (rectangles of > 8 tiles only) are split into chunks of 8 rows.
     if (p.counters->overflow) return;  // set by k_tile_scan: the binning buffer is too small for this frame
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
     if (vis) tile_rect(r0.x, r0.y, radius, p.gx, p.gy, x0, y0, x1, y1);
-    const int h = y1 - y0, cnt = (x1 - x0) * h;
-    const uint32_t dbits = __float_as_uint(r1.z);
-    const uint32_t lo_id = PACKED ? idx << 8 : idx;
-    if (cnt > 0 && cnt <= 8) {
+    const int w = x1 - x0, h = y1 - y0, cnt = w * h;
+    const int cpc = (h + 7) >> 3;  // chunks per column
+    const int n_items = w * cpc;
+    float* own = wstage;  // the SH staging area is free after sh_eval
+    __syncwarp();
+    {
         StripCtx sc = {};
-        bool none = false;
-        if (PACKED) {
+        if (PACKED && cnt > 0) {
             const float um = fmaxf(r0.x - (float)(x0 * GSR_TILE), (float)(x1 * GSR_TILE) - r0.x);
             const float vm = fmaxf(r0.y - (float)(y0 * GSR_TILE), (float)(y1 * GSR_TILE) - r0.y);
             sc = strip_ctx(r0.x, r0.y, r0.z, r0.w, r1.x, r1.w, um, vm);
-            none = sc.none;
         }
-        const uint32_t* rk = p.ranks + 8 * (size_t)idx;
-        int kk = 0;
-        for (int tx = x0; tx < x1; tx++) {
-            float ylo0 = 0.f, yhi0 = 0.f, ylo1 = 0.f, yhi1 = 0.f;
-            bool v0 = false, v1 = false;
-            if (PACKED && sc.ok && !none) {
-                v0 = strip_rows(sc, (float)(tx * GSR_TILE), 8.f, ylo0, yhi0);
-                v1 = strip_rows(sc, (float)(tx * GSR_TILE + 8), 8.f, ylo1, yhi1);
-            }
-            for (int ty = y0; ty < y1; ty++, kk++) {
-                const uint32_t rank = rk[kk];
-                uint32_t mask = 0;
-                if (PACKED) {
-                    if (!sc.ok) mask = tile_foot_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.w, tx, ty);
-                    else {
-                        const float Y = (float)(ty * GSR_TILE);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            if (v0 && ylo0 <= Y + (4.f * j + 3.f) && yhi0 >= Y + 4.f * j) mask |= 1u << (2 * j);
-                            if (v1 && ylo1 <= Y + (4.f * j + 3.f) && yhi1 >= Y + 4.f * j) mask |= 2u << (2 * j);
-                        }
-                    }
-                }
-                if (!TIGHT || rank != 0xffffffffu) p.pairs[p.ranges[ty * p.gx + tx].x + rank] = make_uint2(lo_id | mask, dbits);  // little endian: u64 = depth bits << 32 | low word
-            }
-        }
+        own[0 * 32 + lane] = r0.x; own[1 * 32 + lane] = r0.y; own[2 * 32 + lane] = r0.w; own[3 * 32 + lane] = sc.det;
+        own[4 * 32 + lane] = sc.rc; own[5 * 32 + lane] = sc.cT; own[6 * 32 + lane] = sc.sstar;
+        own[7 * 32 + lane] = __uint_as_float((sc.ok ? 1u : 0u) | (sc.none ? 2u : 0u) | (cnt > 8 ? 4u : 0u));
+        own[8 * 32 + lane] = __uint_as_float((uint32_t)x0 | ((uint32_t)y0 << 16));
+        own[9 * 32 + lane] = __uint_as_float((uint32_t)w | ((uint32_t)h << 16));
+        own[10 * 32 + lane] = __uint_as_float(idx);
+        own[11 * 32 + lane] = r1.z;   // depth
+        own[12 * 32 + lane] = r0.z;   // conic a
+        own[13 * 32 + lane] = r1.x;   // conic c
+        own[14 * 32 + lane] = r1.w;   // tau
     }
-    // > 8 tiles: walked by the whole warp, positions from the per-tile cursor initialised by k_tile_scan; the tight-tile
-    // test is re-evaluated on the same stored values k_project used (bitwise same decision).  The owner computes the strip
-    // context once; the warp's lanes then only evaluate the two strips of their tile.
-    {
-        const bool big = cnt > 8;
-        StripCtx bc = {};
-        if (PACKED && big) {
-            const float um = fmaxf(r0.x - (float)(x0 * GSR_TILE), (float)(x1 * GSR_TILE) - r0.x);
-            const float vm = fmaxf(r0.y - (float)(y0 * GSR_TILE), (float)(y1 * GSR_TILE) - r0.y);
-            bc = strip_ctx(r0.x, r0.y, r0.z, r0.w, r1.x, r1.w, um, vm);
+    int incl = n_items;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(GSR_FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    own[15 * 32 + lane] = __int_as_float(incl - n_items);  // exclusive prefix of the item counts
+    const int total = __shfl_sync(GSR_FULL, incl, 31);
+    __syncwarp();
+    for (int j = lane; j < total; j += 32) {
+        int g = 0;  // owner: the last Gaussian whose prefix is <= j
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+            if (__float_as_int(own[15 * 32 + g + step]) <= j) g += step;
+        const int local = j - __float_as_int(own[15 * 32 + g]);
+        const uint32_t wh = __float_as_uint(own[9 * 32 + g]), xy = __float_as_uint(own[8 * 32 + g]), fl = __float_as_uint(own[7 * 32 + g]);
+        const int gh = (int)(wh >> 16), gx0 = (int)(xy & 0xffffu), gy0 = (int)(xy >> 16);
+        const int gcpc = (gh + 7) >> 3;
+        const int col = gcpc == 1 ? local : local / gcpc, chunk = local - col * gcpc;
+        const int tx = gx0 + col, ty_lo = gy0 + 8 * chunk, ty_hi = min(gy0 + gh, ty_lo + 8);
+        const uint32_t gid = __float_as_uint(own[10 * 32 + g]), dbits = __float_as_uint(own[11 * 32 + g]);
+        const uint32_t lo_id = PACKED ? gid << 8 : gid;
+        const bool big = fl & 4u;
+        const float gpx = own[0 * 32 + g], gpy = own[1 * 32 + g], gb = own[2 * 32 + g];
+        float ylo0 = 0.f, yhi0 = 0.f, ylo1 = 0.f, yhi1 = 0.f;
+        bool v0 = false, v1 = false;
+        if (PACKED && (fl & 1u) && !(fl & 2u)) {
+            StripCtx c2;
+            c2.px = gpx; c2.py = gpy; c2.b = gb; c2.det = own[3 * 32 + g]; c2.rc = own[4 * 32 + g]; c2.cT = own[5 * 32 + g]; c2.sstar = own[6 * 32 + g];
+            c2.ok = true; c2.none = false;
+            v0 = strip_rows(c2, (float)(tx * GSR_TILE), 8.f, ylo0, yhi0);
+            v1 = strip_rows(c2, (float)(tx * GSR_TILE + 8), 8.f, ylo1, yhi1);
         }
-        const uint32_t pay[14] = {lo_id, dbits, __float_as_uint(r0.x), __float_as_uint(r0.y), __float_as_uint(r0.z),
-                                  __float_as_uint(r0.w), __float_as_uint(r1.x), __float_as_uint(r1.w),
-                                  __float_as_uint(bc.det), __float_as_uint(bc.rc), __float_as_uint(bc.cT), __float_as_uint(bc.sstar),
-                                  (uint32_t)bc.ok, (uint32_t)bc.none};
-        uint32_t* tf = p.tile_fill;
-        uint2* pr = p.pairs;
-        for_each_tile<0, 14>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, p.gx, pay, [&](int tile, int tx, int ty, const uint32_t(&o)[14]) {
-            const float ox = __uint_as_float(o[2]), oy = __uint_as_float(o[3]), oa = __uint_as_float(o[4]), ob = __uint_as_float(o[5]),
-                        oc = __uint_as_float(o[6]), ot = __uint_as_float(o[7]);
-            if (TIGHT && !tile_may_touch(ox, oy, oa, ob, oc, ot, tx, ty)) return;
+        const uint32_t* rk = p.ranks + 8 * (size_t)gid + col * gh;  // column-major ranks of a <= 8-tile rectangle
+        for (int ty = ty_lo; ty < ty_hi; ty++) {
+            const int tile = ty * p.gx + tx;
             uint32_t mask = 0;
             if (PACKED) {
-                if (!o[12]) mask = tile_foot_mask(ox, oy, oa, ob, oc, ot, tx, ty);
-                else if (!o[13]) {
-                    StripCtx c2;
-                    c2.px = ox; c2.py = oy; c2.b = ob; c2.det = __uint_as_float(o[8]); c2.rc = __uint_as_float(o[9]);
-                    c2.cT = __uint_as_float(o[10]); c2.sstar = __uint_as_float(o[11]); c2.ok = true; c2.none = false;
-                    mask = strip_tile_mask(c2, tx, ty);
+                if (!(fl & 1u)) mask = tile_foot_mask(gpx, gpy, own[12 * 32 + g], gb, own[13 * 32 + g], own[14 * 32 + g], tx, ty);
+                else {
+                    const float Y = (float)(ty * GSR_TILE);
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        if (v0 && ylo0 <= Y + (4.f * r + 3.f) && yhi0 >= Y + 4.f * r) mask |= 1u << (2 * r);
+                        if (v1 && ylo1 <= Y + (4.f * r + 3.f) && yhi1 >= Y + 4.f * r) mask |= 2u << (2 * r);
+                    }
                 }
             }
-            pr[atomicAdd(&tf[tile], 1u)] = make_uint2(o[0] | mask, o[1]);
-        });
+            uint32_t pos;
+            if (!big) {
+                const uint32_t rank = rk[ty - gy0];
+                if (TIGHT && rank == 0xffffffffu) continue;
+                pos = p.ranges[tile].x + rank;
+            } else {
+                // > 8 tiles: position from the per-tile cursor initialised by k_tile_scan; the tight-tile test is re-evaluated on the
+                // same stored values k_project used (bitwise same decision)
+                if (TIGHT && !tile_may_touch(gpx, gpy, own[12 * 32 + g], gb, own[13 * 32 + g], own[14 * 32 + g], tx, ty)) continue;
+                pos = atomicAdd(&p.tile_fill[tile], 1u);
+            }
+            p.pairs[pos] = make_uint2(lo_id | mask, dbits);  // little endian: u64 = depth bits << 32 | low word
+        }
     }
 }
 

@@ -263,6 +263,14 @@ def reference_arm(args, K, Wm, dev, g, cams, my_cams, my_cams_host, workload, g_
         del g2
     except Exception as ex:  # noqa: BLE001
         cfg2 = {"value": None, "error": str(ex)}
+    knn = None
+    try:
+        ref_cuda.dist2(g["means3D"][:100000])
+        torch.cuda.synchronize()
+        ms_knn, _ = cuda_time(lambda i: ref_cuda.dist2(g["means3D"]).shape[0], 1, torch.cuda.synchronize)
+        knn = {"value": ms_knn, "unit": "ms", "points": int(g["means3D"].shape[0]), "higher_is_better": False, "what": "SimpleKNN::knn (KNN/simple_knn.cu:185-220) on the 3M means, 1 call"}
+    except Exception as ex:  # noqa: BLE001
+        knn = {"value": None, "error": str(ex)}
     emit_result({"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": K, "warmup": Wm, "ms_per_step": ms,
                  "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                  "config": {"workload": workload, "reference": "unmodified diff-gaussian-rasterization CUDA (oracle/_ref) on the same B200",
@@ -270,7 +278,7 @@ def reference_arm(args, K, Wm, dev, g, cams, my_cams, my_cams_host, workload, g_
                  "clocks": clocks,
                  "train_step": {"value": 1000.0 / ms_tr, "unit": "iterations/s", "ms": ms_tr, "iterations": n_tr,
                                 "what": "Rasterizer::forward + Rasterizer::backward, dL/dimage ~ N(0,1) seed 7"},
-                 "product_frame": product, "config2": cfg2,
+                 "product_frame": product, "config2": cfg2, "dist2": knn,
                  "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference",
                                   "sample": "%d frames; the reference path is CUDA, driven by 1 host thread incl. its per-frame blocking D2H" % K},
                  "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
@@ -651,6 +659,18 @@ def main():
             line["config5"] = {"value": None, "error": "%s: %s" % (type(ex).__name__, ex)}
 
     log("[bench] config5 done (%.0f s)" % (time.time() - t0))
+    if not args.quick and rank == 0:
+        # ---- distCUDA2 (simple_knn) on the scene's 3M points: init-time call of GaussianModel.create_from_pcd ----
+        try:
+            from simple_knn._C import distCUDA2
+            distCUDA2(g["means3D"])
+            torch.cuda.synchronize()
+            ms_knn, _ = cuda_time(lambda i: distCUDA2(g["means3D"]).shape[0], 3, torch.cuda.synchronize)
+            line["dist2"] = {"value": ms_knn, "unit": "ms", "points": P, "higher_is_better": False,
+                             "what": "simple_knn._C.distCUDA2 on the 3M means (exact 3-NN mean squared distance); the reference arm times SimpleKNN::knn on the same points"}
+        except Exception as ex:  # noqa: BLE001
+            line["dist2"] = {"value": None, "error": str(ex)}
+
     # ---- CPU baselines (rank 0, N=1 only) ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
