@@ -169,10 +169,14 @@ class _DeviceState:
     def grow(self, needed: int) -> None:
         self.capacity = max(self.capacity, int(needed * 1.25) + 4096)
 
-    def ensure_capacity(self, P: int) -> None:
+    def ensure_capacity(self, P: int, W: int = 0, H: int = 0) -> None:
         # first guess: a few instances per Gaussian; corrected from the counters of real frames
         if self.capacity < 4 * P:
             self.capacity = 4 * P
+        # the binning workspace also holds the footprint ballot matrix: capacity / 32 + 131072 rows, one per 32 list entries + one per tile
+        tiles = ((W + 15) // 16) * ((H + 15) // 16)
+        if tiles > 131072 and self.capacity < 32 * (tiles - 131072) + 64:
+            self.capacity = 32 * (tiles - 131072) + 64
 
     def next_slot(self):
         i = self.cursor
@@ -331,7 +335,7 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
         geom_b, img_b = _L.gsr_geom_bytes(P), _L.gsr_image_bytes(W, H)
         geom = st.workspace("geom", geom_b, for_backward)
         image = st.workspace("image", img_b, for_backward)
-        st.ensure_capacity(P)
+        st.ensure_capacity(P, W, H)
         do_sync = (_SYNC_MODE == "safe") if sync is None else sync
         stream = torch.cuda.current_stream(device)
         use_tight = _TIGHT_TILES if tight is None else tight
@@ -453,7 +457,7 @@ class PreparedForward:
         with torch.cuda.device(self.device):
             geom = st.workspace("geom", _L.gsr_geom_bytes(self.P), False)
             image = st.workspace("image", _L.gsr_image_bytes(self.W, self.H), False)
-            st.ensure_capacity(self.P)
+            st.ensure_capacity(self.P, self.W, self.H)
             binning = st.workspace("binning", _L.gsr_binning_bytes(st.capacity), False)
         self._bufs = (geom, binning, image)
         self._key = (geom.data_ptr(), geom.numel(), binning.data_ptr(), binning.numel(), image.data_ptr(), image.numel())

@@ -222,7 +222,7 @@ def test_capacity_overflow_is_detected_and_recovered(dev):
     try:
         st.cache.clear()    # cached binning buffers from earlier tests are larger than the capacity under test
         st.capacity = 1000  # far below R = 41671
-        st.ensure_capacity = lambda P: None  # keep the tiny capacity for this test
+        st.ensure_capacity = lambda P, W=0, H=0: None  # keep the tiny capacity for this test
         s = Hh.settings_from(a)
         # async: the frame is incomplete and its ticket says so
         res = R.forward_raw(a["means3D"], a["shs"], None, a["opacities"], a["scales"], a["rotations"], None, s, sync=False)
@@ -619,3 +619,18 @@ def test_frame_loop_two_streams_and_pack8(dev, scene3m):
         packed = RD.pack_frame(fr[0:3], fr[4], fr[3], None, depth_scale=3.0)
         assert torch.equal(got8[i]["rgba8"].to(dev), packed["rgba8"]) and torch.equal(got8[i]["depth8"].to(dev), packed["depth8"])
         assert torch.equal(got8[i]["depth"], want[i][3])
+
+
+def test_more_tiles_than_the_fixed_ballot_rows(dev):
+    """6144x6144 = 147,456 tiles, more than the 131,072 ballot-matrix rows the fixed part of the binning workspace provides: the
+    capacity is raised so that the rows fit, and the image equals the compiled reference's."""
+    g = scene.synthetic_gaussians(20000, seed=51, extent=(1.0, 1.0, 0.5), log_scale_mean=math.log(0.01), log_scale_std=0.4)
+    cam = scene.lookat_camera((0.2, -2.2, 0.6), (0, 0, 0), 6144, 6144, 50.0, fov_y_deg=50.0)
+    a = Hh.resolve(dict(g=g, cam=cam, sh_degree=3, bg=(0.0, 0.0, 0.0), scale_modifier=1.0), dev)
+    ours = Hh.run_ours(a, debug=False, exact=True)
+    assert ours["stats"]["overflow"] == 0 and ours["stats"]["num_rendered"] > 100000
+    if _have_ref():
+        ref = Hh.run_ref(a)
+        assert ref["num_rendered"] == ours["stats"]["num_rendered"]
+        for k in ("color", "alpha", "radii"):
+            assert torch.equal(ours[k], ref[k]), k
