@@ -294,7 +294,8 @@ __global__ void __launch_bounds__(WARPS * 32, OCC / WARPS) k_blend_lists(const B
             }
             const bool any_ill = __any_sync(GSR_FULL, ill);
             consumed += (uint32_t)cnt;
-            refill();       // positions of the batch after next
+            // the ring must hold the two batches after this one; expand only when it runs short (one call fills up to RING entries ahead)
+            if (filled - consumed < 96u && (block_open || nblk < nblocks)) refill();
             __syncwarp();   // staging + ring stores visible to every lane
             // next batch's records and the one after's ids go in flight now
             pos_c = pos1;

@@ -116,12 +116,16 @@ typedef struct gsr_counters {
 } gsr_counters;
 
 size_t gsr_geom_bytes(int32_t P);
+/* 13 bytes per instance of capacity (8-byte sort pair, 4-byte list entry, 1 byte of the footprint ballot matrix) + a fixed 4 MiB of
+ * ballot rows (one 32-byte row per 32 list entries and one extra per tile: enough for 131,072 tiles; an image with more tiles needs
+ * capacity >= 32 * (tiles - 131072)). */
 size_t gsr_binning_bytes(size_t capacity_instances);
 size_t gsr_image_bytes(int32_t W, int32_t H);
 /* Largest capacity (in instances) a binning workspace of `bytes` bytes provides. */
 size_t gsr_binning_capacity(size_t bytes);
 
-/* Forward: preprocess -> per-tile histogram/scan -> key emission -> per-tile depth sort -> blend.
+/* Forward: projection (+ per-tile histogram) -> tile scan -> colour + key emission (+ footprint masks) -> per-tile depth sort
+ * (+ footprint ballot matrix) -> blend (one warp per 8x4-pixel footprint).
  * Outputs: out_color [3,H,W], out_depth [1,H,W], out_alpha [1,H,W], radii [P] (int32).
  * All four are fully written (no pre-zeroing needed).  With P == 0 the images are zero-filled
  * (reference: rasterize_points.cu:68-71,82).  Asynchronous on `stream`. */
