@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
                 float4 A, B;
                 if (s < cnt && (uint32_t)(b * BWD_THREADS + s + 1) <= warp_last) {
                     A = lds128b(sa); B = lds128b(sa + 16);
-                    keep = footprint_may_touch(A.x - fcx, A.y - fcy, A.z, A.w, B.x, B.w);
+                    keep = footprint_may_touch(A.x - fcx, A.y - fcy, A.z, A.w, B.x, footprint_tau(B.y));
                 }
                 const unsigned mask = __ballot_sync(GSR_FULL, keep);
                 if (mask) {

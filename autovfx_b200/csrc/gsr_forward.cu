@@ -1,21 +1,20 @@
-// gsr_b200 forward pass: preprocess -> tile histogram/scan -> instance emission -> per-tile depth sort -> blend.
+// gsr_b200 forward pass: projection -> tile histogram/scan -> colour + instance emission -> per-tile depth sort -> blend.
 //
 // Replaces CudaRasterizer::Rasterizer::forward (DGR/cuda_rasterizer/rasterizer_impl.cu:197-339) and the
 // kernels it drives (forward.cu:155-256 preprocessCUDA, rasterizer_impl.cu:70-138 duplicateWithKeys /
 // identifyTileRanges, CUB InclusiveSum + DeviceRadixSort, forward.cu:261-378 renderCUDA).
 //
-// Pipeline differences (results are identical):
-//   * one 48-byte record per visible Gaussian {x,y,conic.a,conic.b | conic.c,opacity,depth,tau | r,g,b,-}
-//     replaces the reference's five SoA arrays, so the blend gathers 3 aligned float4 per instance;
-//   * SH coefficients are staged into shared memory with coalesced 16-byte cp.async by each warp, only for
-//     the Gaussians that survived culling, and read back conflict-free (row stride 13 float4);
-//   * binning is a two-level sort: per-tile histogram (atomics, in preprocess) -> exclusive scan over the
-//     tiles (gives the ranges and R on the device, no host round trip) -> scatter of (depth bits, id) pairs
-//     into the tile's bucket -> one CTA per tile sorts its bucket by (depth bits, id) in shared memory.
-//     The resulting order is exactly the reference's stable radix sort of (tile | depth) keys, because the
-//     reference emits every (tile, Gaussian) pair once in ascending Gaussian id (rasterizer_impl.cu:98-108);
-//   * the blend kernel culls splats per 8x4-pixel warp footprint (one splat per lane, ballot) before the
-//     per-pixel evaluation, which itself uses the reference's fp32 expressions.
+// Pipeline (results are identical):
+//   k_project     every Gaussian: near cull, conservative screen test, EWA projection, radius, tile rectangle, ranked per-tile
+//                 tickets, the geometry part of the record, the compact list of visible Gaussians;
+//   k_tile_scan   exclusive scan over the tiles: ranges, R and the overflow flag stay on the device (no host round trip);
+//   k_color_emit  every VISIBLE Gaussian: SH -> RGB from a TMA-staged row, one (depth bits, id, footprint mask) pair per
+//                 (Gaussian, tile) scattered to ranges[tile].x + rank;
+//   k_sort_tiles  one CTA per tile sorts its bucket by (depth bits, id) — exactly the order of the reference's stable radix sort
+//                 of (tile | depth) keys, because the reference emits every (tile, Gaussian) pair once in ascending Gaussian id
+//                 (rasterizer_impl.cu:98-108) — and transposes the footprint masks into the ballot matrix;
+//   k_blend_lists (gsr_blend.cu) one warp per 8x4-pixel footprint blends its survivors.
+//   Record, 48 bytes per visible Gaussian: {x, y, conic.a, conic.b | conic.c, opacity, depth, radius | r, g, b, log2 opacity}.
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -380,7 +379,8 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) k_project(const PreParams p
         if (vis) {
             float4* rec = p.records + 3 * (size_t)idx;
             rec[0] = make_float4(px, py, con_a, con_b);
-            rec[1] = make_float4(con_c, opacity, depth, tau);
+            rec[1] = make_float4(con_c, opacity, depth, __int_as_float(radius));
+            rec[2] = make_float4(c.mx, c.my, c.mz, 0.0f);  // the mean, for k_color_emit's view direction (it overwrites the quad with the colour)
             if (rect_n <= 8) {
                 uint4* rr = reinterpret_cast<uint4*>(p.ranks + 8 * (size_t)idx);
                 rr[0] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
@@ -476,10 +476,9 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
 // =====================================================================================================
 struct EmitParams {
     int P, M, gx, gy, for_backward;
-    const float *means3D, *shs, *colors_precomp, *campos;
+    const float *shs, *colors_precomp, *campos;
     float4* records;
     uint8_t* clamped;
-    const int* radii;
     const uint32_t* ranks;
     const uint32_t* vis_list;
     const uint2* ranges;
@@ -512,13 +511,16 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_color_emit(const EmitParams 
     const uint32_t k = blockIdx.x * PRE_THREADS + tid;
     const bool vis = k < nvis;
     const uint32_t idx = vis ? p.vis_list[k] : 0u;
-    float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
+    // the whole 48-byte record (two 32-byte sectors whichever part is read): geometry, radius, and the mean k_project parked in the colour quad
+    float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0;
     int radius = 0;
     if (vis) {
         r0 = p.records[3 * (size_t)idx];
         r1 = p.records[3 * (size_t)idx + 1];
-        radius = p.radii[idx];
+        r2 = p.records[3 * (size_t)idx + 2];
+        radius = __float_as_int(r1.w);
     }
+    const float tau = footprint_tau(r1.y);  // = the value k_project used for its tight-tile decisions (same function of the same opacity)
 
     // ---- colour ----
     float rgb[3] = {0, 0, 0};
@@ -531,8 +533,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_color_emit(const EmitParams 
             rgb[2] = p.colors_precomp[3 * (size_t)idx + 2];
         }
     } else {
-        float3 mean = {0, 0, 0};
-        if (vis) mean = make_float3(p.means3D[3 * (size_t)idx], p.means3D[3 * (size_t)idx + 1], p.means3D[3 * (size_t)idx + 2]);
+        const float3 mean = {r2.x, r2.y, r2.z};
         const unsigned vismask = __ballot_sync(GSR_FULL, vis);
         const size_t row_floats = (size_t)p.M * 3;
         int win_off = 0;  // floats between the start of the staged window and the row's first coefficient (WIN only)
@@ -597,7 +598,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_color_emit(const EmitParams 
         if (PACKED && cnt > 0) {
             const float um = fmaxf(r0.x - (float)(x0 * GSR_TILE), (float)(x1 * GSR_TILE) - r0.x);
             const float vm = fmaxf(r0.y - (float)(y0 * GSR_TILE), (float)(y1 * GSR_TILE) - r0.y);
-            sc = strip_ctx(r0.x, r0.y, r0.z, r0.w, r1.x, r1.w, um, vm);
+            sc = strip_ctx(r0.x, r0.y, r0.z, r0.w, r1.x, tau, um, vm);
         }
         own[0 * 32 + lane] = r0.x; own[1 * 32 + lane] = r0.y; own[2 * 32 + lane] = r0.w; own[3 * 32 + lane] = sc.det;
         own[4 * 32 + lane] = sc.rc; own[5 * 32 + lane] = sc.cT; own[6 * 32 + lane] = sc.sstar;
@@ -608,7 +609,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_color_emit(const EmitParams 
         own[11 * 32 + lane] = r1.z;   // depth
         own[12 * 32 + lane] = r0.z;   // conic a
         own[13 * 32 + lane] = r1.x;   // conic c
-        own[14 * 32 + lane] = r1.w;   // tau
+        own[14 * 32 + lane] = tau;
     }
     int incl = n_items;
 #pragma unroll
@@ -862,7 +863,7 @@ __device__ void foot_ballots(const FootArgs& fa, const unsigned long long* keys,
             const uint32_t rbase = c0 + u * SORT_THREADS + warp * 32;  // warp-uniform
             if (rbase < n) {
                 uint32_t m = 0;
-                if (rbase + lane < n) m = PACKED ? lo[u] & 0xffu : tile_foot_mask_any(r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].w, tx, ty);
+                if (rbase + lane < n) m = PACKED ? lo[u] & 0xffu : tile_foot_mask_any(r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, footprint_tau(r1[u].y), tx, ty);
                 uint32_t mine = 0;
 #pragma unroll
                 for (int f = 0; f < GSR_FOOTS; f++) {
@@ -1139,8 +1140,8 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     const bool packed = packed_ok && f->P <= (1 << 24);
     EmitParams ep;
     ep.P = f->P; ep.M = f->M; ep.gx = il.gx; ep.gy = il.gy; ep.for_backward = pp.for_backward;
-    ep.means3D = f->means3D; ep.shs = f->shs; ep.colors_precomp = f->colors_precomp; ep.campos = f->campos;
-    ep.records = pp.records; ep.clamped = pp.clamped; ep.radii = radii; ep.ranks = pp.ranks; ep.vis_list = pp.vis_list;
+    ep.shs = f->shs; ep.colors_precomp = f->colors_precomp; ep.campos = f->campos;
+    ep.records = pp.records; ep.clamped = pp.clamped; ep.ranks = pp.ranks; ep.vis_list = pp.vis_list;
     ep.ranges = ranges; ep.tile_fill = (uint32_t*)(img + il.tile_fill); ep.pairs = (uint2*)(bin + bl.pairs); ep.counters = counters;
     if (f->colors_precomp) launch_color_emit<-1>(false, false, pp.tight, packed, ep, st);
     else {

@@ -215,7 +215,7 @@ int gsr_dist2(int32_t P, const float* points, float* mean_dists, void* workspace
 /* Device pointers into the workspaces of the last layout (P, capacity, W, H) — for parity tests that
  * compare per-stage buffers with the reference.  Pure pointer arithmetic, no CUDA calls. */
 typedef struct gsr_views {
-    const float* records;        /* [P,12]: x, y, conic_a, conic_b | conic_c, opacity, depth, tau | r, g, b, - */
+    const float* records;        /* [P,12]: x, y, conic_a, conic_b | conic_c, opacity, depth, radius (int bits) | r, g, b, log2 opacity */
     const float* cov3D;          /* [P,6]  (GSR_FLAG_FOR_BACKWARD only)                             */
     const uint8_t* clamped;      /* [P]    bit c set = channel c clamped (GSR_FLAG_FOR_BACKWARD only) */
     const uint32_t* point_list;  /* [capacity] Gaussian ids, per tile front-to-back                 */

@@ -127,6 +127,37 @@ def test_pack_frame_bytes():
     assert set(only) == {"rgba8"} and int(only["rgba8"][..., 3].min()) == 255
 
 
+def test_pack_frame_bytes_against_torchvision_and_cv2(tmp_path):
+    """The per-frame conversions of the reference's loop (scene_representation.py:424-438) executed with the REAL libraries it calls —
+    torchvision.utils.save_image -> PNG, cv2.applyColorMap(COLORMAP_TURBO) (sugar/render.py:18-22), numpy astype(uint8) + cv2.cvtColor —
+    against gsr_pack_frame's bytes and the exported TURBO table."""
+    import cv2
+    import torchvision
+    from autovfx_b200 import renderer
+    g = torch.Generator().manual_seed(19)
+    H, W = 135, 240
+    rgb = (torch.rand(3, H, W, generator=g) * 1.3 - 0.15).to(DEV)
+    alpha = torch.rand(H, W, generator=g).to(DEV)
+    depth = (torch.rand(H, W, generator=g) * 4.5 - 0.4).to(DEV)
+    nrm = torch.nn.functional.normalize(torch.randn(H, W, 3, generator=g), dim=-1).to(DEV)
+    out = renderer.pack_frame(rgb, alpha, depth, nrm, depth_scale=3.0)
+    # rgb image: torchvision.utils.save_image(result["render"], png)
+    png = str(tmp_path / "f.png")
+    torchvision.utils.save_image(torch.cat([rgb, alpha[None]], 0), png)
+    bgra = cv2.imread(png, cv2.IMREAD_UNCHANGED)
+    assert bgra.shape == (H, W, 4)
+    assert np.array_equal(out["rgba8"].cpu().numpy(), bgra[..., [2, 1, 0, 3]])
+    # depth map: depth2img(depth_raw, scale=3.0) = cv2.applyColorMap((clip(depth / scale, 0, 1) * 255).astype(uint8), COLORMAP_TURBO)
+    d = depth.cpu().numpy()
+    idx = (np.clip(d / 3.0, a_min=0., a_max=1.) * 255).astype(np.uint8)
+    assert np.array_equal(out["depth8"].cpu().numpy(), idx)
+    assert np.array_equal(renderer.TURBO_LUT_BGR.numpy()[out["depth8"].cpu().numpy()], cv2.applyColorMap(idx, cv2.COLORMAP_TURBO))
+    # normal map: ((normal + 1) / 2 * 255).astype(uint8), written through cv2.cvtColor(RGB2BGR)
+    n8 = (((nrm.cpu().numpy() + 1) / 2) * 255).astype(np.uint8)
+    assert np.array_equal(out["normal8"].cpu().numpy(), n8)
+    assert np.array_equal(out["normal8"].cpu().numpy()[..., ::-1], cv2.cvtColor(n8, cv2.COLOR_RGB2BGR))
+
+
 class _PC:
     """Duck-typed stand-in for the reference's GaussianModel (scene/gaussian_model.py): activated parameters."""
 
