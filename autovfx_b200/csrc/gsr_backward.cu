@@ -8,20 +8,19 @@
 // The per-pixel recursion of the blend backward is the reference's (it must replay the forward's decisions); the per-Gaussian
 // chain rule is derived here in matrix form (see sh_grad, geometry_grad, cov3d_grad).  Differences in mechanism:
 //   * the reference issues 10 global atomicAdds per contributing (pixel, Gaussian) pair; here each warp
-//     (an 8x4 pixel footprint) reduces the 10 partial gradients with shuffles and issues one global
-//     reduction per (warp, Gaussian, component);
-//   * splats that cannot touch a warp's footprint are culled exactly as in the forward blend;
+//     (an 8x4 pixel footprint) sums the gradients of a splat over its pixels as moments (see the kernel's
+//     comment) and issues one global reduction per (warp, Gaussian, component);
+//   * a warp only visits the splats whose footprint-ballot bit is set (the forward's survivor lists);
 //   * the two per-Gaussian backward kernels are fused; SH rows are staged through shared memory with
 //     coalesced accesses in both directions, and the kernel writes every output row itself (zeros for
 //     culled Gaussians) so only the 48 B/Gaussian of atomically accumulated gradients need a memset
 //     (the reference zero-fills all 304 B/Gaussian, rasterize_points.cu:158-168).
 // Gradient sums are accumulated in a different order than the reference's atomics (which are themselves
 // unordered), so parity is to a tolerance, not bitwise.
+#include <cstdlib>
 #include "gsr_common.cuh"
 
 namespace gsr {
-
-constexpr int BWD_THREADS = 256;
 
 __device__ __forceinline__ float4 lds128b(uint32_t a) {
     float4 v;
@@ -32,216 +31,267 @@ __device__ __forceinline__ void sts128b(uint32_t a, const float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// Sum 10 per-lane values over the warp with a reduce-scatter butterfly: at every level each lane keeps the
-// half of the values its group is responsible for and ships the other half, so 5+3+2+1+1 = 12 shuffles replace
-// 10 full butterflies (50).  Afterwards the (even) lane with `valid` holds the warp total of value `vid`.
-__device__ __forceinline__ float reduce10(const float (&v)[10], int lane, int& vid, bool& valid) {
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-    float w[5], x[3], y[2];
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-        const float send = b4 ? v[i] : v[i + 5], keep = b4 ? v[i + 5] : v[i];
-        w[i] = keep + __shfl_xor_sync(GSR_FULL, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        const float hi = (i + 3 < 5) ? w[(i + 3 < 5) ? i + 3 : 0] : 0.f;
-        const float send = b3 ? w[i] : hi, keep = b3 ? hi : w[i];
-        x[i] = keep + __shfl_xor_sync(GSR_FULL, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        const float hi = (i + 2 < 3) ? x[(i + 2 < 3) ? i + 2 : 0] : 0.f;
-        const float send = b2 ? x[i] : hi, keep = b2 ? hi : x[i];
-        y[i] = keep + __shfl_xor_sync(GSR_FULL, send, 4);
-    }
-    const float send = b1 ? y[0] : y[1], keep = b1 ? y[1] : y[0];
-    float z = keep + __shfl_xor_sync(GSR_FULL, send, 2);
-    z += __shfl_xor_sync(GSR_FULL, z, 1);
-    valid = !(b2 && (b3 || b1)) && !(lane & 1);
-    vid = (b4 ? 5 : 0) + (b3 ? (b1 ? 4 : 3) : (b2 ? 2 : (b1 ? 1 : 0)));
-    return z;
+// -----------------------------------------------------------------------------------------------------------------------
+// Blend backward over the footprint lists.
+//
+// Like the forward blend (gsr_blend.cu) one WARP owns an 8x4-pixel footprint and walks that footprint's own survivors — the
+// entries of the tile's sorted list whose ballot bit says the splat can reach alpha >= 1/255 inside the footprint — this time
+// from the back (position n_contrib of the furthest pixel) to the front.  No block-level staging, no barrier, no cull.
+//
+// Per batch of 16 survivors the work is split into two phases with different lane roles:
+//   phase 1, lane = pixel: the per-pixel recursion (it has to replay the forward's decisions, forward.cu:330-366, so `power`
+//            is evaluated with the forward's instruction sequence and alpha with the same expf).  The reference carries one
+//            running "colour behind" per channel (backward.cu:533-562); everything downstream only needs its inner product
+//            with the pixel's loss gradient, so the five channel recursions collapse into ONE scalar recursion
+//                D_k = dL/dC . c_k + dL/dDepth * depth_k + dL/dAlpha,      R <- alpha_last * D_last + (1 - alpha_last) * R,
+//                dL/dalpha_k = (D_k - R) * T_k - T_final / (1 - alpha_k) * (bg . dL/dC).
+//            The phase leaves two numbers per (survivor, pixel) in shared memory: w = alpha_k T_k and s = G_k dL/dalpha_k.
+//   phase 2, lane = survivor (x half of the pixels): every gradient of the splat is a moment of w or s over the footprint,
+//                dL/dcolour = sum w dL/dC,   dL/ddepth = sum w dL/dDepth,   dL/dopacity = sum s,
+//                dL/dmean2D = -o (W/2, H/2) * (a Sx + b Sy, b Sx + c Sy),   dL/dconic = -o/2 (Sxx, Sxy, Syy),
+//            with S* = sum s {dx, dy, dx^2, dx dy, dy^2}.  The lane accumulates them over 16 pixels with plain FMAs — no
+//            shuffle reduction per (splat, component) — the two halves meet in one exchange, and ten lanes-wide reductions
+//            (RED.ADD.F32) per 16 splats go to global memory.
+// -----------------------------------------------------------------------------------------------------------------------
+struct BwdArgs {
+    const uint2* ranges; const uint32_t* point_list; const float4* records; const uint32_t* bal;
+    int W, H, gx;
+    const float *bg, *accum_alphas; const uint32_t* n_contrib;
+    const float *dL_dpixels, *dL_dpixel_depths, *dL_dpixel_alphas;
+    float *dL_dmean2D /*[P,3]*/, *dL_dconic /*[P,4]*/, *dL_dopacity, *dL_dcolors /*[P,3]*/, *dL_ddepths;
+};
+
+constexpr int BWL_WARPS = 4;
+struct BwlCfg {
+    static constexpr int REC = 32 * 48;        // staged records of one 32-survivor gather
+    static constexpr int WROW = 66;            // words per (w, s) row: 32 pixels x 2, + 2 so that rows start 2 banks apart
+    static constexpr int WS = 16 * WROW * 4;   // one 16-survivor batch
+    static constexpr int DLP = 32 * 16;        // the footprint's loss gradients {dL/dC.rgb, dL/dDepth} per pixel
+    static constexpr int RING = 128;           // expanded survivor positions (u32)
+    static constexpr int WB = REC + WS + DLP + 4 * RING;
+};
+
+__device__ __forceinline__ void sts64b(uint32_t a, float x, float y) {
+    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ float2 lds64b(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
 }
 
-constexpr int BWD_QCAP = 48;
-
-// One CTA per tile; batches of the tile's list are walked from the back.
-__global__ void __launch_bounds__(BWD_THREADS) k_blend_backward(
-    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const float4* __restrict__ records, int W, int H, int gx,
-    const float* __restrict__ bg, const float* __restrict__ accum_alphas, const uint32_t* __restrict__ n_contrib,
-    const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dpixel_alphas,
-    float* __restrict__ dL_dmean2D /*[P,3]*/, float* __restrict__ dL_dconic /*[P,4]*/, float* __restrict__ dL_dopacity,
-    float* __restrict__ dL_dcolors /*[P,3]*/, float* __restrict__ dL_ddepths) {
-    __shared__ __align__(16) float4 sRec[BWD_THREADS * 3];                    // staged batch, 48 B per splat
-    __shared__ __align__(16) float4 sQ[(BWD_THREADS / 32) * BWD_QCAP * 3];    // per-warp survivor queues (back to front)
-    __shared__ uint32_t sId[BWD_THREADS];
-    __shared__ uint32_t s_wl[BWD_THREADS / 32];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.y * gx + blockIdx.x;
-    const int X0 = blockIdx.x * GSR_TILE + (warp & 1) * 8, Y0 = blockIdx.y * GSR_TILE + (warp >> 1) * 4;
+template <int OCC>
+__global__ void __launch_bounds__(BWL_WARPS * 32, OCC) k_blend_backward(const BwdArgs a) {
+    typedef BwlCfg Cfg;
+    constexpr int PARTS = GSR_FOOTS / BWL_WARPS;
+    constexpr int RING = Cfg::RING;
+    __shared__ __align__(16) unsigned char sm[BWL_WARPS * Cfg::WB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx = blockIdx.x / PARTS, part = blockIdx.x - tx * PARTS;
+    const int f = part * BWL_WARPS + warp;
+    const int tile = blockIdx.y * a.gx + tx;
+    const int X0 = tx * GSR_TILE + (f & 1) * 8, Y0 = blockIdx.y * GSR_TILE + (f >> 1) * 4;
     const int pxi = X0 + (lane & 7), pyi = Y0 + (lane >> 3);
-    const bool inside = pxi < W && pyi < H;
+    const bool inside = pxi < a.W && pyi < a.H;
     const float pixx = (float)pxi, pixy = (float)pyi;
-    // warp-uniform values go through a broadcast so the compiler keeps them instead of re-deriving them from the ids in the loops
-    const float fcx = __shfl_sync(GSR_FULL, (float)X0 + FOOT_HX, 0), fcy = __shfl_sync(GSR_FULL, (float)Y0 + FOOT_HY, 0);
-    const size_t pid = (size_t)W * pyi + pxi, HW = (size_t)H * W;
-    const uint32_t rec_base = __shfl_sync(GSR_FULL, (uint32_t)__cvta_generic_to_shared(sRec), 0);
-    const uint32_t q_base = __shfl_sync(GSR_FULL, (uint32_t)__cvta_generic_to_shared(sQ) + (uint32_t)warp * (BWD_QCAP * 48), 0);
-    const unsigned gt_mask = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
+    const uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(sm) + (uint32_t)warp * Cfg::WB;
+    const uint32_t ws_base = rec_base + Cfg::REC, dlp_base = ws_base + Cfg::WS;
+    uint32_t* ring = reinterpret_cast<uint32_t*>(sm + (size_t)warp * Cfg::WB + Cfg::REC + Cfg::WS + Cfg::DLP);
 
-    const uint2 range = ranges[tile];
-    const int n = (int)(range.y - range.x);
-    if (n == 0) return;
-
-    // After reduce10 the warp total of gradient component `vid` sits in one fixed lane (vid depends on the lane only), so
-    // each of those ten lanes keeps the array and stride its component goes to and adds the total straight to global memory
-    // with a fire-and-forget reduction (RED.ADD.F32): one per (warp, splat, component).  (Combining the 8 warps of a tile in
-    // shared memory first costs a compare-and-swap loop per add — shared memory has no native float add — plus two extra
-    // barriers and a flush pass per batch.)
-    float* my_dst;
-    uint32_t my_stride;
-    {
-        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-        const int vid = (b4 ? 5 : 0) + (b3 ? (b1 ? 4 : 3) : (b2 ? 2 : (b1 ? 1 : 0)));  // as in reduce10
-        float* const dst[10] = {dL_dcolors, dL_dcolors + 1, dL_dcolors + 2, dL_ddepths, dL_dmean2D, dL_dmean2D + 1,
-                                dL_dconic, dL_dconic + 1, dL_dconic + 3, dL_dopacity};
-        const uint32_t strd[10] = {3, 3, 3, 1, 3, 3, 4, 4, 4, 1};
-        my_dst = dst[0];
-        my_stride = strd[0];
-#pragma unroll
-        for (int k = 1; k < 10; k++)
-            if (vid == k) { my_dst = dst[k]; my_stride = strd[k]; }
-    }
-
-    const float T_final = inside ? (1 - accum_alphas[pid]) : 0;
-    float T = T_final;
-    const uint32_t last_contributor = inside ? n_contrib[pid] : 0;
-    float accum_rec0 = 0, accum_rec1 = 0, accum_rec2 = 0, accum_red = 0, accum_rea = 0;
-    float dLp0 = 0, dLp1 = 0, dLp2 = 0, dLd = 0, dLa = 0;
-    if (inside) {
-        dLp0 = dL_dpixels[pid]; dLp1 = dL_dpixels[HW + pid]; dLp2 = dL_dpixels[2 * HW + pid];
-        dLd = dL_dpixel_depths[pid];
-        dLa = dL_dpixel_alphas[pid];
-    }
-    float last_alpha = 0, last_c0 = 0, last_c1 = 0, last_c2 = 0, last_depth = 0;
-    const float ddelx_dx = 0.5 * W, ddely_dy = 0.5 * H;  // backward.cu:488-489
-    const float bg_dot_dpixel = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
-
-    // entries with 1-based position > the warp's furthest contributor are skipped by every lane
+    const uint2 rg = a.ranges[tile];
+    if (rg.y == rg.x) return;
+    const size_t pid = (size_t)a.W * pyi + pxi, HW = (size_t)a.H * a.W;
+    const uint32_t last_contributor = inside ? a.n_contrib[pid] : 0u;  // 1-based position of the pixel's last contributor
     uint32_t warp_last = last_contributor;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(GSR_FULL, warp_last, o));
-    if (lane == 0) s_wl[warp] = warp_last;
-    __syncthreads();
-    uint32_t tile_last = 0;
-#pragma unroll
-    for (int k = 0; k < BWD_THREADS / 32; k++) tile_last = max(tile_last, s_wl[k]);
-    if (tile_last == 0) return;  // nothing contributed anywhere in this tile
+    if (warp_last == 0u) return;  // nothing contributed anywhere in this footprint
 
-    int qn = 0;
-    // replay the queued splats (back to front) for this lane's pixel: backward.cu:494-597
-    auto drain = [&](int batch) {
-        __syncwarp();
-        uint32_t qa = q_base;
-        for (int k = 0; k < qn; k++, qa += 48) {
-            const float4 A = lds128b(qa), B = lds128b(qa + 16), Cc = lds128b(qa + 32);
-            const uint32_t pos = __float_as_uint(Cc.w);  // 1-based position in the tile list
-            float g[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // dcolor[3], ddepth, dmean2D.x, .y, dconic.x, .y, .w, dopacity
-            bool contrib = false;
-            if (pos <= last_contributor) {
-                const float2 d = {A.x - pixx, A.y - pixy};
-                const float power = -0.5f * (A.z * d.x * d.x + B.x * d.y * d.y) - A.w * d.x * d.y;
-                if (!(power > 0.0f)) {
-                    const float G = exp(power);
-                    const float alpha = min(0.99f, B.y * G);
-                    if (!(alpha < 1.0f / 255.0f)) {
-                        contrib = true;
-                        T = T / (1.f - alpha);
-                        const float dchannel_dcolor = alpha * T;
-                        float dL_dalpha = 0.0f;
-                        accum_rec0 = last_alpha * last_c0 + (1.f - last_alpha) * accum_rec0;
-                        last_c0 = Cc.x;
-                        dL_dalpha += (Cc.x - accum_rec0) * dLp0;
-                        g[0] = dchannel_dcolor * dLp0;
-                        accum_rec1 = last_alpha * last_c1 + (1.f - last_alpha) * accum_rec1;
-                        last_c1 = Cc.y;
-                        dL_dalpha += (Cc.y - accum_rec1) * dLp1;
-                        g[1] = dchannel_dcolor * dLp1;
-                        accum_rec2 = last_alpha * last_c2 + (1.f - last_alpha) * accum_rec2;
-                        last_c2 = Cc.z;
-                        dL_dalpha += (Cc.z - accum_rec2) * dLp2;
-                        g[2] = dchannel_dcolor * dLp2;
-                        const float dep = B.z;
-                        accum_red = last_alpha * last_depth + (1.f - last_alpha) * accum_red;
-                        last_depth = dep;
-                        dL_dalpha += (dep - accum_red) * dLd;
-                        g[3] = dchannel_dcolor * dLd;
-                        accum_rea = last_alpha + (1.f - last_alpha) * accum_rea;
-                        dL_dalpha += (1 - accum_rea) * dLa;
-                        dL_dalpha *= T;
-                        last_alpha = alpha;
-                        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-                        const float dL_dG = B.y * dL_dalpha;
-                        const float gdx = G * d.x, gdy = G * d.y;
-                        const float dG_ddelx = -gdx * A.z - gdy * A.w;
-                        const float dG_ddely = -gdy * B.x - gdx * A.w;
-                        g[4] = dL_dG * dG_ddelx * ddelx_dx;
-                        g[5] = dL_dG * dG_ddely * ddely_dy;
-                        g[6] = -0.5f * gdx * d.x * dL_dG;
-                        g[7] = -0.5f * gdx * d.y * dL_dG;
-                        g[8] = -0.5f * gdy * d.y * dL_dG;
-                        g[9] = G * dL_dalpha;
-                    }
+    // ---- pixel state (phase 1) ----
+    float dLp0 = 0, dLp1 = 0, dLp2 = 0, dLd = 0, dLa = 0, T_final = 0;
+    if (inside) {
+        T_final = 1.0f - a.accum_alphas[pid];
+        dLp0 = a.dL_dpixels[pid]; dLp1 = a.dL_dpixels[HW + pid]; dLp2 = a.dL_dpixels[2 * HW + pid];
+        dLd = a.dL_dpixel_depths[pid];
+        dLa = a.dL_dpixel_alphas[pid];
+    }
+    sts128b(dlp_base + (uint32_t)lane * 16, make_float4(dLp0, dLp1, dLp2, dLd));
+    float T = T_final;
+    const float tfbg = -T_final * (a.bg[0] * dLp0 + a.bg[1] * dLp1 + a.bg[2] * dLp2);  // -T_final (bg . dL/dC), backward.cu:566-572
+    float R = 0.f, D_last = 0.f, alpha_last = 0.f, om_last = 1.f;
+
+    const uint32_t* __restrict__ balcol = a.bal + bal_row_base(rg.x, tile) * GSR_FOOTS + f;
+    const uint32_t* __restrict__ plist = a.point_list + rg.x;
+
+    // ---- survivor stream, back to front: stream index 0 is the set bit with the highest list position <= warp_last - 1 ----
+    const uint32_t pmax = warp_last - 1u, row_top = pmax >> 5;
+    const uint32_t nblocks = (row_top + 32u) >> 5;  // 32-row blocks, block b holds rows row_top - 32 b - lane
+    uint32_t rbits = 0, roff = 0, rrow = 0, sbase = 0, nblk = 0, filled = 0, consumed = 0;
+    bool block_open = false;
+    auto col_word = [&](uint32_t blk) -> uint32_t {
+        const uint32_t back = blk * 32u + (uint32_t)lane;
+        if (back > row_top) return 0u;
+        uint32_t w = balcol[(size_t)(row_top - back) * GSR_FOOTS];
+        if (back == 0u) w &= (2u << (pmax & 31u)) - 1u;  // entries behind the last contributor of every pixel
+        return w;
+    };
+    uint32_t wnext = col_word(0);
+    auto refill = [&]() {
+        const uint32_t limit = consumed + RING;
+        while (true) {
+            if (!block_open) {
+                if (nblk == nblocks) break;
+                rbits = wnext;
+                rrow = (row_top - min(row_top, nblk * 32u + (uint32_t)lane)) * 32u;
+                nblk++;
+                wnext = nblk < nblocks ? col_word(nblk) : 0u;
+                const uint32_t c = (uint32_t)__popc(rbits);
+                uint32_t incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(GSR_FULL, incl, o);
+                    if (lane >= o) incl += v;
                 }
+                roff = sbase + incl - c;
+                sbase += __shfl_sync(GSR_FULL, incl, 31);
+                block_open = true;
             }
-            if (__any_sync(GSR_FULL, contrib)) {
-                int vid;
-                bool valid;
-                const float z = reduce10(g, lane, vid, valid);
-                (void)vid;
-                if (valid && z != 0.0f) atomicAdd(my_dst + (size_t)sId[(int)pos - 1 - batch * BWD_THREADS] * my_stride, z);
+            while (rbits && roff < limit) {
+                const uint32_t bit = 31u - (uint32_t)__clz(rbits);
+                rbits ^= 1u << bit;
+                ring[roff & (RING - 1)] = rrow + bit;
+                roff++;
             }
+            if (__any_sync(GSR_FULL, rbits != 0u)) { filled = limit; return; }
+            block_open = false;
+            filled = sbase;
+            if (filled >= limit) return;
         }
-        qn = 0;
-        __syncwarp();
+        filled = sbase;
     };
 
-    for (int b = (int)((tile_last - 1) / BWD_THREADS); b >= 0; b--) {
-        const int cnt = min(BWD_THREADS, n - b * BWD_THREADS);
-        __syncthreads();  // every warp is done with the previous batch's records
-        if (tid < cnt) {
-            const uint32_t id = point_list[range.x + b * BWD_THREADS + tid];
-            const float4* r = records + 3 * (size_t)id;
-            float4 rc = r[2];
-            rc.w = __uint_as_float((uint32_t)(b * BWD_THREADS + tid + 1));
-            const uint32_t sa = rec_base + (uint32_t)tid * 48;
-            sts128b(sa, r[0]); sts128b(sa + 16, r[1]); sts128b(sa + 32, rc);
-            sId[tid] = id;
-        }
-        __syncthreads();
+    float4 ra = make_float4(0, 0, 0, 0), rb = ra, rc = ra;
+    uint32_t pos_c = 0, id_c = 0, pos1 = 0, id1 = 0;
+    refill();
+    __syncwarp();
+    if (consumed + lane < filled) {
+        pos_c = ring[(consumed + lane) & (RING - 1)];
+        id_c = plist[pos_c];
+        const float4* r = a.records + 3 * (size_t)id_c;
+        ra = r[0]; rb = r[1]; rc = r[2];
+    }
+    if (consumed + 32 + lane < filled) { pos1 = ring[(consumed + 32 + lane) & (RING - 1)]; id1 = plist[pos1]; }
 
-        if ((uint32_t)(b * BWD_THREADS) < warp_last) {
-            for (int base = ((cnt - 1) / 32) * 32; base >= 0; base -= 32) {
-                const int s = base + lane;
-                const uint32_t sa = rec_base + (uint32_t)s * 48;
-                bool keep = false;
-                float4 A, B;
-                if (s < cnt && (uint32_t)(b * BWD_THREADS + s + 1) <= warp_last) {
-                    A = lds128b(sa); B = lds128b(sa + 16);
-                    keep = footprint_may_touch(A.x - fcx, A.y - fcy, A.z, A.w, B.x, footprint_tau(B.y));
-                }
-                const unsigned mask = __ballot_sync(GSR_FULL, keep);
-                if (mask) {
-                    if (keep) {  // later list positions (higher lanes) are replayed first
-                        const uint32_t qa = q_base + (uint32_t)(qn + __popc(mask & gt_mask)) * 48;
-                        sts128b(qa, A); sts128b(qa + 16, B); sts128b(qa + 32, lds128b(sa + 32));
+    const float half_w = 0.5f * a.W, half_h = 0.5f * a.H;  // d(pixel)/d(ndc), backward.cu:488-489
+    const int j = lane & 15, h = lane >> 4;
+    while (consumed < filled) {
+        const int cnt = (int)min(32u, filled - consumed);
+        if (lane < cnt) {  // stage: {x, y, a, b | c, opacity, depth, position (1-based) | r, g, b, id}
+            const uint32_t sa = rec_base + (uint32_t)lane * 48;
+            sts128b(sa, ra);
+            sts128b(sa + 16, make_float4(rb.x, rb.y, rb.z, __uint_as_float(pos_c + 1u)));
+            sts128b(sa + 32, make_float4(rc.x, rc.y, rc.z, __uint_as_float(id_c)));
+        }
+        consumed += (uint32_t)cnt;
+        if (filled - consumed < 64u && (block_open || nblk < nblocks)) refill();
+        __syncwarp();
+        pos_c = pos1; id_c = id1;
+        if (consumed + lane < filled) {
+            const float4* r = a.records + 3 * (size_t)id_c;
+            ra = r[0]; rb = r[1]; rc = r[2];
+        }
+        if (consumed + 32 + lane < filled) { pos1 = ring[(consumed + 32 + lane) & (RING - 1)]; id1 = plist[pos1]; }
+
+        for (int sub = 0; sub < cnt; sub += 16) {
+            const int c16 = min(16, cnt - sub);
+            // ---- phase 1: lane = pixel ----
+            bool anyc = false;
+            uint32_t qa = rec_base + (uint32_t)sub * 48, wa = ws_base + (uint32_t)lane * 8;
+            for (int k = 0; k < c16; k++, qa += 48, wa += Cfg::WROW * 4) {
+                const float4 A = lds128b(qa), B = lds128b(qa + 16);
+                float w = 0.f, s = 0.f;
+                if (__float_as_uint(B.w) <= last_contributor) {
+                    const float dx = A.x - pixx, dy = A.y - pixy;
+                    // the forward's rounding sequence for `power` (gsr_blend.cu drain_exact): the decisions below replay the forward's
+                    const float t1 = __fmul_rn(B.x, dy), t3 = __fmul_rn(A.z, dx), t2 = __fmul_rn(-A.w, dx);
+                    const float t4 = __fmul_rn(dy, t1), t5 = __fmul_rn(dy, t2), t6 = __fmaf_rn(dx, t3, t4);
+                    const float power = __fmaf_rn(t6, -0.5f, t5);
+                    if (!(power > 0.0f)) {
+                        const float G = exp(power);
+                        const float alpha = min(0.99f, __fmul_rn(B.y, G));
+                        if (!(alpha < 1.0f / 255.0f)) {
+                            const float4 Cc = lds128b(qa + 32);
+                            const float om = 1.0f - alpha;
+                            const float rcp = 1.0f / om;
+                            T *= rcp;           // transmittance in front of this splat
+                            w = alpha * T;
+                            const float D = fmaf(Cc.x, dLp0, fmaf(Cc.y, dLp1, fmaf(Cc.z, dLp2, fmaf(B.z, dLd, dLa))));
+                            R = fmaf(alpha_last, D_last, om_last * R);
+                            const float dL_dalpha = fmaf(tfbg, rcp, (D - R) * T);
+                            s = G * dL_dalpha;
+                            alpha_last = alpha; om_last = om; D_last = D;
+                            anyc = true;
+                        }
                     }
-                    qn += __popc(mask);
-                    if (qn > BWD_QCAP - 32) drain(b);
+                }
+                sts64b(wa, w, s);
+            }
+            const bool anyw = __any_sync(GSR_FULL, anyc);
+            __syncwarp();
+            // ---- phase 2: lane = (survivor j, pixel half h) ----
+            if (anyw) {
+                float gc0 = 0, gc1 = 0, gc2 = 0, gd = 0, S0 = 0, Sx = 0, Sy = 0, Sxx = 0, Sxy = 0, Syy = 0;
+                float ca = 0, cb = 0, cc = 0, op = 0;
+                uint32_t gid = 0;
+                const bool mine = j < c16;
+                if (mine) {
+                    const uint32_t sa = rec_base + (uint32_t)(sub + j) * 48;
+                    const float4 A = lds128b(sa), B = lds128b(sa + 16);
+                    gid = __float_as_uint(lds128b(sa + 32).w);
+                    ca = A.z; cb = A.w; cc = B.x; op = B.y;
+                    const float dx0 = A.x - (float)X0, dy0 = A.y - (float)(Y0 + 2 * h);
+                    const uint32_t wr = ws_base + (uint32_t)(j * Cfg::WROW + 32 * h) * 4, dr = dlp_base + (uint32_t)h * 256;
+#pragma unroll 1
+                    for (int q = 0; q < 4; q++) {  // four pixels at a time: (row q >> 1 of the half, columns 4 (q & 1) ..)
+                        const float dy = dy0 - (float)(q >> 1), dxq = dx0 - (float)(4 * (q & 1));
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            const float2 ws2 = lds64b(wr + (uint32_t)(q * 4 + c) * 8);
+                            const float4 dl = lds128b(dr + (uint32_t)(q * 4 + c) * 16);
+                            const float dx = dxq - (float)c;
+                            gc0 = fmaf(ws2.x, dl.x, gc0); gc1 = fmaf(ws2.x, dl.y, gc1); gc2 = fmaf(ws2.x, dl.z, gc2); gd = fmaf(ws2.x, dl.w, gd);
+                            const float sx = ws2.y * dx, sy = ws2.y * dy;
+                            S0 += ws2.y; Sx += sx; Sy += sy;
+                            Sxx = fmaf(sx, dx, Sxx); Sxy = fmaf(sx, dy, Sxy); Syy = fmaf(sy, dy, Syy);
+                        }
+                    }
+                }
+                // the two halves of the footprint meet
+                gc0 += __shfl_xor_sync(GSR_FULL, gc0, 16); gc1 += __shfl_xor_sync(GSR_FULL, gc1, 16);
+                gc2 += __shfl_xor_sync(GSR_FULL, gc2, 16); gd += __shfl_xor_sync(GSR_FULL, gd, 16);
+                S0 += __shfl_xor_sync(GSR_FULL, S0, 16); Sx += __shfl_xor_sync(GSR_FULL, Sx, 16); Sy += __shfl_xor_sync(GSR_FULL, Sy, 16);
+                Sxx += __shfl_xor_sync(GSR_FULL, Sxx, 16); Sxy += __shfl_xor_sync(GSR_FULL, Sxy, 16); Syy += __shfl_xor_sync(GSR_FULL, Syy, 16);
+                if (mine) {
+                    // half 0 sends colour, depth, mean2D.x; half 1 mean2D.y, conic (xx, xy, yy), opacity
+                    const float nop = -op;
+                    const float v0 = h ? nop * half_h * fmaf(cb, Sx, cc * Sy) : gc0;
+                    const float v1 = h ? 0.5f * nop * Sxx : gc1;
+                    const float v2 = h ? 0.5f * nop * Sxy : gc2;
+                    const float v3 = h ? 0.5f * nop * Syy : gd;
+                    const float v4 = h ? S0 : nop * half_w * fmaf(ca, Sx, cb * Sy);
+                    float* const p0 = h ? a.dL_dmean2D + 3 * (size_t)gid + 1 : a.dL_dcolors + 3 * (size_t)gid;
+                    float* const p1 = h ? a.dL_dconic + 4 * (size_t)gid : a.dL_dcolors + 3 * (size_t)gid + 1;
+                    float* const p2 = h ? a.dL_dconic + 4 * (size_t)gid + 1 : a.dL_dcolors + 3 * (size_t)gid + 2;
+                    float* const p3 = h ? a.dL_dconic + 4 * (size_t)gid + 3 : a.dL_ddepths + gid;
+                    float* const p4 = h ? a.dL_dopacity + gid : a.dL_dmean2D + 3 * (size_t)gid;
+                    if (v0 != 0.0f) atomicAdd(p0, v0);
+                    if (v1 != 0.0f) atomicAdd(p1, v1);
+                    if (v2 != 0.0f) atomicAdd(p2, v2);
+                    if (v3 != 0.0f) atomicAdd(p3, v3);
+                    if (v4 != 0.0f) atomicAdd(p4, v4);
                 }
             }
-            if (qn) drain(b);
+            __syncwarp();  // the (w, s) rows and, after the second batch, the staged records are free again
         }
     }
 }
@@ -581,10 +631,20 @@ int backward_impl(const gsr_frame* f, const gsr_workspace* ws, const int32_t* ra
     char* img = (char*)ws->image; char* geo = (char*)ws->geom; char* bin = (char*)ws->binning;
     const int D = f->D < 0 ? 0 : (f->D > 3 ? 3 : f->D);
 
-    k_blend_backward<<<dim3(il.gx, il.gy), BWD_THREADS, 0, st>>>(
-        (const uint2*)(img + il.ranges), (const uint32_t*)(bin + bl.point_list), (const float4*)(geo + gl.records), f->W, f->H, il.gx, f->bg,
-        out_alpha, (const uint32_t*)(img + il.n_contrib), dL_dc, dL_dd, dL_da, g->dL_dmeans2D, g->dL_dconic, g->dL_dopacity, g->dL_dcolors,
-        g->dL_ddepths);
+    BwdArgs ba;
+    ba.ranges = (const uint2*)(img + il.ranges); ba.point_list = (const uint32_t*)(bin + bl.point_list); ba.records = (const float4*)(geo + gl.records);
+    ba.bal = (const uint32_t*)(bin + bl.bal);
+    ba.W = f->W; ba.H = f->H; ba.gx = il.gx; ba.bg = f->bg; ba.accum_alphas = out_alpha; ba.n_contrib = (const uint32_t*)(img + il.n_contrib);
+    ba.dL_dpixels = dL_dc; ba.dL_dpixel_depths = dL_dd; ba.dL_dpixel_alphas = dL_da;
+    ba.dL_dmean2D = g->dL_dmeans2D; ba.dL_dconic = g->dL_dconic; ba.dL_dopacity = g->dL_dopacity; ba.dL_dcolors = g->dL_dcolors; ba.dL_ddepths = g->dL_ddepths;
+    {
+        const dim3 grid(il.gx * (GSR_FOOTS / BWL_WARPS), il.gy);
+        static int occ = -1;  // GSR_BWD_OCC=8|6|5: resident CTAs per SM the kernel is compiled for (64 / 80 / 96 registers), an experiment knob
+        if (occ < 0) { const char* e = getenv("GSR_BWD_OCC"); occ = e ? atoi(e) : 6; }
+        if (occ == 8) k_blend_backward<8><<<grid, BWL_WARPS * 32, 0, st>>>(ba);
+        else if (occ == 5) k_blend_backward<5><<<grid, BWL_WARPS * 32, 0, st>>>(ba);
+        else k_blend_backward<6><<<grid, BWL_WARPS * 32, 0, st>>>(ba);
+    }
     int rc = check_launch("gsr_backward/blend", debug, st);
     if (rc) return rc;
 

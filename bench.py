@@ -12,8 +12,8 @@ Keys of the JSON line (rank 0 prints exactly one line on stdout):
 * ``value``        frames/s with the Gaussians and cameras resident in HBM (async issue, no host sync, no D2H).
 * ``e2e``          the same metric through the public frame loop (``autovfx_b200.render_loop.FrameLoop``) with HOST buffers: every
                    step copies its camera payload pinned-host -> device and the finished frame device -> pinned-host inside the timed
-                   region.  ``e2e`` hands off the five fp32 planes (41.5 MB/frame, the PCIe link is the limit); ``e2e_pack8`` hands off
-                   what the reference's loop gives its encoders (RGBA8 + fp32 depth + 8-bit depth index, 18.7 MB/frame).
+                   region.  ``e2e`` hands the frame off as the reference's loop stores it (RGBA8 + fp32 depth + 8-bit depth index,
+                   18.7 MB/frame); ``e2e_fp32`` hands off the five fp32 planes (41.5 MB/frame).
 * ``dropin``       frames/s through the literal drop-in call of the reference's callers: ``GaussianRasterizer(settings)(means3D=..)``
                    with nn.Parameter inputs under torch.no_grad(), safe mode (one event sync per call), fresh output tensors.
 * ``value_single_stream``  the same K frames issued on ONE stream (this pass also provides ``roofline.kernel_ms``); ``value`` alternates
@@ -604,18 +604,19 @@ def main():
 
     loop = RL.FrameLoop(g, 3, W_IMG, H_IMG, device=dev, ring=4, to_host=True, streams=2)
     e2e_s = run_loop(loop, e2e_cams, lambda fr: float(fr[4, H_IMG // 2, W_IMG // 2]))
-    line["e2e"] = {"value": frames_total / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": loop.h2d_bytes_per_frame, "d2h_bytes_per_step": loop.d2h_bytes_per_frame,
-                   "api": "autovfx_b200.render_loop.FrameLoop.render (one rasterizer forward per frame, async D2H ring of [5,H,W] fp32 frames)",
-                   "rerendered": loop.rerendered, "d2h_gbs_per_gpu": loop.d2h_bytes_per_frame * K / e2e_s / 1e9}
+    line["e2e_fp32"] = {"value": frames_total / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": loop.h2d_bytes_per_frame, "d2h_bytes_per_step": loop.d2h_bytes_per_frame,
+                        "api": "FrameLoop.render, five fp32 planes [5,H,W] per frame to pinned host memory (41.5 MB/frame: the PCIe link / host memory is the limit at N=8)",
+                        "rerendered": loop.rerendered, "d2h_gbs_per_gpu": loop.d2h_bytes_per_frame * K / e2e_s / 1e9}
     del loop
     loop8 = RL.FrameLoop(g, 3, W_IMG, H_IMG, device=dev, ring=4, to_host=True, pack8=True, streams=2)
-    e2e8_s = run_loop(loop8, e2e_cams, lambda fr: int(fr["rgba8"][H_IMG // 2, W_IMG // 2, 0]))
-    line["e2e_pack8"] = {"value": frames_total / e2e8_s, "unit": "frames/s", "h2d_bytes_per_step": loop8.h2d_bytes_per_frame,
-                         "d2h_bytes_per_step": loop8.d2h_bytes_per_frame, "rerendered": loop8.rerendered,
-                         "api": "FrameLoop(pack8=True): RGBA8 + fp32 depth + 8-bit depth index to pinned host memory (what the reference's loop hands its encoders)",
-                         "d2h_gbs_per_gpu": loop8.d2h_bytes_per_frame * K / e2e8_s / 1e9}
+    e2e8_s = run_loop(loop8, e2e_cams, lambda fr: int(fr["rgba8"][H_IMG // 2, W_IMG // 2, 0]) + float(fr["depth"][H_IMG // 2, W_IMG // 2]))
+    line["e2e"] = {"value": frames_total / e2e8_s, "unit": "frames/s", "h2d_bytes_per_step": loop8.h2d_bytes_per_frame,
+                   "d2h_bytes_per_step": loop8.d2h_bytes_per_frame, "rerendered": loop8.rerendered,
+                   "api": "autovfx_b200.render_loop.FrameLoop(pack8=True, streams=2).render: per frame the camera payload host -> device, one rasterizer forward, and the "
+                          "frame as the reference's loop stores it (scene_representation.py:424-433: RGBA as 8-bit PNG pixels, depth as float32 .npy + its 8-bit colormap "
+                          "index) device -> pinned host memory",
+                   "d2h_gbs_per_gpu": loop8.d2h_bytes_per_frame * K / e2e8_s / 1e9}
 
-    log("[bench] e2e done (%.0f s)" % (time.time() - t0))
     # ---- strong scaling: the whole 300-frame trajectory as ONE job over the N ranks (8-bit hand-off) ----
     if not args.quick:
         t_job = run_loop(loop8, my_cams_host, lambda fr: int(fr["rgba8"][H_IMG // 2, W_IMG // 2, 0]))
