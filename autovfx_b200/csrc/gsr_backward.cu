@@ -18,7 +18,9 @@
 // Gradient sums are accumulated in a different order than the reference's atomics (which are themselves
 // unordered), so parity is to a tolerance, not bitwise.
 #include <cstdlib>
+#include <type_traits>
 #include "gsr_common.cuh"
+#include "gsr_packed.cuh"
 
 namespace gsr {
 
@@ -62,6 +64,7 @@ struct BwdArgs {
 };
 
 constexpr int BWL_WARPS = 4;
+constexpr float BWL_LOG2E = 1.4426950408889634f;
 struct BwlCfg {
     static constexpr int REC = 32 * 48;        // staged records of one 32-survivor gather
     static constexpr int WROW = 66;            // words per (w, s) row: 32 pixels x 2, + 2 so that rows start 2 banks apart
@@ -191,6 +194,11 @@ __global__ void __launch_bounds__(BWL_WARPS * 32, OCC) k_blend_backward(const Bw
             sts128b(sa, ra);
             sts128b(sa + 16, make_float4(rb.x, rb.y, rb.z, __uint_as_float(pos_c + 1u)));
             sts128b(sa + 32, make_float4(rc.x, rc.y, rc.z, __uint_as_float(id_c)));
+        } else if (lane == cnt && (cnt & 1)) {  // completes the last pair of an odd batch: a splat behind every pixel's last contributor
+            const uint32_t sa = rec_base + (uint32_t)lane * 48;
+            sts128b(sa, make_float4(0.f, 0.f, 0.f, 0.f));
+            sts128b(sa + 16, make_float4(0.f, 0.f, 0.f, __uint_as_float(0xffffffffu)));
+            sts128b(sa + 32, make_float4(0.f, 0.f, 0.f, 0.f));
         }
         consumed += (uint32_t)cnt;
         if (filled - consumed < 64u && (block_open || nblk < nblocks)) refill();
@@ -205,42 +213,75 @@ __global__ void __launch_bounds__(BWL_WARPS * 32, OCC) k_blend_backward(const Bw
         for (int sub = 0; sub < cnt; sub += 16) {
             const int c16 = min(16, cnt - sub);
             // ---- phase 1: lane = pixel ----
+            // Straight-line code (a splat that does not contribute runs the recursion with alpha = 0, which leaves the state
+            // unchanged) so that the independent front parts of consecutive splats overlap the serial T / R chain.
+            // G = exp(power) comes from one MUFU (relative error < 1.2e-6 against expf).  The only place that needs more is the
+            // forward's skip decision alpha < 1/255: if any evaluation of the batch lands inside the error band, the warp restores
+            // its state and repeats the batch with the forward's own expf (a fraction of a percent of the batches).
             bool anyc = false;
-            uint32_t qa = rec_base + (uint32_t)sub * 48, wa = ws_base + (uint32_t)lane * 8;
-            for (int k = 0; k < c16; k++, qa += 48, wa += Cfg::WROW * 4) {
-                const float4 A = lds128b(qa), B = lds128b(qa + 16);
-                float w = 0.f, s = 0.f;
-                if (__float_as_uint(B.w) <= last_contributor) {
+            auto phase1 = [&](auto exact_tag) -> bool {
+                constexpr bool EXACT = decltype(exact_tag)::value;
+                bool near = false;
+                uint32_t qa = rec_base + (uint32_t)sub * 48, wa = ws_base + (uint32_t)lane * 8;
+                // everything of a splat that does not depend on the pixel's running state
+                auto front = [&](uint32_t q, float& G, float& alpha, bool& hit, float& D) {
+                    const float4 A = lds128b(q), B = lds128b(q + 16), Cc = lds128b(q + 32);
                     const float dx = A.x - pixx, dy = A.y - pixy;
                     // the forward's rounding sequence for `power` (gsr_blend.cu drain_exact): the decisions below replay the forward's
                     const float t1 = __fmul_rn(B.x, dy), t3 = __fmul_rn(A.z, dx), t2 = __fmul_rn(-A.w, dx);
                     const float t4 = __fmul_rn(dy, t1), t5 = __fmul_rn(dy, t2), t6 = __fmaf_rn(dx, t3, t4);
                     const float power = __fmaf_rn(t6, -0.5f, t5);
-                    if (!(power > 0.0f)) {
-                        const float G = exp(power);
-                        const float alpha = min(0.99f, __fmul_rn(B.y, G));
-                        if (!(alpha < 1.0f / 255.0f)) {
-                            const float4 Cc = lds128b(qa + 32);
-                            const float om = 1.0f - alpha;
-                            const float rcp = 1.0f / om;
-                            T *= rcp;           // transmittance in front of this splat
-                            w = alpha * T;
-                            const float D = fmaf(Cc.x, dLp0, fmaf(Cc.y, dLp1, fmaf(Cc.z, dLp2, fmaf(B.z, dLd, dLa))));
-                            R = fmaf(alpha_last, D_last, om_last * R);
-                            const float dL_dalpha = fmaf(tfbg, rcp, (D - R) * T);
-                            s = G * dL_dalpha;
-                            alpha_last = alpha; om_last = om; D_last = D;
-                            anyc = true;
-                        }
-                    }
+                    G = EXACT ? exp(power) : ex2_approx(power * BWL_LOG2E);
+                    const float oG = __fmul_rn(B.y, G);
+                    if (!EXACT) near |= fabsf(fmaf(oG, 255.0f, -1.0f)) < 8.0e-6f;
+                    alpha = min(0.99f, oG);
+                    hit = __float_as_uint(B.w) <= last_contributor && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                    D = fmaf(Cc.x, dLp0, fmaf(Cc.y, dLp1, fmaf(Cc.z, dLp2, fmaf(B.z, dLd, dLa))));
+                };
+                // the recursion: T, R and the (w, s) pair of this (splat, pixel)
+                auto step = [&](float G, float alpha, bool hit, float D, float& w, float& sv) {
+                    const float a_eff = hit ? alpha : 0.0f;
+                    const float om = 1.0f - a_eff;  // in [0.01, 1]: the approximate reciprocal (1 ulp, exact for 1) needs no special cases
+                    float rcp;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(om));
+                    T *= rcp;                       // transmittance in front of this splat
+                    w = a_eff * T;
+                    const float Rn = fmaf(alpha_last, D_last, om_last * R);
+                    R = hit ? Rn : R;
+                    const float dL_dalpha = fmaf(tfbg, rcp, (D - Rn) * T);
+                    sv = hit ? G * dL_dalpha : 0.0f;
+                    alpha_last = hit ? alpha : alpha_last;
+                    om_last = hit ? om : om_last;
+                    D_last = hit ? D : D_last;
+                    anyc |= hit;
+                };
+                for (int k = 0; k < c16; k += 2, qa += 96, wa += 2 * Cfg::WROW * 4) {  // two splats per iteration (an odd batch ends on a dummy)
+                    float G0, G1, al0, al1, D0, D1, w0, w1, s0, s1;
+                    bool h0, h1;
+                    front(qa, G0, al0, h0, D0);
+                    front(qa + 48, G1, al1, h1, D1);
+                    step(G0, al0, h0, D0, w0, s0);
+                    step(G1, al1, h1, D1, w1, s1);
+                    sts64b(wa, w0, s0);
+                    sts64b(wa + Cfg::WROW * 4, w1, s1);
                 }
-                sts64b(wa, w, s);
+                return near;
+            };
+            {
+                const float T0 = T, R0 = R, al0 = alpha_last, om0 = om_last, D0 = D_last;
+                if (__any_sync(GSR_FULL, phase1(std::false_type()))) {
+                    T = T0; R = R0; alpha_last = al0; om_last = om0; D_last = D0;
+                    anyc = false;
+                    phase1(std::true_type());
+                }
             }
             const bool anyw = __any_sync(GSR_FULL, anyc);
             __syncwarp();
             // ---- phase 2: lane = (survivor j, pixel half h) ----
             if (anyw) {
-                float gc0 = 0, gc1 = 0, gc2 = 0, gd = 0, S0 = 0, Sx = 0, Sy = 0, Sxx = 0, Sxy = 0, Syy = 0;
+                // packed fp32: (colour r, g), (colour b, depth), (Sx, Sy) and (Sxx, Syy) live in register pairs
+                f32x2 G01 = pk2(0.f, 0.f), G2D = G01, SXY = G01, SQ = G01;
+                float S0 = 0, Sxy = 0;
                 float ca = 0, cb = 0, cc = 0, op = 0;
                 uint32_t gid = 0;
                 const bool mine = j < c16;
@@ -252,20 +293,29 @@ __global__ void __launch_bounds__(BWL_WARPS * 32, OCC) k_blend_backward(const Bw
                     const float dx0 = A.x - (float)X0, dy0 = A.y - (float)(Y0 + 2 * h);
                     const uint32_t wr = ws_base + (uint32_t)(j * Cfg::WROW + 32 * h) * 4, dr = dlp_base + (uint32_t)h * 256;
 #pragma unroll 1
-                    for (int q = 0; q < 4; q++) {  // four pixels at a time: (row q >> 1 of the half, columns 4 (q & 1) ..)
-                        const float dy = dy0 - (float)(q >> 1), dxq = dx0 - (float)(4 * (q & 1));
+                    for (int q = 0; q < 4; q++) {  // four pixels at a time: row q >> 1 of the half, columns 4 (q & 1) ..
+                        const f32x2 dq = pk2(dx0 - (float)(4 * (q & 1)), dy0 - (float)(q >> 1));
 #pragma unroll
                         for (int c = 0; c < 4; c++) {
                             const float2 ws2 = lds64b(wr + (uint32_t)(q * 4 + c) * 8);
                             const float4 dl = lds128b(dr + (uint32_t)(q * 4 + c) * 16);
-                            const float dx = dxq - (float)c;
-                            gc0 = fmaf(ws2.x, dl.x, gc0); gc1 = fmaf(ws2.x, dl.y, gc1); gc2 = fmaf(ws2.x, dl.z, gc2); gd = fmaf(ws2.x, dl.w, gd);
-                            const float sx = ws2.y * dx, sy = ws2.y * dy;
-                            S0 += ws2.y; Sx += sx; Sy += sy;
-                            Sxx = fmaf(sx, dx, Sxx); Sxy = fmaf(sx, dy, Sxy); Syy = fmaf(sy, dy, Syy);
+                            const f32x2 dxy = c ? add2(dq, pk2(-(float)c, 0.0f)) : dq;
+                            const f32x2 ww = pk2(ws2.x, ws2.x), ss = pk2(ws2.y, ws2.y);
+                            G01 = fma2(ww, pk2(dl.x, dl.y), G01);
+                            G2D = fma2(ww, pk2(dl.z, dl.w), G2D);
+                            const f32x2 sxy = mul2(ss, dxy);  // s (dx, dy)
+                            SXY = add2(SXY, sxy);
+                            SQ = fma2(sxy, dxy, SQ);          // s (dx^2, dy^2)
+                            float sx, sy_, dx_, dy;
+                            upk2(sxy, sx, sy_);
+                            upk2(dxy, dx_, dy);
+                            Sxy = fmaf(sx, dy, Sxy);
+                            S0 += ws2.y;
                         }
                     }
                 }
+                float gc0, gc1, gc2, gd, Sx, Sy, Sxx, Syy;
+                upk2(G01, gc0, gc1); upk2(G2D, gc2, gd); upk2(SXY, Sx, Sy); upk2(SQ, Sxx, Syy);
                 // the two halves of the footprint meet
                 gc0 += __shfl_xor_sync(GSR_FULL, gc0, 16); gc1 += __shfl_xor_sync(GSR_FULL, gc1, 16);
                 gc2 += __shfl_xor_sync(GSR_FULL, gc2, 16); gd += __shfl_xor_sync(GSR_FULL, gd, 16);
