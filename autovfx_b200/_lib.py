@@ -55,6 +55,8 @@ GSR_FLAG_SORTED_KEYS = 2
 GSR_FLAG_TIGHT_TILES = 4
 GSR_FLAG_REUSE_GEOMETRY = 8
 GSR_FLAG_EXACT_IMAGES = 16
+GSR_FLAG_BINNING_ONLY = 32
+GSR_FLAG_RESUME = 64
 ABI_VERSION = 3
 
 EXPORTS = ("gsr_abi_version", "gsr_last_error", "gsr_geom_bytes", "gsr_binning_bytes", "gsr_binning_capacity", "gsr_image_bytes",

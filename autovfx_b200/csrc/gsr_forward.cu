@@ -200,7 +200,7 @@ struct ProjCand {  // one phase-1 survivor
     int idx;
 };
 
-template <int MINB>
+template <int MINB, bool TIGHT>
 __global__ void __launch_bounds__(PRE_THREADS, MINB) k_project(const PreParams p) {
     __shared__ CamConsts cam;
     __shared__ float s_w2;                       // upper bound of the squared spectral norm of the view matrix's 3x3 part
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) k_project(const PreParams p
         for (int k = 0; k < 8; k++) {
             if (k < rect_n) {
                 rk[k] = 0xffffffffu;
-                if (!p.tight || tile_may_touch(px, py, con_a, con_b, con_c, tau, tx, ty)) rk[k] = atomicAdd(&p.tile_count[ty * p.gx + tx], 1u);
+                if (!TIGHT || tile_may_touch(px, py, con_a, con_b, con_c, tau, tx, ty)) rk[k] = atomicAdd(&p.tile_count[ty * p.gx + tx], 1u);
                 if (++ty == y1) { ty = y0; tx++; }
             }
         }
@@ -364,14 +364,19 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) k_project(const PreParams p
     {
         const bool big = rect_n > 8;
         uint32_t* tb = p.tile_big;
-        const int tight = p.tight;
-        const uint32_t pay[6] = {__float_as_uint(px), __float_as_uint(py), __float_as_uint(con_a), __float_as_uint(con_b),
-                                 __float_as_uint(con_c), __float_as_uint(tau)};
-        for_each_tile<0, 6>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, p.gx, pay, [&](int tile, int tx, int ty, const uint32_t(&o)[6]) {
-            if (!tight || tile_may_touch(__uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]),
-                                         __uint_as_float(o[4]), __uint_as_float(o[5]), tx, ty))
-                atomicAdd(&tb[tile], 1u);
-        });
+        if (TIGHT) {
+            const uint32_t pay[6] = {__float_as_uint(px), __float_as_uint(py), __float_as_uint(con_a), __float_as_uint(con_b),
+                                     __float_as_uint(con_c), __float_as_uint(tau)};
+            for_each_tile<0, 6>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, p.gx, pay, [&](int tile, int tx, int ty, const uint32_t(&o)[6]) {
+                if (tile_may_touch(__uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]),
+                                   __uint_as_float(o[4]), __uint_as_float(o[5]), tx, ty))
+                    atomicAdd(&tb[tile], 1u);
+            });
+        } else {
+            const uint32_t pay[1] = {0u};
+            for_each_tile<0, 1>(big ? x0 : 0, big ? y0 : 0, big ? x1 : 0, big ? y1 : 0, p.gx, pay,
+                                [&](int tile, int, int, const uint32_t(&)[1]) { atomicAdd(&tb[tile], 1u); });
+        }
     }
 
     if (valid) {
@@ -644,33 +649,44 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_color_emit(const EmitParams 
             v0 = strip_rows(c2, (float)(tx * GSR_TILE), 8.f, ylo0, yhi0);
             v1 = strip_rows(c2, (float)(tx * GSR_TILE + 8), 8.f, ylo1, yhi1);
         }
-        const uint32_t* rk = p.ranks + 8 * (size_t)gid + col * gh;  // column-major ranks of a <= 8-tile rectangle
-        for (int ty = ty_lo; ty < ty_hi; ty++) {
-            const int tile = ty * p.gx + tx;
-            uint32_t mask = 0;
-            if (PACKED) {
-                if (!(fl & 1u)) mask = tile_foot_mask(gpx, gpy, own[12 * 32 + g], gb, own[13 * 32 + g], own[14 * 32 + g], tx, ty);
-                else {
-                    const float Y = (float)(ty * GSR_TILE);
+        // Slots of the column's (at most 8) tiles first — rank + start of the tile's bucket, or a ticket from the per-tile cursor for
+        // rectangles of > 8 tiles — so that up to 16 independent loads / atomics are in flight while the masks are computed.
+        const uint32_t* rk = p.ranks + 8 * (size_t)gid + col * gh + (ty_lo - gy0);  // column-major ranks of a <= 8-tile rectangle
+        uint32_t pos[8];
 #pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        if (v0 && ylo0 <= Y + (4.f * r + 3.f) && yhi0 >= Y + 4.f * r) mask |= 1u << (2 * r);
-                        if (v1 && ylo1 <= Y + (4.f * r + 3.f) && yhi1 >= Y + 4.f * r) mask |= 2u << (2 * r);
-                    }
+        for (int r = 0; r < 8; r++) {
+            pos[r] = 0xffffffffu;
+            const int ty = ty_lo + r;
+            if (ty < ty_hi) {
+                const int tile = ty * p.gx + tx;
+                if (!big) {
+                    const uint32_t rank = rk[r];
+                    const uint32_t start = p.ranges[tile].x;
+                    pos[r] = (TIGHT && rank == 0xffffffffu) ? 0xffffffffu : start + rank;
+                } else if (!TIGHT || tile_may_touch(gpx, gpy, own[12 * 32 + g], gb, own[13 * 32 + g], own[14 * 32 + g], tx, ty)) {
+                    // the tight-tile test is re-evaluated on the same stored values k_project used (bitwise same decision)
+                    pos[r] = atomicAdd(&p.tile_fill[tile], 1u);
                 }
             }
-            uint32_t pos;
-            if (!big) {
-                const uint32_t rank = rk[ty - gy0];
-                if (TIGHT && rank == 0xffffffffu) continue;
-                pos = p.ranges[tile].x + rank;
-            } else {
-                // > 8 tiles: position from the per-tile cursor initialised by k_tile_scan; the tight-tile test is re-evaluated on the
-                // same stored values k_project used (bitwise same decision)
-                if (TIGHT && !tile_may_touch(gpx, gpy, own[12 * 32 + g], gb, own[13 * 32 + g], own[14 * 32 + g], tx, ty)) continue;
-                pos = atomicAdd(&p.tile_fill[tile], 1u);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int ty = ty_lo + r;
+            if (ty < ty_hi && pos[r] != 0xffffffffu) {
+                uint32_t mask = 0;
+                if (PACKED) {
+                    if (!(fl & 1u)) mask = tile_foot_mask(gpx, gpy, own[12 * 32 + g], gb, own[13 * 32 + g], own[14 * 32 + g], tx, ty);
+                    else {
+                        const float Y = (float)(ty * GSR_TILE);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            if (v0 && ylo0 <= Y + (4.f * q + 3.f) && yhi0 >= Y + 4.f * q) mask |= 1u << (2 * q);
+                            if (v1 && ylo1 <= Y + (4.f * q + 3.f) && yhi1 >= Y + 4.f * q) mask |= 2u << (2 * q);
+                        }
+                    }
+                }
+                p.pairs[pos[r]] = make_uint2(lo_id | mask, dbits);  // little endian: u64 = depth bits << 32 | low word
             }
-            p.pairs[pos] = make_uint2(lo_id | mask, dbits);  // little endian: u64 = depth bits << 32 | low word
         }
     }
 }
@@ -1097,8 +1113,15 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
         return check_launch("gsr_forward/blend(reuse)", debug, st);
     }
 
-    cudaMemsetAsync(img, 0, il.zero_bytes(), st);
-    prof_mark(0, st);
+    // a frame can be issued in two calls — GSR_FLAG_BINNING_ONLY (projection + tile scan: the counters are final except for
+    // exact_redos) and GSR_FLAG_RESUME (everything after it) — so that a caller who validates the capacity on the host can
+    // start that round trip while the rest of the frame runs
+    const bool resume = (flags & GSR_FLAG_RESUME) != 0;
+    if ((flags & GSR_FLAG_BINNING_ONLY) && resume) { set_error("gsr_forward: GSR_FLAG_BINNING_ONLY and GSR_FLAG_RESUME are exclusive"); return GSR_ERR_INVALID; }
+    if (!resume) {
+        cudaMemsetAsync(img, 0, il.zero_bytes(), st);
+        prof_mark(0, st);
+    }
 
     PreParams pp;
     pp.P = f->P; pp.D = D; pp.M = f->M; pp.W = f->W; pp.H = f->H; pp.gx = il.gx; pp.gy = il.gy;
@@ -1116,22 +1139,24 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     pp.ranks = (uint32_t*)(geo + gl.ranks); pp.counters = counters;
 
     pp.vis_list = (uint32_t*)(geo + gl.vis_list);
-    {
+    uint2* ranges = (uint2*)(img + il.ranges);
+    int rc = GSR_OK;
+    if (!resume) {
         static int minb = -1;  // GSR_PROJ_MINB=8|10|12: resident CTAs per SM the kernel is compiled for (experiment knob)
         if (minb < 0) { const char* e = getenv("GSR_PROJ_MINB"); minb = e ? atoi(e) : 8; }
         const int grid = (f->P + PRE_THREADS - 1) / PRE_THREADS;
-        if (minb == 12) k_project<12><<<grid, PRE_THREADS, 0, st>>>(pp);
-        else if (minb == 10) k_project<10><<<grid, PRE_THREADS, 0, st>>>(pp);
-        else k_project<8><<<grid, PRE_THREADS, 0, st>>>(pp);
-    }
-    prof_mark(1, st);
-    int rc = check_launch("gsr_forward/project", debug, st);
-    if (rc) return rc;
+        if (pp.tight) k_project<8, true><<<grid, PRE_THREADS, 0, st>>>(pp);
+        else if (minb == 12) k_project<12, false><<<grid, PRE_THREADS, 0, st>>>(pp);
+        else if (minb == 10) k_project<10, false><<<grid, PRE_THREADS, 0, st>>>(pp);
+        else k_project<8, false><<<grid, PRE_THREADS, 0, st>>>(pp);
+        prof_mark(1, st);
+        if ((rc = check_launch("gsr_forward/project", debug, st))) return rc;
 
-    uint2* ranges = (uint2*)(img + il.ranges);
-    k_tile_scan<<<1, 1024, 0, st>>>(pp.tile_count, pp.tile_big, (uint32_t*)(img + il.tile_fill), ranges, counters, il.tiles, (uint32_t)(cap > 0xffffffffull ? 0xffffffffull : cap));
-    prof_mark(2, st);
-    if ((rc = check_launch("gsr_forward/tile_scan", debug, st))) return rc;
+        k_tile_scan<<<1, 1024, 0, st>>>(pp.tile_count, pp.tile_big, (uint32_t*)(img + il.tile_fill), ranges, counters, il.tiles, (uint32_t)(cap > 0xffffffffull ? 0xffffffffull : cap));
+        prof_mark(2, st);
+        if ((rc = check_launch("gsr_forward/tile_scan", debug, st))) return rc;
+    }
+    if (flags & GSR_FLAG_BINNING_ONLY) return GSR_OK;
 
     // footprint masks travel in the low byte of the pair's id word when the ids fit 24 bits; GSR_PACKED_KEYS=0 forces the
     // general path (masks computed by k_sort_tiles from gathered records), which is what P > 2^24 uses

@@ -163,6 +163,7 @@ class _DeviceState:
         self.cursor = 0
         self.cache: Dict[Tuple, torch.Tensor] = {}
         self.last_ticket: Optional[FrameTicket] = None
+        self.side_stream: Optional[torch.cuda.Stream] = None
         # geometry of the last full (non-autograd) forward per stream: (key, tensors kept alive, radii)
         self.geom_cache: Dict[int, Tuple] = {}
 
@@ -191,12 +192,24 @@ class _DeviceState:
         self.events[i] = ev
         return self.pinned[i], ev
 
-    def issue_ticket(self, counters: torch.Tensor, stream, capacity: int) -> "FrameTicket":
-        """Async copy of a frame's 32-byte counters into the next pinned ring slot + the event that says it has landed."""
+    def issue_ticket(self, counters: torch.Tensor, stream, capacity: int, early: bool = False) -> "FrameTicket":
+        """Async copy of a frame's 32-byte counters into the next pinned ring slot + the event that says it has landed.
+        ``early``: the copy runs on a side stream that only waits for what ``stream`` holds right now, so it neither waits for
+        nor delays the work enqueued on ``stream`` afterwards (the safe mode's capacity check between the two halves of a frame)."""
         i = self.cursor
         slot, ev = self.next_slot()
-        slot.copy_(counters, non_blocking=True)
-        ev.record(stream)
+        if early:
+            if self.side_stream is None:
+                self.side_stream = torch.cuda.Stream(self.device)
+            mark = torch.cuda.Event()
+            mark.record(stream)
+            self.side_stream.wait_event(mark)
+            with torch.cuda.stream(self.side_stream):
+                slot.copy_(counters, non_blocking=True)
+            ev.record(self.side_stream)
+        else:
+            slot.copy_(counters, non_blocking=True)
+            ev.record(stream)
         ticket = FrameTicket(ev, slot, capacity, self)
         self.tickets[i] = weakref.ref(ticket)
         self.last_ticket = ticket
@@ -372,14 +385,22 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, cov3
             ws = _lib.gsr_workspace(geom.data_ptr(), geom.numel(), binning.data_ptr(), binning.numel(), image.data_ptr(), image.numel())
             if extra is not None and P == 0:
                 extra_out.zero_()
-            rc = _L.gsr_forward_multi(C.byref(fr), C.byref(ws), color.data_ptr(), depth.data_ptr(), alpha.data_ptr(),
-                                      radii.data_ptr() if P > 0 else None, _ptr(extra) if P > 0 else None,
-                                      _ptr(extra_out) if extra is not None and P > 0 else None, flags, C.c_void_p(stream.cuda_stream))
-            _lib.check(rc, "gsr_forward")
-            ticket = st.issue_ticket(image[:32].view(torch.int32), stream, _L.gsr_binning_capacity(binning.numel()))
+            args = (C.byref(fr), C.byref(ws), color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), radii.data_ptr() if P > 0 else None,
+                    _ptr(extra) if P > 0 else None, _ptr(extra_out) if extra is not None and P > 0 else None)
+            cap_now = _L.gsr_binning_capacity(binning.numel())
+            if do_sync and P > 0 and not settings.debug:
+                # safe mode: the frame is issued in two halves; the counters are final after the first (projection + tile scan), so
+                # the host waits for THAT copy while colour / emission / sort / blend are already queued behind it
+                _lib.check(_L.gsr_forward_multi(*args, flags | _lib.GSR_FLAG_BINNING_ONLY, C.c_void_p(stream.cuda_stream)), "gsr_forward")
+                check = st.issue_ticket(image[:32].view(torch.int32), stream, cap_now, early=True)
+                _lib.check(_L.gsr_forward_multi(*args, flags | _lib.GSR_FLAG_RESUME, C.c_void_p(stream.cuda_stream)), "gsr_forward")
+                ticket = st.issue_ticket(image[:32].view(torch.int32), stream, cap_now)  # the frame's final counters (exact_redos)
+            else:
+                _lib.check(_L.gsr_forward_multi(*args, flags, C.c_void_p(stream.cuda_stream)), "gsr_forward")
+                check = ticket = st.issue_ticket(image[:32].view(torch.int32), stream, cap_now)
             if not do_sync:
                 break
-            s = ticket.stats()
+            s = check.stats()
             if s["trapped"]:
                 raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")  # auxiliary.h:158
             if not s["overflow"]:

@@ -66,6 +66,12 @@ enum {
                                   the approximation's error band is detected and that warp's pixels are re-blended exactly, so
                                   the images differ from the exact ones by ~1e-6 relative (requirement: 1e-4 max abs) and
                                   n_contrib / all integer outputs are unchanged. */
+    GSR_FLAG_BINNING_ONLY = 32, /* first half of a frame issued in two calls: projection + tile scan only.  Afterwards the counters
+                                  (num_rendered, overflow, max_tile, trapped, num_visible) are final, so a caller that validates the
+                                  binning capacity on the host (the reference blocks on the same number, rasterizer_impl.cu:281-282)
+                                  can start that copy now and let it overlap the rest of the frame. */
+    GSR_FLAG_RESUME = 64,       /* second half: same arguments and workspaces as the GSR_FLAG_BINNING_ONLY call; runs colour +
+                                  emission, the tile sort and the blend. */
 };
 
 /* One rasterizer invocation = the argument list of Rasterizer::forward (DGR/cuda_rasterizer/rasterizer.h:33-58). */

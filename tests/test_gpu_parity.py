@@ -202,6 +202,26 @@ def test_full_size_3m_1080p_properties_and_reference(dev, scene3m):
         assert 0 < o2["stats"]["exact_redos"] < 6000 and o3["stats"]["exact_redos"] == 0
 
 
+def test_full_size_3m_gradients_match_compiled_reference(dev, scene3m):
+    """Config 3's backward half at full size (3M Gaussians, 1080p): every gradient against the reference's own CUDA backward."""
+    if not _have_ref():
+        pytest.skip("oracle/_ref/libref_dgr.so not present")
+    from oracle import ref_cuda
+    g, cams = scene3m
+    for ci in (42, 171):
+        a = Hh.resolve(dict(g=g, cam=cams[ci], sh_degree=3, bg=(0.1, 0.2, 0.3), scale_modifier=1.0), dev)
+        dc, dd, da = Hh.image_grads(a, device=dev)
+        gr = ref_cuda.backward(Hh.run_ref(a), dc, dd, da)
+        outs, go = Hh.ours_backward(a, dc, dd, da)
+        for mine, theirs in (("means3D", "dL_dmeans3D"), ("means2D", "dL_dmeans2D"), ("opacities", "dL_dopacity"), ("shs", "dL_dsh"),
+                             ("scales", "dL_dscales"), ("rotations", "dL_drotations")):
+            assert Hh.relerr(go[mine].reshape(gr[theirs].shape), gr[theirs]) < 2e-4, (ci, mine)
+        # Gaussians the frame does not see get exactly zero, like the reference's zero-initialised outputs
+        unseen = outs[3] == 0
+        assert float(go["shs"][unseen].abs().max()) == 0.0 and float(go["means3D"][unseen].abs().max()) == 0.0
+        del gr, go
+
+
 def test_p_zero_returns_zero_images(dev):
     from autovfx_b200.rasterizer import GaussianRasterizer
     a = Hh.resolve(Hh.case_inputs("small_sh"), dev)
