@@ -66,7 +66,10 @@ struct BwdArgs {
 constexpr int BWL_WARPS = 4;
 constexpr float BWL_LOG2E = 1.4426950408889634f;
 struct BwlCfg {
-    static constexpr int REC = 32 * 48;        // staged records of one 32-survivor gather
+    // one gather of 32 survivors, two per 112-byte pair so that phase 1 runs both on the halves of packed fp32 registers:
+    // {x0,x1,y0,y1 | a0,a1,-b0,-b1 | c0,c1,o0,o1 | r0,r1,g0,g1 | b0,b1,depth0,depth1 | pos0,pos1,-,- | pad}, then the 32 ids
+    static constexpr int PAIRB = 112;
+    static constexpr int REC = 16 * PAIRB + 32 * 4;
     static constexpr int WROW = 66;            // words per (w, s) row: 32 pixels x 2, + 2 so that rows start 2 banks apart
     static constexpr int WS = 16 * WROW * 4;   // one 16-survivor batch
     static constexpr int DLP = 32 * 16;        // the footprint's loss gradients {dL/dC.rgb, dL/dDepth} per pixel
@@ -76,6 +79,11 @@ struct BwlCfg {
 
 __device__ __forceinline__ void sts64b(uint32_t a, float x, float y) {
     asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ float lds32b(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
 }
 __device__ __forceinline__ float2 lds64b(uint32_t a) {
     float2 v;
@@ -98,7 +106,7 @@ __global__ void __launch_bounds__(BWL_WARPS * 32, OCC) k_blend_backward(const Bw
     const bool inside = pxi < a.W && pyi < a.H;
     const float pixx = (float)pxi, pixy = (float)pyi;
     const uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(sm) + (uint32_t)warp * Cfg::WB;
-    const uint32_t ws_base = rec_base + Cfg::REC, dlp_base = ws_base + Cfg::WS;
+    const uint32_t id_base = rec_base + 16 * Cfg::PAIRB, ws_base = rec_base + Cfg::REC, dlp_base = ws_base + Cfg::WS;
     uint32_t* ring = reinterpret_cast<uint32_t*>(sm + (size_t)warp * Cfg::WB + Cfg::REC + Cfg::WS + Cfg::DLP);
 
     const uint2 rg = a.ranges[tile];
@@ -121,7 +129,8 @@ __global__ void __launch_bounds__(BWL_WARPS * 32, OCC) k_blend_backward(const Bw
     sts128b(dlp_base + (uint32_t)lane * 16, make_float4(dLp0, dLp1, dLp2, dLd));
     float T = T_final;
     const float tfbg = -T_final * (a.bg[0] * dLp0 + a.bg[1] * dLp1 + a.bg[2] * dLp2);  // -T_final (bg . dL/dC), backward.cu:566-572
-    float R = 0.f, D_last = 0.f, alpha_last = 0.f, om_last = 1.f;
+    float Rn = 0.f;  // the "behind" term of the recursion for the next splat that hits
+    const f32x2 npx2 = pk2(-pixx, -pixx), npy2 = pk2(-pixy, -pixy);
 
     const uint32_t* __restrict__ balcol = a.bal + bal_row_base(rg.x, tile) * GSR_FOOTS + f;
     const uint32_t* __restrict__ plist = a.point_list + rg.x;
@@ -189,16 +198,19 @@ __global__ void __launch_bounds__(BWL_WARPS * 32, OCC) k_blend_backward(const Bw
     const int j = lane & 15, h = lane >> 4;
     while (consumed < filled) {
         const int cnt = (int)min(32u, filled - consumed);
-        if (lane < cnt) {  // stage: {x, y, a, b | c, opacity, depth, position (1-based) | r, g, b, id}
-            const uint32_t sa = rec_base + (uint32_t)lane * 48;
-            sts128b(sa, ra);
-            sts128b(sa + 16, make_float4(rb.x, rb.y, rb.z, __uint_as_float(pos_c + 1u)));
-            sts128b(sa + 32, make_float4(rc.x, rc.y, rc.z, __uint_as_float(id_c)));
-        } else if (lane == cnt && (cnt & 1)) {  // completes the last pair of an odd batch: a splat behind every pixel's last contributor
-            const uint32_t sa = rec_base + (uint32_t)lane * 48;
-            sts128b(sa, make_float4(0.f, 0.f, 0.f, 0.f));
-            sts128b(sa + 16, make_float4(0.f, 0.f, 0.f, __uint_as_float(0xffffffffu)));
-            sts128b(sa + 32, make_float4(0.f, 0.f, 0.f, 0.f));
+        {
+            const uint32_t qa = rec_base + (uint32_t)(lane >> 1) * Cfg::PAIRB + (uint32_t)(lane & 1) * 4;
+            if (lane < cnt) {
+                sts32(qa, ra.x); sts32(qa + 8, ra.y); sts32(qa + 16, ra.z); sts32(qa + 24, -ra.w);
+                sts32(qa + 32, rb.x); sts32(qa + 40, rb.y);
+                sts32(qa + 48, rc.x); sts32(qa + 56, rc.y); sts32(qa + 64, rc.z); sts32(qa + 72, rb.z);
+                sts32(qa + 80, __uint_as_float(pos_c + 1u));  // 1-based position in the tile's list, compared with n_contrib
+                sts32(id_base + (uint32_t)lane * 4, __uint_as_float(id_c));
+            } else if (lane == cnt && (cnt & 1)) {  // completes the last pair of an odd batch: a splat behind every pixel's last contributor
+                sts32(qa, 0.f); sts32(qa + 8, 0.f); sts32(qa + 16, 0.f); sts32(qa + 24, 0.f); sts32(qa + 32, 0.f); sts32(qa + 40, 0.f);
+                sts32(qa + 48, 0.f); sts32(qa + 56, 0.f); sts32(qa + 64, 0.f); sts32(qa + 72, 0.f);
+                sts32(qa + 80, __uint_as_float(0xffffffffu));
+            }
         }
         consumed += (uint32_t)cnt;
         if (filled - consumed < 64u && (block_open || nblk < nblocks)) refill();
@@ -222,23 +234,8 @@ __global__ void __launch_bounds__(BWL_WARPS * 32, OCC) k_blend_backward(const Bw
             auto phase1 = [&](auto exact_tag) -> bool {
                 constexpr bool EXACT = decltype(exact_tag)::value;
                 bool near = false;
-                uint32_t qa = rec_base + (uint32_t)sub * 48, wa = ws_base + (uint32_t)lane * 8;
-                // everything of a splat that does not depend on the pixel's running state
-                auto front = [&](uint32_t q, float& G, float& alpha, bool& hit, float& D) {
-                    const float4 A = lds128b(q), B = lds128b(q + 16), Cc = lds128b(q + 32);
-                    const float dx = A.x - pixx, dy = A.y - pixy;
-                    // the forward's rounding sequence for `power` (gsr_blend.cu drain_exact): the decisions below replay the forward's
-                    const float t1 = __fmul_rn(B.x, dy), t3 = __fmul_rn(A.z, dx), t2 = __fmul_rn(-A.w, dx);
-                    const float t4 = __fmul_rn(dy, t1), t5 = __fmul_rn(dy, t2), t6 = __fmaf_rn(dx, t3, t4);
-                    const float power = __fmaf_rn(t6, -0.5f, t5);
-                    G = EXACT ? exp(power) : ex2_approx(power * BWL_LOG2E);
-                    const float oG = __fmul_rn(B.y, G);
-                    if (!EXACT) near |= fabsf(fmaf(oG, 255.0f, -1.0f)) < 8.0e-6f;
-                    alpha = min(0.99f, oG);
-                    hit = __float_as_uint(B.w) <= last_contributor && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-                    D = fmaf(Cc.x, dLp0, fmaf(Cc.y, dLp1, fmaf(Cc.z, dLp2, fmaf(B.z, dLd, dLa))));
-                };
-                // the recursion: T, R and the (w, s) pair of this (splat, pixel)
+                uint32_t qa = rec_base + (uint32_t)(sub >> 1) * Cfg::PAIRB, wa = ws_base + (uint32_t)lane * 8;
+                // the recursion: T, Rn and the (w, s) pair of this (splat, pixel)
                 auto step = [&](float G, float alpha, bool hit, float D, float& w, float& sv) {
                     const float a_eff = hit ? alpha : 0.0f;
                     const float om = 1.0f - a_eff;  // in [0.01, 1]: the approximate reciprocal (1 ulp, exact for 1) needs no special cases
@@ -246,20 +243,39 @@ __global__ void __launch_bounds__(BWL_WARPS * 32, OCC) k_blend_backward(const Bw
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(om));
                     T *= rcp;                       // transmittance in front of this splat
                     w = a_eff * T;
-                    const float Rn = fmaf(alpha_last, D_last, om_last * R);
-                    R = hit ? Rn : R;
                     const float dL_dalpha = fmaf(tfbg, rcp, (D - Rn) * T);
                     sv = hit ? G * dL_dalpha : 0.0f;
-                    alpha_last = hit ? alpha : alpha_last;
-                    om_last = hit ? om : om_last;
-                    D_last = hit ? D : D_last;
+                    Rn = hit ? fmaf(alpha, D, om * Rn) : Rn;
                     anyc |= hit;
                 };
-                for (int k = 0; k < c16; k += 2, qa += 96, wa += 2 * Cfg::WROW * 4) {  // two splats per iteration (an odd batch ends on a dummy)
-                    float G0, G1, al0, al1, D0, D1, w0, w1, s0, s1;
-                    bool h0, h1;
-                    front(qa, G0, al0, h0, D0);
-                    front(qa + 48, G1, al1, h1, D1);
+                const f32x2 mhalf2 = pk2(-0.5f, -0.5f), l2e2 = pk2(BWL_LOG2E, BWL_LOG2E);
+                const f32x2 g0 = pk2(dLp0, dLp0), g1 = pk2(dLp1, dLp1), g2 = pk2(dLp2, dLp2), gd2 = pk2(dLd, dLd), ga2 = pk2(dLa, dLa);
+                for (int k = 0; k < c16; k += 2, qa += Cfg::PAIRB, wa += 2 * Cfg::WROW * 4) {  // two splats per iteration (an odd batch ends on a dummy)
+                    const float4 L0 = lds128b(qa), L1 = lds128b(qa + 16), L2 = lds128b(qa + 32), L3 = lds128b(qa + 48), L4 = lds128b(qa + 64);
+                    const float2 P5 = lds64b(qa + 80);
+                    // everything that does not depend on the pixel's running state, both splats in the halves of packed registers.
+                    // `power` with the forward's rounding sequence (gsr_blend.cu): the decisions below replay the forward's
+                    const f32x2 dx = add2(pk2(L0.x, L0.y), npx2), dy = add2(pk2(L0.z, L0.w), npy2);
+                    const f32x2 t1 = mul2(pk2(L2.x, L2.y), dy), t3 = mul2(pk2(L1.x, L1.y), dx), t2 = mul2(pk2(L1.z, L1.w), dx);
+                    const f32x2 t4 = mul2(dy, t1), t5 = mul2(dy, t2), t6 = fma2(dx, t3, t4);
+                    const f32x2 pw = fma2(t6, mhalf2, t5);
+                    float p0, p1, G0, G1;
+                    upk2(pw, p0, p1);
+                    if (EXACT) { G0 = exp(p0); G1 = exp(p1); }
+                    else {
+                        float e0, e1;
+                        upk2(mul2(pw, l2e2), e0, e1);
+                        G0 = ex2_approx(e0); G1 = ex2_approx(e1);
+                    }
+                    float oG0, oG1;
+                    upk2(mul2(pk2(L2.z, L2.w), pk2(G0, G1)), oG0, oG1);
+                    if (!EXACT) near |= fabsf(fmaf(oG0, 255.0f, -1.0f)) < 8.0e-6f || fabsf(fmaf(oG1, 255.0f, -1.0f)) < 8.0e-6f;
+                    const float al0 = min(0.99f, oG0), al1 = min(0.99f, oG1);
+                    const bool h0 = __float_as_uint(P5.x) <= last_contributor && !(p0 > 0.0f) && !(al0 < 1.0f / 255.0f);
+                    const bool h1 = __float_as_uint(P5.y) <= last_contributor && !(p1 > 0.0f) && !(al1 < 1.0f / 255.0f);
+                    float D0, D1;
+                    upk2(fma2(pk2(L3.x, L3.y), g0, fma2(pk2(L3.z, L3.w), g1, fma2(pk2(L4.x, L4.y), g2, fma2(pk2(L4.z, L4.w), gd2, ga2)))), D0, D1);
+                    float w0, w1, s0, s1;
                     step(G0, al0, h0, D0, w0, s0);
                     step(G1, al1, h1, D1, w1, s1);
                     sts64b(wa, w0, s0);
@@ -268,9 +284,9 @@ __global__ void __launch_bounds__(BWL_WARPS * 32, OCC) k_blend_backward(const Bw
                 return near;
             };
             {
-                const float T0 = T, R0 = R, al0 = alpha_last, om0 = om_last, D0 = D_last;
+                const float T0 = T, R0 = Rn;
                 if (__any_sync(GSR_FULL, phase1(std::false_type()))) {
-                    T = T0; R = R0; alpha_last = al0; om_last = om0; D_last = D0;
+                    T = T0; Rn = R0;
                     anyc = false;
                     phase1(std::true_type());
                 }
@@ -286,11 +302,10 @@ __global__ void __launch_bounds__(BWL_WARPS * 32, OCC) k_blend_backward(const Bw
                 uint32_t gid = 0;
                 const bool mine = j < c16;
                 if (mine) {
-                    const uint32_t sa = rec_base + (uint32_t)(sub + j) * 48;
-                    const float4 A = lds128b(sa), B = lds128b(sa + 16);
-                    gid = __float_as_uint(lds128b(sa + 32).w);
-                    ca = A.z; cb = A.w; cc = B.x; op = B.y;
-                    const float dx0 = A.x - (float)X0, dy0 = A.y - (float)(Y0 + 2 * h);
+                    const uint32_t sa = rec_base + (uint32_t)((sub + j) >> 1) * Cfg::PAIRB + (uint32_t)((sub + j) & 1) * 4;
+                    gid = __float_as_uint(lds32b(id_base + (uint32_t)(sub + j) * 4));
+                    ca = lds32b(sa + 16); cb = -lds32b(sa + 24); cc = lds32b(sa + 32); op = lds32b(sa + 40);
+                    const float dx0 = lds32b(sa) - (float)X0, dy0 = lds32b(sa + 8) - (float)(Y0 + 2 * h);
                     const uint32_t wr = ws_base + (uint32_t)(j * Cfg::WROW + 32 * h) * 4, dr = dlp_base + (uint32_t)h * 256;
 #pragma unroll 1
                     for (int q = 0; q < 4; q++) {  // four pixels at a time: row q >> 1 of the half, columns 4 (q & 1) ..
