@@ -89,13 +89,21 @@ def broadcast_gaussians(g: Optional[Dict[str, torch.Tensor]], device, group=None
         return {k: v.to(device) for k, v in g.items()}
     rank = dist.get_rank(group)
     keys = ["means3D", "scales", "rotations", "opacities", "shs"]
-    meta = [None]
+    # shapes first, as one small tensor on the collective's own path (no pickling, no extra host round trips)
+    is_cuda = torch.device(device).type == "cuda"
+    meta = torch.zeros((len(keys), 4), dtype=torch.int64, device=device if is_cuda else "cpu")
     if rank == 0:
-        meta = [{k: tuple(g[k].shape) for k in keys}]
-    dist.broadcast_object_list(meta, src=0, group=group)
+        for i, k in enumerate(keys):
+            shp = tuple(g[k].shape)
+            meta[i, 0] = len(shp)
+            for j, n in enumerate(shp):
+                meta[i, 1 + j] = n
+    dist.broadcast(meta, src=0, group=group)
+    meta = meta.cpu().tolist()
     out = {}
-    for k in keys:
-        t = g[k].to(device).float().contiguous() if rank == 0 else torch.empty(meta[0][k], dtype=torch.float32, device=device)
+    for i, k in enumerate(keys):
+        shape = tuple(int(n) for n in meta[i][1:1 + int(meta[i][0])])
+        t = g[k].to(device).float().contiguous() if rank == 0 else torch.empty(shape, dtype=torch.float32, device=device)
         dist.broadcast(t, src=0, group=group)
         out[k] = t
     return out
