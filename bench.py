@@ -349,6 +349,7 @@ def main():
         dist.broadcast(warm, src=0)
         del warm
         RL.scatter_cameras(torch.zeros((world, RL.CAM_FLOATS)) if rank == 0 else None, world, dev)
+    torch.zeros((N_TRAJ, RL.CAM_FLOATS)).to(dev)  # first small pageable host -> device copy of the process (driver-side staging set-up), untimed
     barrier()
     t_b0 = time.perf_counter()
     g = RL.broadcast_gaussians(g0, dev) if use_dist else g0

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--tight", action="store_true")
     ap.add_argument("--backward", action="store_true", help="also time forward+backward through autograd (20 iterations)")
     ap.add_argument("--streams", type=int, default=1, help="issue consecutive frames round-robin on this many CUDA streams")
+    ap.add_argument("--prepared", action="store_true", help="issue frames through PreparedForward (a few microseconds of host time per frame)")
+    ap.add_argument("--depth", type=int, default=0, help="with --prepared: wait for the ticket of frame i - depth before issuing frame i (0: never wait)")
     ap.add_argument("--tag", default="")
     args = ap.parse_args()
     from autovfx_b200 import rasterizer as R, _lib
@@ -48,16 +50,35 @@ def main():
              torch.empty((P,), dtype=torch.int32, device=dev)) for _ in range(NS)]
     streams = [torch.cuda.current_stream(dev)] if NS == 1 else [torch.cuda.Stream(dev) for _ in range(NS)]
 
+    prepared = {}
+    issued = []
+
     def frame(i, sync):
+        if args.prepared and not sync:
+            ci = i % 300
+            with torch.cuda.stream(streams[i % NS]):
+                pf = prepared.get((ci, i % NS))
+                if pf is None:
+                    pf = prepared[(ci, i % NS)] = R.PreparedForward(g["means3D"], g["shs"], g["opacities"], g["scales"], g["rotations"], packed[ci], 1920, 1080, bg,
+                                                                    3, 1.0, outs[i % NS], tight=args.tight, exact=args.exact)
+                if args.depth > 0 and len(issued) >= args.depth:
+                    issued[-args.depth].event.synchronize()
+                t = pf.launch(float(host[ci, 35]), float(host[ci, 36]))
+                issued.append(t)
+                return (None,) * 5 + (t,)
         with torch.cuda.stream(streams[i % NS]):
             return R.forward_raw(g["means3D"], g["shs"], None, g["opacities"], g["scales"], g["rotations"], None, S[i], sync=sync, out=outs[i % NS],
                                  tight=args.tight, exact=args.exact)
     torch.cuda.synchronize()
     for i in range(K + 5):
         frame(i, True)
+    if args.prepared:
+        for i in range(K + 5):
+            frame(i, False)
     for i in range(5):
         frame(i, False)
     torch.cuda.synchronize()
+    del issued[:]
     _lib.check(_lib.lib.gsr_profile_begin_strided(K, 2), "profile")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if NS > 1:
