@@ -32,7 +32,7 @@ class gsr_workspace(C.Structure):
 class gsr_counters(C.Structure):
     _fields_ = [("num_rendered", C.c_uint32), ("overflow", C.c_uint32), ("max_tile", C.c_uint32), ("trapped", C.c_uint32),
                 ("num_visible", C.c_uint32), ("foot_total", C.c_uint32), ("exact_redos", C.c_uint32),
-                ("reserved", C.c_uint32 * 1)]
+                ("blend_next", C.c_uint32)]
 
 
 class gsr_grads(C.Structure):
@@ -62,7 +62,7 @@ ABI_VERSION = 3
 EXPORTS = ("gsr_abi_version", "gsr_last_error", "gsr_geom_bytes", "gsr_binning_bytes", "gsr_binning_capacity", "gsr_image_bytes",
            "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_dist2_bytes", "gsr_dist2", "gsr_get_views",
            "gsr_profile_begin", "gsr_profile_begin_strided", "gsr_profile_end", "gsr_forward_multi", "gsr_axis_normals", "gsr_normal_maps",
-           "gsr_pack_frame", "gsr_activate_gaussians")
+           "gsr_pack_frame", "gsr_activate_gaussians", "gsr_set_option")
 
 
 def _load() -> C.CDLL:
@@ -119,6 +119,8 @@ def _load() -> C.CDLL:
     lib.gsr_profile_begin.argtypes = [C.c_int]
     lib.gsr_profile_begin_strided.restype = C.c_int
     lib.gsr_profile_begin_strided.argtypes = [C.c_int, C.c_int]
+    lib.gsr_set_option.restype = C.c_int
+    lib.gsr_set_option.argtypes = [C.c_char_p, C.c_int]
     lib.gsr_profile_end.restype = C.c_int
     lib.gsr_profile_end.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
     return lib

@@ -1,5 +1,6 @@
 // gsr_b200 — extern "C" surface declared in include/gsr_b200.h.
 #include "gsr_common.cuh"
+#include <cstring>
 #include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: the ranges cost nothing unless a profiler is attached
 
 namespace {
@@ -26,6 +27,7 @@ int compose_impl(int N, int M, const float* xyz, const float* f_dc, const float*
 int dist2_impl(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t dist2_bytes(int P);
 int profile_begin(int max_frames, int stride);
+int set_blend_persist(int k);
 int profile_end(float* ms, int* frames);
 
 // checkFrustum (rasterizer_impl.cu:54-66): in_frustum() only tests view-space z (auxiliary.h:154)
@@ -111,6 +113,14 @@ int gsr_dist2(int32_t P, const float* points, float* mean_dists, void* workspace
 int gsr_profile_begin(int max_frames) { return gsr::profile_begin(max_frames, 1); }
 int gsr_profile_begin_strided(int max_frames, int stride) { return gsr::profile_begin(max_frames, stride); }
 int gsr_profile_end(float* ms_per_kernel, int* frames) { return gsr::profile_end(ms_per_kernel, frames); }
+
+int gsr_set_option(const char* name, int value) {
+    if (!name) { gsr::set_error("gsr_set_option: null name"); return GSR_ERR_INVALID; }
+    int rc = GSR_ERR_INVALID;
+    if (strcmp(name, "blend_persist") == 0) rc = gsr::set_blend_persist(value);
+    if (rc != GSR_OK) gsr::set_error("gsr_set_option: unknown option or bad value (%s = %d)", name, value);
+    return rc;
+}
 
 int gsr_get_views(const gsr_workspace* ws, int32_t P, int32_t W, int32_t H, gsr_views* out) {
     if (!ws || !out) { gsr::set_error("gsr_get_views: null argument"); return GSR_ERR_INVALID; }
