@@ -27,7 +27,7 @@ int compose_impl(int N, int M, const float* xyz, const float* f_dc, const float*
 int dist2_impl(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t dist2_bytes(int P);
 int profile_begin(int max_frames, int stride);
-int set_blend_persist(int k);
+int set_option(const char* name, int value);
 int profile_end(float* ms, int* frames);
 
 // checkFrustum (rasterizer_impl.cu:54-66): in_frustum() only tests view-space z (auxiliary.h:154)
@@ -116,8 +116,7 @@ int gsr_profile_end(float* ms_per_kernel, int* frames) { return gsr::profile_end
 
 int gsr_set_option(const char* name, int value) {
     if (!name) { gsr::set_error("gsr_set_option: null name"); return GSR_ERR_INVALID; }
-    int rc = GSR_ERR_INVALID;
-    if (strcmp(name, "blend_persist") == 0) rc = gsr::set_blend_persist(value);
+    const int rc = gsr::set_option(name, value);
     if (rc != GSR_OK) gsr::set_error("gsr_set_option: unknown option or bad value (%s = %d)", name, value);
     return rc;
 }

@@ -837,6 +837,112 @@ __device__ void sort_bucket(const unsigned long long* __restrict__ g, uint32_t n
     }
 }
 
+// ---- the same bucket sort for n <= SORT_SMALL: one pass over global memory -------------------------------------------------
+// The shared key array is split into two halves: the keys are read from global memory ONCE into the first half (the depth
+// range is reduced on the way), the tickets (bucket << 5 | slot) live in a 16-bit shared array instead of the output buffer, and
+// the scatter goes shared -> shared into the second half.  A bucket with more than SORT_BUCKET_MAX keys (slot saturates at 31)
+// sorts the first half with the generic network instead.  Returns the array that holds the sorted keys.
+constexpr int SORT_SMALL = SORT_CAP / 2;
+
+template <bool PACKED>
+__device__ unsigned long long* sort_bucket_small(const unsigned long long* __restrict__ g, uint32_t n, uint32_t* __restrict__ out,
+                                                 unsigned long long* __restrict__ gkeep, unsigned long long* s, uint32_t* hist, uint16_t* tk16) {
+    __shared__ uint32_t red_min[SORT_THREADS / 32], red_max[SORT_THREADS / 32], wsum[SORT_THREADS / 32];
+    __shared__ int fallback;
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t B = min((uint32_t)SORT_BUCKETS, max(32u, next_pow2(n)));
+    unsigned long long* A = s;
+    unsigned long long* Bf = s + SORT_SMALL;
+    uint32_t dmin = 0xffffffffu, dmax = 0u;
+#pragma unroll 4
+    for (uint32_t i = t; i < n; i += SORT_THREADS) {
+        const unsigned long long k = g[i];
+        A[i] = k;
+        const uint32_t d = (uint32_t)(k >> 32);
+        dmin = min(dmin, d);
+        dmax = max(dmax, d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dmin = min(dmin, __shfl_xor_sync(GSR_FULL, dmin, o));
+        dmax = max(dmax, __shfl_xor_sync(GSR_FULL, dmax, o));
+    }
+    if (lane == 0) { red_min[warp] = dmin; red_max[warp] = dmax; }
+    if (t == 0) fallback = 0;
+    for (uint32_t b = t; b <= B; b += SORT_THREADS) hist[b] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < SORT_THREADS / 32; w++) { dmin = min(dmin, red_min[w]); dmax = max(dmax, red_max[w]); }
+    const float zmin = __uint_as_float(dmin), zmax = __uint_as_float(dmax);  // positive floats: bit order == value order
+    const float scale = zmax > zmin ? (float)(B - 1) / (zmax - zmin) : 0.f;
+    bool over = false;
+    for (uint32_t i = t; i < n; i += SORT_THREADS) {
+        const float d = __uint_as_float((uint32_t)(A[i] >> 32));
+        const uint32_t b = min(B - 1, (uint32_t)((d - zmin) * scale));
+        const uint32_t slot = atomicAdd(&hist[b], 1u);
+        over |= slot >= (uint32_t)SORT_BUCKET_MAX;
+        tk16[i] = (uint16_t)((b << 5) | min(slot, 31u));
+    }
+    if (over) fallback = 1;
+    __syncthreads();
+    if (fallback) {  // block-uniform
+        sort_smem(A, n);  // ends with a barrier
+    } else {
+        {   // exclusive scan of hist[0..B) in place, hist[B] = n
+            const uint32_t per = B / SORT_THREADS > 0 ? B / SORT_THREADS : 1;  // B is a power of two >= 32
+            const uint32_t b0 = t * per;
+            uint32_t loc[SORT_BUCKETS / SORT_THREADS];
+            uint32_t sum = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < SORT_BUCKETS / SORT_THREADS; k++) {
+                loc[k] = 0;
+                if (k < per && b0 + k < B) { loc[k] = hist[b0 + k]; }
+                sum += loc[k];
+            }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t x = __shfl_up_sync(GSR_FULL, incl, o);
+                if (lane >= o) incl += x;
+            }
+            if (lane == 31) wsum[warp] = incl;
+            __syncthreads();
+            uint32_t base = incl - sum;
+#pragma unroll
+            for (int w = 0; w < SORT_THREADS / 32; w++) base += (w < (int)warp) ? wsum[w] : 0u;
+#pragma unroll
+            for (uint32_t k = 0; k < SORT_BUCKETS / SORT_THREADS; k++) {
+                if (k < per && b0 + k < B) { hist[b0 + k] = base; base += loc[k]; }
+            }
+            if (t == 0) hist[B] = n;
+        }
+        __syncthreads();
+        for (uint32_t i = t; i < n; i += SORT_THREADS) {
+            const uint32_t tk = tk16[i];
+            Bf[hist[tk >> 5] + (tk & 31u)] = A[i];
+        }
+        __syncthreads();
+        for (uint32_t b = t; b < B; b += SORT_THREADS) {  // order the few keys that share a bucket
+            const uint32_t lo = hist[b], c = hist[b + 1] - lo;
+            for (uint32_t i = 1; i < c; i++) {
+                const unsigned long long x = Bf[lo + i];
+                uint32_t j = i;
+                while (j > 0 && Bf[lo + j - 1] > x) { Bf[lo + j] = Bf[lo + j - 1]; j--; }
+                Bf[lo + j] = x;
+            }
+        }
+        __syncthreads();
+    }
+    unsigned long long* r = fallback ? A : Bf;
+    for (uint32_t i = t; i < n; i += SORT_THREADS) {
+        const unsigned long long x = r[i];
+        const uint32_t id = PACKED ? (uint32_t)x >> 8 : (uint32_t)x;  // PACKED: low word = id << 8 | footprint mask
+        out[i] = id;
+        if (gkeep) gkeep[i] = (x & 0xffffffff00000000ull) | id;
+    }
+    return r;
+}
+
 // ---- footprint ballot matrix ------------------------------------------------------------------------------------
 // After the sort every entry of the tile carries an 8-bit mask: which of the tile's eight 8x4-pixel warp footprints the splat
 // can touch (PACKED: the low byte of the key, computed by k_color_emit; otherwise the record is gathered and the mask computed
@@ -896,12 +1002,17 @@ __device__ void foot_ballots(const FootArgs& fa, const unsigned long long* keys,
 // s: SORT_CAP u64 of shared memory, hist: SORT_BUCKETS+1 u32.  Block-wide (SORT_THREADS threads), ends without a barrier.
 template <bool PACKED>
 __device__ void sort_tile(const uint2 rg, unsigned long long* __restrict__ pairs, uint32_t* __restrict__ point_list, int keep_pairs,
-                          unsigned long long* s, uint32_t* hist, const FootArgs& fa, int tile) {
+                          unsigned long long* s, uint32_t* hist, uint16_t* tk16, const FootArgs& fa, int tile) {
     const uint32_t n = rg.y - rg.x;
     const uint32_t tid = threadIdx.x;
     if (n == 0) return;
     unsigned long long* g = pairs + rg.x;
     uint32_t* out = point_list + rg.x;
+    if (n <= SORT_SMALL && tk16 != nullptr) {
+        const unsigned long long* r = sort_bucket_small<PACKED>(g, n, out, keep_pairs ? g : nullptr, s, hist, tk16);
+        foot_ballots<PACKED>(fa, r, n, rg.x, tile);  // r[] is only read after the sort's last barrier
+        return;
+    }
     if (n <= SORT_CAP) {
         sort_bucket<PACKED>(g, n, out, keep_pairs ? g : nullptr, s, hist);
         foot_ballots<PACKED>(fa, s, n, rg.x, tile);  // s[] still holds the sorted keys (only read after the sort's last barrier)
@@ -952,11 +1063,13 @@ __device__ void sort_tile(const uint2 rg, unsigned long long* __restrict__ pairs
 template <bool PACKED>
 __global__ void __launch_bounds__(SORT_THREADS, 5) k_sort_tiles(const uint2* __restrict__ ranges, unsigned long long* __restrict__ pairs,
                                                              uint32_t* __restrict__ point_list,
-                                                             const gsr_counters* __restrict__ counters, int keep_pairs, const FootArgs fa) {
+                                                             const gsr_counters* __restrict__ counters, int keep_pairs, const FootArgs fa,
+                                                             const int sort_small_enabled) {
     if (counters->overflow) return;  // set by k_tile_scan, before this kernel started
     __shared__ unsigned long long s[SORT_CAP];
     __shared__ uint32_t hist[SORT_BUCKETS + 1];
-    sort_tile<PACKED>(ranges[blockIdx.x], pairs, point_list, keep_pairs, s, hist, fa, (int)blockIdx.x);
+    __shared__ uint16_t tk16[SORT_SMALL];
+    sort_tile<PACKED>(ranges[blockIdx.x], pairs, point_list, keep_pairs, s, hist, sort_small_enabled ? tk16 : nullptr, fa, (int)blockIdx.x);
 }
 
 // =====================================================================================================
@@ -1052,6 +1165,18 @@ static void launch_color_emit(bool vec, bool win, bool tight, bool packed, const
 }
 
 static void launch_blend(const BlendArgs& a, cudaStream_t st) { launch_blend_lists(a, st); }
+
+// process-wide experiment / tuning options of the forward (gsr_set_option)
+struct ForwardOptions {
+    int sort_single_pass = 1;  // tiles of <= SORT_SMALL instances are read from global memory once (sort_bucket_small)
+};
+static ForwardOptions g_opt;
+int set_blend_persist(int k);
+int set_option(const char* name, int value) {
+    if (strcmp(name, "blend_persist") == 0) return set_blend_persist(value);
+    if (strcmp(name, "sort_single_pass") == 0) { g_opt.sort_single_pass = value ? 1 : 0; return GSR_OK; }
+    return GSR_ERR_INVALID;
+}
 
 int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, float* out_depth, float* out_alpha,
                  int32_t* radii, const float* extra_colors, float* out_extra, int flags, cudaStream_t st) {
@@ -1186,8 +1311,8 @@ int forward_impl(const gsr_frame* f, const gsr_workspace* ws, float* out_color, 
     const int keep_pairs = (flags & GSR_FLAG_SORTED_KEYS) ? 1 : 0;
     uint32_t* n_contrib = (flags & GSR_FLAG_FOR_BACKWARD) ? (uint32_t*)(img + il.n_contrib) : nullptr;
     FootArgs fa{pp.records, (uint32_t*)(bin + bl.bal), il.gx};
-    if (packed) k_sort_tiles<true><<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters, keep_pairs, fa);
-    else k_sort_tiles<false><<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters, keep_pairs, fa);
+    if (packed) k_sort_tiles<true><<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters, keep_pairs, fa, g_opt.sort_single_pass);
+    else k_sort_tiles<false><<<il.tiles, SORT_THREADS, 0, st>>>(ranges, (unsigned long long*)(bin + bl.pairs), (uint32_t*)(bin + bl.point_list), counters, keep_pairs, fa, g_opt.sort_single_pass);
     prof_mark(4, st);
     if ((rc = check_launch("gsr_forward/sort", debug, st))) return rc;
     BlendArgs ba{ranges, (const uint32_t*)(bin + bl.point_list), pp.records, extra_colors, f->W, f->H, il.gx, il.gy, f->bg,

@@ -244,7 +244,8 @@ int gsr_profile_end(float* ms_per_kernel, int* frames);
 /* Process-wide tuning options (not part of the reference's surface; defaults are what bench.py measures unless it says so):
  *   "blend_persist" = K   0: one CTA per half tile (default).  K in 1..16: the blend runs as a persistent kernel with K CTAs per SM
  *                         drawing work from gsr_counters.blend_next, so that it never holds more than 4 K warps of an SM and the
- *                         geometry kernels of the next frame, issued on another stream, run beside it. */
+ *                         geometry kernels of the next frame, issued on another stream, run beside it.
+ *   "sort_single_pass" = 0|1   1 (default): the per-tile sort reads a tile of <= 2048 instances from global memory once. */
 int gsr_set_option(const char* name, int value);
 
 const char* gsr_last_error(void);

@@ -1,11 +1,13 @@
-"""Developer experiment: does a blend that leaves part of every SM free let the next frame's geometry kernels run beside it?
+"""Developer A/B harness for the gsr_set_option knobs: one process, one scene, many configurations.
 
-    python tools/sweep_overlap.py --frames 120 --persist 0,7,6,5,4,3 --streams 1,2,3
+    python tools/sweep_options.py --frames 120 --configs "sort_single_pass=0;sort_single_pass=1;blend_persist=5" --streams 1,2
 
-One process, one scene (3M Gaussians, 1080p trajectory); for every (blend_persist, streams) pair the frames of the trajectory
-are issued through PreparedForward round-robin over the streams and timed with CUDA events (async issue, the same loop as
-bench.py's headline).  The first configuration's images are the reference for a bit-equality check of every other one (the
-persistent blend must not change a single bit).  Appends one JSON line per configuration to gpurun_out/sweep_overlap.jsonl."""
+One scene (3M Gaussians, 1080p trajectory); for every configuration (';'-separated, each a ','-separated list of name=value; options
+not named are reset to their defaults) and stream count the frames of the trajectory are issued through PreparedForward round-robin
+over the streams and timed with CUDA events (async issue, the same loop as bench.py's headline); with one stream the per-kernel
+times come from the events inside gsr_forward.  The first configuration's images are the reference for a bit-equality check of every
+other one.  Appends one JSON line per (configuration, streams) to gpurun_out/sweep_options.jsonl.  (The co-residency experiment of
+profiles/r02_experiments.md was: --configs "blend_persist=0;blend_persist=7;...;blend_persist=3" --streams 1,2,3.)"""
 import argparse
 import json
 import os
@@ -23,8 +25,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=120)
     ap.add_argument("--gaussians", type=int, default=3_000_000)
-    ap.add_argument("--persist", default="0,7,6,5,4,3")
-    ap.add_argument("--streams", default="1,2,3")
+    ap.add_argument("--configs", default="blend_persist=0;blend_persist=5")
+    ap.add_argument("--streams", default="1,2")
     ap.add_argument("--repeat", type=int, default=2)
     args = ap.parse_args()
     from autovfx_b200 import rasterizer as R, _lib, render_loop as RL
@@ -36,7 +38,15 @@ def main():
     bg = torch.zeros(3, device=dev)
     P = g["means3D"].shape[0]
     K = args.frames
-    persists = [int(x) for x in args.persist.split(",")]
+    DEFAULTS = {"blend_persist": 0, "sort_single_pass": 1}
+    configs = []
+    for c in args.configs.split(";"):
+        d = dict(DEFAULTS)
+        for kv in c.split(","):
+            if kv.strip():
+                k_, v_ = kv.split("=")
+                d[k_.strip()] = int(v_)
+        configs.append((c, d))
     nstreams = [int(x) for x in args.streams.split(",")]
     NSMAX = max(nstreams)
     outs = [(torch.empty((3, 1080, 1920), device=dev), torch.empty((1, 1080, 1920), device=dev), torch.empty((1, 1080, 1920), device=dev),
@@ -65,8 +75,12 @@ def main():
     ref_img = None
     results = []
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    for pk in persists:
-        _lib.check(_lib.lib.gsr_set_option(b"blend_persist", pk), "set_option")
+    import ctypes as C
+    for cname, cfg in configs:
+        for k_, v_ in cfg.items():
+            rc = _lib.lib.gsr_set_option(k_.encode(), v_)
+            if rc != 0 and k_ in cname:
+                raise RuntimeError("unknown option %s" % k_)
         # correctness: frame 7 on stream 0 against the first configuration's frame
         t = launch(7, 1)
         torch.cuda.synchronize()
@@ -77,7 +91,10 @@ def main():
         same = bool(torch.equal(img, ref_img))
         for NS in nstreams:
             best = None
+            kms = None
             for rep in range(args.repeat):
+                if NS == 1:
+                    _lib.check(_lib.lib.gsr_profile_begin_strided(K, 2), "profile")
                 for i in range(8):
                     launch(i, NS)
                 torch.cuda.synchronize()
@@ -94,16 +111,22 @@ def main():
                 e1.record(cur)
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / K
+                if NS == 1:
+                    ms_k, nfr = (C.c_float * 5)(), C.c_int(0)
+                    _lib.check(_lib.lib.gsr_profile_end(ms_k, C.byref(nfr)), "profile_end")
+                    if best is None or ms < best:
+                        kms = {k_: round(float(ms_k[i_]), 4) for i_, k_ in enumerate(["project", "tile_scan", "color_emit", "sort_tiles", "blend"])}
                 ovf = sum(t_.stats()["overflow"] for t_ in tk)
                 best = ms if best is None else min(best, ms)
-            res = {"blend_persist": pk, "streams": NS, "ms_per_frame": round(best, 4), "fps": round(1000.0 / best, 1), "bit_equal": same,
+            res = {"config": cname, "streams": NS, "kernel_ms": kms, "ms_per_frame": round(best, 4), "fps": round(1000.0 / best, 1), "bit_equal": same,
                    "overflow": ovf, "redos7": st7["exact_redos"]}
             results.append(res)
             line = json.dumps(res)
             print(line, flush=True)
-            with open(os.path.join(ROOT, "gpurun_out", "sweep_overlap.jsonl"), "a") as f:
+            with open(os.path.join(ROOT, "gpurun_out", "sweep_options.jsonl"), "a") as f:
                 f.write(line + "\n")
-    _lib.lib.gsr_set_option(b"blend_persist", 0)
+    for k_, v_ in DEFAULTS.items():
+        _lib.lib.gsr_set_option(k_.encode(), v_)
 
 
 if __name__ == "__main__":
