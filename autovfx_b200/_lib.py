@@ -57,7 +57,7 @@ GSR_FLAG_REUSE_GEOMETRY = 8
 GSR_FLAG_EXACT_IMAGES = 16
 GSR_FLAG_BINNING_ONLY = 32
 GSR_FLAG_RESUME = 64
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTS = ("gsr_abi_version", "gsr_last_error", "gsr_geom_bytes", "gsr_binning_bytes", "gsr_binning_capacity", "gsr_image_bytes",
            "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_dist2_bytes", "gsr_dist2", "gsr_get_views",

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GSR_ABI_VERSION 3
+#define GSR_ABI_VERSION 4
 
 enum {
     GSR_OK = 0,

@@ -29,7 +29,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(_lib.lib, n), n
     assert set(names) == set(_lib.EXPORTS)
-    assert _lib.lib.gsr_abi_version() == _lib.ABI_VERSION == 3
+    assert _lib.lib.gsr_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_set_option_validates_names_and_values():
