@@ -413,16 +413,35 @@ __global__ void __launch_bounds__(PRE_THREADS, MINB) k_project(const PreParams p
 __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_big,
                                                     uint32_t* __restrict__ tile_fill, uint2* __restrict__ ranges,
                                                     gsr_counters* counters, int tiles, uint32_t capacity) {
+    // Every thread owns SCAN_PER consecutive tiles (16-byte loads and stores; the arrays are 256-byte aligned), so a 1080p frame
+    // (8,160 tiles) is one pass with two barriers instead of eight chunks of 1024 tiles with three barriers each.
+    constexpr int SCAN_PER = 8;
     __shared__ uint32_t warp_sum[32];
     __shared__ uint32_t warp_max[32];
     __shared__ uint32_t chunk_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t carry = 0, lmax = 0;
-    for (int base = 0; base < tiles; base += 1024) {  // chunks of 1024 consecutive tiles: coalesced loads and stores
-        const int t = base + tid;
-        const uint32_t cs = t < tiles ? tile_count[t] : 0u, c = cs + (t < tiles ? tile_big[t] : 0u);
-        lmax = max(lmax, c);
-        uint32_t incl = c;
+    for (int base = 0; base < tiles; base += 1024 * SCAN_PER) {
+        const int t0 = base + tid * SCAN_PER;
+        uint32_t cs[SCAN_PER], c[SCAN_PER];
+        if (t0 + SCAN_PER <= tiles) {
+            const uint4 a0 = *reinterpret_cast<const uint4*>(tile_count + t0), a1 = *reinterpret_cast<const uint4*>(tile_count + t0 + 4);
+            const uint4 b0 = *reinterpret_cast<const uint4*>(tile_big + t0), b1 = *reinterpret_cast<const uint4*>(tile_big + t0 + 4);
+            cs[0] = a0.x; cs[1] = a0.y; cs[2] = a0.z; cs[3] = a0.w; cs[4] = a1.x; cs[5] = a1.y; cs[6] = a1.z; cs[7] = a1.w;
+            c[0] = a0.x + b0.x; c[1] = a0.y + b0.y; c[2] = a0.z + b0.z; c[3] = a0.w + b0.w;
+            c[4] = a1.x + b1.x; c[5] = a1.y + b1.y; c[6] = a1.z + b1.z; c[7] = a1.w + b1.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_PER; k++) {
+                const int t = t0 + k;
+                cs[k] = t < tiles ? tile_count[t] : 0u;
+                c[k] = cs[k] + (t < tiles ? tile_big[t] : 0u);
+            }
+        }
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_PER; k++) { sum += c[k]; lmax = max(lmax, c[k]); }
+        uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t v = __shfl_up_sync(GSR_FULL, incl, o);
@@ -442,22 +461,33 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* __restrict__
             if (lane == 31) chunk_total = si;
         }
         __syncthreads();
-        const uint32_t start = carry + warp_sum[warp] + (incl - c);
-        if (t < tiles) {
-            ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
-            tile_fill[t] = start + cs;  // absolute cursor of the tile's un-ranked (large-rectangle) instances
+        uint32_t start = carry + warp_sum[warp] + (incl - sum);
+        uint2 rg[SCAN_PER];
+        uint32_t fill[SCAN_PER];
+#pragma unroll
+        for (int k = 0; k < SCAN_PER; k++) {
+            rg[k] = c[k] ? make_uint2(start, start + c[k]) : make_uint2(0u, 0u);
+            fill[k] = start + cs[k];  // absolute cursor of the tile's un-ranked (large-rectangle) instances
+            start += c[k];
+        }
+        if (t0 + SCAN_PER <= tiles) {
+#pragma unroll
+            for (int k = 0; k < SCAN_PER; k += 2) reinterpret_cast<uint4*>(ranges + t0)[k >> 1] = make_uint4(rg[k].x, rg[k].y, rg[k + 1].x, rg[k + 1].y);
+            reinterpret_cast<uint4*>(tile_fill + t0)[0] = make_uint4(fill[0], fill[1], fill[2], fill[3]);
+            reinterpret_cast<uint4*>(tile_fill + t0)[1] = make_uint4(fill[4], fill[5], fill[6], fill[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_PER; k++)
+                if (t0 + k < tiles) { ranges[t0 + k] = rg[k]; tile_fill[t0 + k] = fill[k]; }
         }
         carry += chunk_total;
         __syncthreads();
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lmax = max(lmax, __shfl_xor_sync(GSR_FULL, lmax, o));
+    lmax = __reduce_max_sync(GSR_FULL, lmax);
     if (lane == 0) warp_max[warp] = lmax;
     __syncthreads();
     if (warp == 0) {
-        uint32_t m = warp_max[lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(GSR_FULL, m, o));
+        const uint32_t m = __reduce_max_sync(GSR_FULL, warp_max[lane]);
         if (lane == 0) {
             counters->num_rendered = carry;
             counters->overflow = carry > capacity ? 1u : 0u;
@@ -870,11 +900,8 @@ __device__ void sort_bucket_small(const unsigned long long* __restrict__ g, uint
         dmin = min(dmin, d);
         dmax = max(dmax, d);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        dmin = min(dmin, __shfl_xor_sync(GSR_FULL, dmin, o));
-        dmax = max(dmax, __shfl_xor_sync(GSR_FULL, dmax, o));
-    }
+    dmin = __reduce_min_sync(GSR_FULL, dmin);  // REDUX: one instruction per warp-wide reduction
+    dmax = __reduce_max_sync(GSR_FULL, dmax);
     if (lane == 0) { red_min[warp] = dmin; red_max[warp] = dmax; }
     if (t == 0) fallback = 0;
     for (uint32_t b = t; b <= B; b += SORT_THREADS) hist[b] = 0;
