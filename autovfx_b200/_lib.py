@@ -128,6 +128,12 @@ def _load() -> C.CDLL:
 
 lib = _load()
 
+# GSR_OPTIONS="name=value,name=value": gsr_set_option calls at import (experiment harnesses; every setting renders the same bits)
+for _kv in filter(None, os.environ.get("GSR_OPTIONS", "").split(",")):
+    _k, _v = _kv.split("=")
+    if lib.gsr_set_option(_k.strip().encode(), int(_v)) != 0:
+        raise ImportError("autovfx_b200: bad GSR_OPTIONS entry %r" % _kv)
+
 
 def check(rc: int, what: str) -> None:
     if rc != 0:

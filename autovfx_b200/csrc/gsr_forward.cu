@@ -874,8 +874,8 @@ __device__ __forceinline__ uint32_t* foot_bal_rows(const FootArgs& fa, uint32_t 
 
 // ---- the same bucket sort for n <= SORT_SMALL: one pass over global memory -------------------------------------------------
 // The shared key array is split into two halves: the keys are read from global memory ONCE into the first half (the depth
-// range is reduced on the way), the tickets (bucket << 5 | slot) live in a 16-bit shared array instead of the output buffer, and
-// the scatter goes shared -> shared into the second half.  A bucket with more than SORT_BUCKET_MAX keys (slot saturates at 31)
+// range is reduced on the way), the tickets (bucket << 6 | slot) live in a 16-bit shared array instead of the output buffer, and
+// the scatter goes shared -> shared into the second half.  A bucket with more than 63 keys (the ticket's slot field saturates)
 // sorts the first half with the generic network instead.  The ids go to point_list and (PACKED) the footprint masks of 32
 // consecutive sorted entries to one row of the ballot matrix in the same pass over the sorted keys.
 constexpr int SORT_SMALL = SORT_CAP / 2;
@@ -887,8 +887,11 @@ __device__ void sort_bucket_small(const unsigned long long* __restrict__ g, uint
     __shared__ uint32_t red_min[SORT_THREADS / 32], red_max[SORT_THREADS / 32], wsum[SORT_THREADS / 32];
     __shared__ int fallback;
     const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    // n/2 .. n buckets (1 - 2 keys each): half the histogram / scan work of one bucket per key, measured 3 % faster; 4x fewer: slower
-    const uint32_t B = min((uint32_t)SORT_BUCKETS, max(32u, next_pow2(n) >> 1));
+    // n/2 .. n buckets (1 - 2 keys each): half the histogram / scan work of one bucket per key, measured 3 % faster; 4x fewer: slower.
+    // B <= 1024 (n <= SORT_SMALL): a ticket is bucket (10 bits) | slot (6 bits), so a bucket may hold up to 63 keys before the
+    // tile falls back to the generic network (depth outliers that stretch the tile's range crowd the other keys into few buckets)
+    const uint32_t B = min((uint32_t)SORT_BUCKETS / 2, max(32u, next_pow2(n) >> 1));
+    constexpr uint32_t SLOT_BITS = 6u, SLOT_MAX = (1u << SLOT_BITS) - 1u;
     unsigned long long* A = s;
     unsigned long long* Bf = s + SORT_SMALL;
     uint32_t dmin = 0xffffffffu, dmax = 0u;
@@ -915,8 +918,8 @@ __device__ void sort_bucket_small(const unsigned long long* __restrict__ g, uint
         const float d = __uint_as_float((uint32_t)(A[i] >> 32));
         const uint32_t b = min(B - 1, (uint32_t)((d - zmin) * scale));
         const uint32_t slot = atomicAdd(&hist[b], 1u);
-        over |= slot >= (uint32_t)SORT_BUCKET_MAX;
-        tk16[i] = (uint16_t)((b << 5) | min(slot, 31u));
+        over |= slot >= SLOT_MAX;
+        tk16[i] = (uint16_t)((b << SLOT_BITS) | min(slot, SLOT_MAX));
     }
     if (over) fallback = 1;
     __syncthreads();
@@ -954,7 +957,7 @@ __device__ void sort_bucket_small(const unsigned long long* __restrict__ g, uint
         __syncthreads();
         for (uint32_t i = t; i < n; i += SORT_THREADS) {
             const uint32_t tk = tk16[i];
-            Bf[hist[tk >> 5] + (tk & 31u)] = A[i];
+            Bf[hist[tk >> SLOT_BITS] + (tk & SLOT_MAX)] = A[i];
         }
         __syncthreads();
         // Final order, one thread per KEY (balanced, no divergent insertion loops): a key's place inside its bucket is the number
