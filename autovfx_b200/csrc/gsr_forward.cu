@@ -679,6 +679,17 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_color_emit(const EmitParams 
             v0 = strip_rows(c2, (float)(tx * GSR_TILE), 8.f, ylo0, yhi0);
             v1 = strip_rows(c2, (float)(tx * GSR_TILE + 8), 8.f, ylo1, yhi1);
         }
+        // The rows [ylo, yhi] a strip covers, as a bit mask over the (at most 32) 4-row bands of this column chunk: band k = rows
+        // [Y0 + 4k, Y0 + 4k + 3] is touched iff ylo <= Y0 + 4k + 3 and yhi >= Y0 + 4k, i.e. ceil((ylo - Y0 - 3) / 4) <= k <= floor((yhi - Y0) / 4).
+        // Two conversions per strip instead of eight comparisons per tile; near a band boundary the subtractions are exact (Y0 is an
+        // integer within a factor two of y), and the strips carry a 0.01-pixel margin anyway.
+        const float Y0 = (float)(ty_lo * GSR_TILE);
+        auto band_bits = [&](const bool v, const float ylo, const float yhi) -> uint32_t {
+            const float a = fminf(fmaxf((ylo - Y0 - 3.f) * 0.25f, -1.f), 33.f), b = fminf(fmaxf((yhi - Y0) * 0.25f, -1.f), 33.f);
+            const int klo = max((int)ceilf(a), 0), khi = min((int)floorf(b), 31);
+            return (v && klo <= khi) ? (0xffffffffu >> (31 - khi)) & (0xffffffffu << klo) : 0u;
+        };
+        const uint32_t bands0 = band_bits(v0, ylo0, yhi0), bands1 = band_bits(v1, ylo1, yhi1);
         // Slots of the column's (at most 8) tiles first — rank + start of the tile's bucket, or a ticket from the per-tile cursor for
         // rectangles of > 8 tiles — so that up to 16 independent loads / atomics are in flight while the masks are computed.
         const uint32_t* rk = p.ranks + 8 * (size_t)gid + col * gh + (ty_lo - gy0);  // column-major ranks of a <= 8-tile rectangle
@@ -706,13 +717,11 @@ __global__ void __launch_bounds__(PRE_THREADS, 8) k_color_emit(const EmitParams 
                 uint32_t mask = 0;
                 if (PACKED) {
                     if (!(fl & 1u)) mask = tile_foot_mask(gpx, gpy, own[12 * 32 + g], gb, own[13 * 32 + g], own[14 * 32 + g], tx, ty);
-                    else {
-                        const float Y = (float)(ty * GSR_TILE);
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            if (v0 && ylo0 <= Y + (4.f * q + 3.f) && yhi0 >= Y + 4.f * q) mask |= 1u << (2 * q);
-                            if (v1 && ylo1 <= Y + (4.f * q + 3.f) && yhi1 >= Y + 4.f * q) mask |= 2u << (2 * q);
-                        }
+                    else {  // the tile's four bands of both strips, interleaved: bit 2q + i = band q of strip i
+                        uint32_t n0 = (bands0 >> (4 * r)) & 15u, n1 = (bands1 >> (4 * r)) & 15u;
+                        n0 = (n0 | (n0 << 2)) & 0x33u; n0 = (n0 | (n0 << 1)) & 0x55u;
+                        n1 = (n1 | (n1 << 2)) & 0x33u; n1 = (n1 | (n1 << 1)) & 0x55u;
+                        mask = n0 | (n1 << 1);
                     }
                 }
                 p.pairs[pos[r]] = make_uint2(lo_id | mask, dbits);  // little endian: u64 = depth bits << 32 | low word
