@@ -876,6 +876,12 @@ __device__ void sort_bucket(const unsigned long long* __restrict__ g, uint32_t n
     }
 }
 
+// bucket of a depth (bit pattern of a positive float): monotone, and pinned to one subtraction and one multiplication so that every
+// evaluation for the same key yields the same bucket (sort_bucket_small evaluates it twice per key)
+__device__ __forceinline__ uint32_t depth_bucket(uint32_t dbits, float zmin, float scale, uint32_t B) {
+    return min(B - 1, (uint32_t)__fmul_rn(__fsub_rn(__uint_as_float(dbits), zmin), scale));
+}
+
 struct FootArgs;  // defined with the ballot matrix below
 template <bool PACKED>
 __device__ void foot_ballots(const FootArgs& fa, const unsigned long long* keys, uint32_t n, uint32_t range_x, int tile);
@@ -924,8 +930,7 @@ __device__ void sort_bucket_small(const unsigned long long* __restrict__ g, uint
     const float scale = zmax > zmin ? (float)(B - 1) / (zmax - zmin) : 0.f;
     bool over = false;
     for (uint32_t i = t; i < n; i += SORT_THREADS) {
-        const float d = __uint_as_float((uint32_t)(A[i] >> 32));
-        const uint32_t b = min(B - 1, (uint32_t)((d - zmin) * scale));
+        const uint32_t b = depth_bucket((uint32_t)(A[i] >> 32), zmin, scale, B);
         const uint32_t slot = atomicAdd(&hist[b], 1u);
         over |= slot >= SLOT_MAX;
         tk16[i] = (uint16_t)((b << SLOT_BITS) | min(slot, SLOT_MAX));
@@ -971,10 +976,9 @@ __device__ void sort_bucket_small(const unsigned long long* __restrict__ g, uint
         __syncthreads();
         // Final order, one thread per KEY (balanced, no divergent insertion loops): a key's place inside its bucket is the number
         // of smaller keys in it (the keys are distinct: the id is part of them); bucket order -> sorted order, second half -> first.
-        for (uint32_t i = t; i < n; i += SORT_THREADS) {
+        for (uint32_t i = t; i < n; i += SORT_THREADS) {  // in bucket order: neighbouring threads read neighbouring buckets
             const unsigned long long k = Bf[i];
-            const float d = __uint_as_float((uint32_t)(k >> 32));
-            const uint32_t b = min(B - 1, (uint32_t)((d - zmin) * scale));  // the same expression as above: the same bucket
+            const uint32_t b = depth_bucket((uint32_t)(k >> 32), zmin, scale, B);  // the very same roundings as the ticket pass
             const uint32_t lo = hist[b], c = hist[b + 1] - lo;
             uint32_t rank = 0;
             for (uint32_t j = 0; j < c; j++) rank += Bf[lo + j] < k ? 1u : 0u;
