@@ -347,9 +347,11 @@ __global__ void __launch_bounds__(WARPS * 32, OCC / WARPS) k_blend_lists(const B
     blend_item<NX, NC, EXACT, WARPS>(a, (int)blockIdx.x, (int)blockIdx.y, sq);
 }
 
-// Persistent variant (gsr_set_option("blend_persist", K)): K CTAs per SM draw work items from counters->blend_next, so the
-// kernel never occupies more than K * WARPS warps of an SM and kernels of the NEXT frame, issued on another stream, co-reside
-// with it (the geometry kernels are latency-bound, the blend is bound by the shared-memory pipe: profiles/r02_experiments.md).
+// Persistent variant (gsr_set_option("blend_persist", K), off by default): K CTAs per SM draw work items from
+// counters->blend_next, so the kernel never holds more than K * WARPS warps of an SM and kernels of the NEXT frame, issued on
+// another stream, can co-reside with it.  Measured (profiles/r02_experiments.md, r02_sweep_overlap.jsonl): with 2 - 3 streams
+// the frame time is the same within 2 % for K = 3 ... 8 — every kernel of the frame loads the LSU pipe, co-residency only trades
+// slots — so this stays an experiment knob; it renders the same bits (tests/test_gpu_options.py).
 template <int NX, bool NC, bool EXACT, int WARPS, int OCC>
 __global__ void __launch_bounds__(WARPS * 32, OCC / WARPS) k_blend_lists_persistent(const BlendArgs a) {
     __shared__ __align__(16) unsigned char sq[WARPS * ListCfg<NX>::WB];
